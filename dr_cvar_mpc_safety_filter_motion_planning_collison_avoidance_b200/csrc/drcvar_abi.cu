@@ -1,0 +1,504 @@
+// drcvar_abi.cu — host side of libdrcvar.so: argument checks, launch planning, host<->device staging.
+// The C ABI is declared in include/drcvar.h (each entry cites the reference interface it replaces).
+#include "../../include/drcvar.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "halfspace_kernel.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return fail(DRCVAR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                  __LINE__);                                                                        \
+  } while (0)
+
+// ---- tail size (mirrors oracle/closed_form.py:tail_count) -------------------------------------------------
+bool tail_count(double alpha, long long n, double* k_f_out, long long* kc_out) {
+  if (!(alpha > 0.0) || !(alpha <= 1.0) || n < 1) return false;
+  double k_f = alpha * static_cast<double>(n);
+  const double kr = std::nearbyint(k_f);
+  if (std::fabs(k_f - kr) <= 1e-9 * std::max(1.0, kr)) k_f = kr;
+  if (k_f > static_cast<double>(n)) k_f = static_cast<double>(n);
+  long long kc = static_cast<long long>(std::ceil(k_f));
+  kc = std::min(std::max(kc, 1LL), n);
+  *k_f_out = k_f;
+  *kc_out = kc;
+  return true;
+}
+
+// ---- inverse normal CDF (Acklam's rational approximation, |rel err| < 1.2e-9): speed heuristic only ---------
+double inv_norm_cdf(double p) {
+  static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                             1.383577518672690e+02,  -3.066479806614716e+01, 2.506628277459239e+00};
+  static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                             6.680131188771972e+01,  -1.328068155288572e+01};
+  static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                             -2.549732539343734e+00, 4.374664141464968e+00,  2.938163982698783e+00};
+  static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                             3.754408661907416e+00};
+  const double plow = 0.02425, phigh = 1 - plow;
+  if (p < plow) {
+    const double q = std::sqrt(-2 * std::log(p));
+    return (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+           ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+  }
+  if (p > phigh) {
+    const double q = std::sqrt(-2 * std::log(1 - p));
+    return -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+           ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+  }
+  const double q = p - 0.5, r = q * q;
+  return (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+         (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1);
+}
+
+// Candidate window [z_lo, z_hi] (in loss-sigma units around the loss mean) expected to bracket the kc-th
+// largest loss.  Purely a speed heuristic: a miss is detected on the device and the general select runs.
+bool plan_window(long long n, long long kc, double* z_lo, double* z_hi) {
+  const double p = static_cast<double>(kc) / static_cast<double>(n);  // upper-tail fraction
+  if (n < 1024 || kc < 16 || n - kc < 16 || p < 1e-3 || p > 0.999) return false;
+  const double z = inv_norm_cdf(1.0 - p);
+  const double phi = std::exp(-0.5 * z * z) / std::sqrt(2.0 * M_PI);
+  const double sq = std::sqrt(p * (1.0 - p) / static_cast<double>(n)) / phi;  // std of the sample quantile
+  const double w = 6.0 * sq + 0.03 + 0.02 * std::fabs(z);
+  const double expect = static_cast<double>(n) * 2.0 * w * phi;
+  if (expect > 0.25 * drcvar::kCandCap * drcvar::kThreads) return false;
+  *z_lo = z - w;
+  *z_hi = z + w;
+  return true;
+}
+
+struct DeviceInfo {
+  bool ready = false;
+  int sms = 0;
+  int max_smem_optin = 0;
+};
+DeviceInfo g_dev[64];
+std::mutex g_dev_mu;
+
+int device_info(int device, DeviceInfo** out) {
+  if (device < 0 || device >= 64) return fail(DRCVAR_ERR_INVALID, "device index %d out of range", device);
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DeviceInfo& d = g_dev[device];
+  if (!d.ready) {
+    CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    d.ready = true;
+  }
+  *out = &d;
+  return DRCVAR_OK;
+}
+
+struct Call {
+  const void* samples;
+  long long B, N, stride_b, stride_n, stride_c;
+  const double* ego;
+  const double* h_in;
+  double alpha, delta, epsilon, r_robot, r_obs;
+  uint32_t flags;
+  double *h_out, *h_mean_out, *g_out, *cvar_out, *var_out, *gstar_out;
+  int32_t* status_out;
+  int32_t* tail_idx_out;
+};
+
+template <typename T>
+int launch_on_device(const Call& c, int device, cudaStream_t stream) {
+  using namespace drcvar;
+  DeviceInfo* di = nullptr;
+  int rc = device_info(device, &di);
+  if (rc) return rc;
+  double k_f;
+  long long kc;
+  if (!tail_count(c.alpha, c.N, &k_f, &kc)) return fail(DRCVAR_ERR_INVALID, "alpha must be in (0,1] and N >= 1");
+  const size_t smem = slot_bytes_for(c.N, sizeof(T)) + fixed_smem_bytes();
+  if (smem > static_cast<size_t>(di->max_smem_optin))
+    return fail(DRCVAR_ERR_UNSUPPORTED, "N=%lld needs %zu B of shared memory per CTA (limit %d)", c.N, smem,
+                di->max_smem_optin);
+  if (c.B == 0) return DRCVAR_OK;
+
+  KernelArgs a{};
+  a.samples = c.samples;
+  a.B = c.B;
+  a.N = static_cast<int>(c.N);
+  a.stride_b = c.stride_b;
+  a.stride_n = c.stride_n;
+  a.stride_c = c.stride_c;
+  a.ego = c.ego;
+  a.h_in = c.h_in;
+  a.delta = c.delta;
+  a.eoa = c.epsilon / c.alpha;
+  a.R = c.r_robot + c.r_obs;
+  a.k_f = k_f;
+  a.kc = static_cast<int>(kc);
+  a.use_window = 0;
+  if (!(c.flags & DRCVAR_FLAG_GENERAL_ONLY)) a.use_window = plan_window(c.N, kc, &a.z_lo, &a.z_hi) ? 1 : 0;
+  const size_t row_bytes = static_cast<size_t>(c.N) * 2 * sizeof(T);
+  const bool contiguous = (c.stride_c == 1 && c.stride_n == 2);
+  a.bulk = contiguous && !(c.flags & DRCVAR_FLAG_NO_BULK) && (reinterpret_cast<uintptr_t>(c.samples) % 16 == 0) &&
+           ((static_cast<size_t>(c.stride_b) * sizeof(T)) % 16 == 0 || c.B == 1) && (row_bytes % 16 == 0) &&
+           row_bytes < (1u << 20);
+  a.h_out = c.h_out;
+  a.h_mean_out = c.h_mean_out;
+  a.g_out = c.g_out;
+  a.cvar_out = c.cvar_out;
+  a.var_out = c.var_out;
+  a.gstar_out = c.gstar_out;
+  a.status_out = c.status_out;
+  a.tail_idx_out = c.tail_idx_out;
+
+  const bool tail = c.tail_idx_out != nullptr;
+  auto kern = tail ? halfspace_kernel<T, true> : halfspace_kernel<T, false>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (per_sm < 1) return fail(DRCVAR_ERR_UNSUPPORTED, "kernel does not fit on an SM for N=%lld", c.N);
+  const long long grid = std::min<long long>(c.B, static_cast<long long>(per_sm) * di->sms);
+  kern<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return DRCVAR_OK;
+}
+
+int check_common(const Call& c) {
+  if (c.B < 0) return fail(DRCVAR_ERR_INVALID, "B must be >= 0");
+  if (c.N < 1) return fail(DRCVAR_ERR_INVALID, "N must be >= 1");
+  if (c.N > 0x7fffff00LL) return fail(DRCVAR_ERR_UNSUPPORTED, "N too large");
+  if (!(c.alpha > 0.0) || !(c.alpha <= 1.0)) return fail(DRCVAR_ERR_INVALID, "alpha must be in (0, 1]");
+  if (c.B > 0 && (!c.samples || !c.h_out || !c.g_out))
+    return fail(DRCVAR_ERR_INVALID, "samples, h_out and g_out must be non-null");
+  if (c.stride_n < 0 || c.stride_c < 0 || c.stride_b < 0) return fail(DRCVAR_ERR_INVALID, "negative strides are not supported");
+  return DRCVAR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// DRCVAR_HOST path: chunked, double-buffered staging through pinned memory, kernels overlapped with copies.
+struct HostCtx {
+  std::mutex mu;
+  int device = -1;
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  void* d_samples[2] = {nullptr, nullptr};
+  size_t d_samples_cap[2] = {0, 0};
+  void* h_pack[2] = {nullptr, nullptr};  // pinned, for strided host inputs
+  size_t h_pack_cap[2] = {0, 0};
+  unsigned char* d_io[2] = {nullptr, nullptr};  // ego/h_in + outputs
+  size_t d_io_cap[2] = {0, 0};
+  double last_stage_ms = 0, last_kernel_ms = 0;
+  long long last_h2d = 0, last_d2h = 0;
+};
+HostCtx g_host;
+
+int ensure_host_ctx(HostCtx& hc) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (hc.device != dev) {
+    // (re)create per-device resources; old buffers are released
+    for (int i = 0; i < 2; ++i) {
+      if (hc.d_samples[i]) cudaFree(hc.d_samples[i]);
+      if (hc.d_io[i]) cudaFree(hc.d_io[i]);
+      if (hc.h_pack[i]) cudaFreeHost(hc.h_pack[i]);
+      hc.d_samples[i] = nullptr; hc.d_samples_cap[i] = 0;
+      hc.d_io[i] = nullptr; hc.d_io_cap[i] = 0;
+      hc.h_pack[i] = nullptr; hc.h_pack_cap[i] = 0;
+      if (hc.streams[i]) cudaStreamDestroy(hc.streams[i]);
+      CUDA_TRY(cudaStreamCreateWithFlags(&hc.streams[i], cudaStreamNonBlocking));
+    }
+    if (!hc.ev_start) {
+      CUDA_TRY(cudaEventCreate(&hc.ev_start));
+      CUDA_TRY(cudaEventCreate(&hc.ev_stop));
+    }
+    hc.device = dev;
+  }
+  return DRCVAR_OK;
+}
+
+int grow_dev(void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return DRCVAR_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  size_t want = std::max(need, static_cast<size_t>(1) << 16);
+  CUDA_TRY(cudaMalloc(p, want));
+  *cap = want;
+  return DRCVAR_OK;
+}
+int grow_pinned(void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return DRCVAR_OK;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr;
+  *cap = 0;
+  size_t want = std::max(need, static_cast<size_t>(1) << 16);
+  CUDA_TRY(cudaMallocHost(p, want));
+  *cap = want;
+  return DRCVAR_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename T>
+int run_host(const Call& c) {
+  HostCtx& hc = g_host;
+  std::lock_guard<std::mutex> lk(hc.mu);
+  int rc = ensure_host_ctx(hc);
+  if (rc) return rc;
+  double k_f;
+  long long kc;
+  if (!tail_count(c.alpha, c.N, &k_f, &kc)) return fail(DRCVAR_ERR_INVALID, "alpha must be in (0,1] and N >= 1");
+  hc.last_stage_ms = hc.last_kernel_ms = 0;
+  hc.last_h2d = hc.last_d2h = 0;
+  if (c.B == 0) return DRCVAR_OK;
+
+  const size_t row_bytes = static_cast<size_t>(c.N) * 2 * sizeof(T);
+  const size_t row_pitch = align_up(row_bytes, 16);  // device rows are 16-B aligned so the bulk loader applies
+  const bool contiguous = (c.stride_c == 1 && c.stride_n == 2 && c.stride_b * sizeof(T) == row_bytes && row_pitch == row_bytes);
+  const size_t target_chunk = static_cast<size_t>(64) << 20;
+  long long chunk_b = static_cast<long long>(std::max<size_t>(1, target_chunk / row_pitch));
+  chunk_b = std::min(chunk_b, c.B);
+  const long long n_chunks = (c.B + chunk_b - 1) / chunk_b;
+
+  CUDA_TRY(cudaEventRecord(hc.ev_start, hc.streams[0]));
+  for (long long ci = 0; ci < n_chunks; ++ci) {
+    const int s = static_cast<int>(ci & 1);
+    cudaStream_t st = hc.streams[s];
+    const long long b0 = ci * chunk_b, nb = std::min(chunk_b, c.B - b0);
+    // buffers of this slot are reused: wait for the chunk that used them two iterations ago
+    if (ci >= 2) CUDA_TRY(cudaStreamSynchronize(st));
+    rc = grow_dev(&hc.d_samples[s], &hc.d_samples_cap[s], static_cast<size_t>(nb) * row_pitch);
+    if (rc) return rc;
+    // io block layout: ego[nb,2] h_in[nb,2] | h[nb,2] hm[nb,2] g[nb,3] cvar[nb] var[nb] gstar[nb] status[nb] tail[nb,kc]
+    const size_t dbl = sizeof(double);
+    const size_t off_ego = 0, off_hin = off_ego + nb * 2 * dbl, off_h = off_hin + nb * 2 * dbl,
+                 off_hm = off_h + nb * 2 * dbl, off_g = off_hm + nb * 2 * dbl, off_cvar = off_g + nb * 3 * dbl,
+                 off_var = off_cvar + nb * dbl, off_gs = off_var + nb * dbl, off_st = off_gs + nb * dbl,
+                 off_tail = align_up(off_st + nb * sizeof(int32_t), 16),
+                 io_bytes = off_tail + (c.tail_idx_out ? static_cast<size_t>(nb) * kc * sizeof(int32_t) : 0);
+    rc = grow_dev(reinterpret_cast<void**>(&hc.d_io[s]), &hc.d_io_cap[s], io_bytes);
+    if (rc) return rc;
+    unsigned char* io = hc.d_io[s];
+
+    // ---- samples H2D
+    const T* src = reinterpret_cast<const T*>(c.samples) + b0 * c.stride_b;
+    if (contiguous) {
+      CUDA_TRY(cudaMemcpyAsync(hc.d_samples[s], src, static_cast<size_t>(nb) * row_bytes, cudaMemcpyHostToDevice, st));
+    } else {
+      // strided host view (e.g. traj[:, t, :], simulation/environment.py:88): pack into pinned memory first
+      rc = grow_pinned(&hc.h_pack[s], &hc.h_pack_cap[s], static_cast<size_t>(nb) * row_pitch);
+      if (rc) return rc;
+      unsigned char* dst = static_cast<unsigned char*>(hc.h_pack[s]);
+      for (long long b = 0; b < nb; ++b) {
+        T* row = reinterpret_cast<T*>(dst + static_cast<size_t>(b) * row_pitch);
+        const T* sb = src + b * c.stride_b;
+        for (long long i = 0; i < c.N; ++i) {
+          row[2 * i] = sb[i * c.stride_n];
+          row[2 * i + 1] = sb[i * c.stride_n + c.stride_c];
+        }
+      }
+      CUDA_TRY(cudaMemcpyAsync(hc.d_samples[s], dst, static_cast<size_t>(nb) * row_pitch, cudaMemcpyHostToDevice, st));
+    }
+    hc.last_h2d += static_cast<long long>(nb) * static_cast<long long>(row_bytes);
+    if (c.ego) {
+      CUDA_TRY(cudaMemcpyAsync(io + off_ego, c.ego + 2 * b0, nb * 2 * dbl, cudaMemcpyHostToDevice, st));
+      hc.last_h2d += nb * 2 * dbl;
+    }
+    if (c.h_in) {
+      CUDA_TRY(cudaMemcpyAsync(io + off_hin, c.h_in + 2 * b0, nb * 2 * dbl, cudaMemcpyHostToDevice, st));
+      hc.last_h2d += nb * 2 * dbl;
+    }
+
+    Call d = c;
+    d.samples = hc.d_samples[s];
+    d.B = nb;
+    d.stride_b = static_cast<long long>(row_pitch / sizeof(T));
+    d.stride_n = 2;
+    d.stride_c = 1;
+    d.ego = c.ego ? reinterpret_cast<const double*>(io + off_ego) : nullptr;
+    d.h_in = c.h_in ? reinterpret_cast<const double*>(io + off_hin) : nullptr;
+    d.h_out = reinterpret_cast<double*>(io + off_h);
+    d.h_mean_out = reinterpret_cast<double*>(io + off_hm);
+    d.g_out = reinterpret_cast<double*>(io + off_g);
+    d.cvar_out = reinterpret_cast<double*>(io + off_cvar);
+    d.var_out = reinterpret_cast<double*>(io + off_var);
+    d.gstar_out = reinterpret_cast<double*>(io + off_gs);
+    d.status_out = reinterpret_cast<int32_t*>(io + off_st);
+    d.tail_idx_out = c.tail_idx_out ? reinterpret_cast<int32_t*>(io + off_tail) : nullptr;
+    rc = launch_on_device<T>(d, hc.device, st);
+    if (rc) return rc;
+
+    // ---- results D2H
+    auto back = [&](void* host, size_t off, size_t bytes) -> cudaError_t {
+      if (!host) return cudaSuccess;
+      hc.last_d2h += static_cast<long long>(bytes);
+      return cudaMemcpyAsync(host, io + off, bytes, cudaMemcpyDeviceToHost, st);
+    };
+    CUDA_TRY(back(c.h_out + 2 * b0, off_h, nb * 2 * dbl));
+    CUDA_TRY(back(c.h_mean_out ? c.h_mean_out + 2 * b0 : nullptr, off_hm, nb * 2 * dbl));
+    CUDA_TRY(back(c.g_out + 3 * b0, off_g, nb * 3 * dbl));
+    CUDA_TRY(back(c.cvar_out ? c.cvar_out + b0 : nullptr, off_cvar, nb * dbl));
+    CUDA_TRY(back(c.var_out ? c.var_out + b0 : nullptr, off_var, nb * dbl));
+    CUDA_TRY(back(c.gstar_out ? c.gstar_out + b0 : nullptr, off_gs, nb * dbl));
+    CUDA_TRY(back(c.status_out ? c.status_out + b0 : nullptr, off_st, nb * sizeof(int32_t)));
+    CUDA_TRY(back(c.tail_idx_out ? c.tail_idx_out + b0 * kc : nullptr, off_tail, static_cast<size_t>(nb) * kc * sizeof(int32_t)));
+  }
+  CUDA_TRY(cudaStreamSynchronize(hc.streams[0]));
+  CUDA_TRY(cudaStreamSynchronize(hc.streams[1]));
+  CUDA_TRY(cudaEventRecord(hc.ev_stop, hc.streams[0]));
+  CUDA_TRY(cudaEventSynchronize(hc.ev_stop));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, hc.ev_start, hc.ev_stop));
+  hc.last_kernel_ms = ms;  // device-side span of the whole pipelined call (copies + kernels)
+  return DRCVAR_OK;
+}
+
+template <typename T>
+int entry(const T* samples, int64_t B, int64_t N, int64_t stride_b, int64_t stride_n, int64_t stride_c,
+          const double* ego, const double* h_in, double alpha, double delta, double epsilon, double r_robot,
+          double r_obs, uint32_t flags, double* h_out, double* h_mean_out, double* g_out, double* cvar_out,
+          double* var_out, double* gstar_out, int32_t* status_out, int32_t* tail_idx_out, int device, void* stream) {
+  Call c{samples, B, N, stride_b, stride_n, stride_c, ego, h_in, alpha, delta, epsilon, r_robot, r_obs, flags,
+         h_out, h_mean_out, g_out, cvar_out, var_out, gstar_out, status_out, tail_idx_out};
+  int rc = check_common(c);
+  if (rc) return rc;
+  if (device == DRCVAR_HOST) return run_host<T>(c);
+  int prev = 0;
+  CUDA_TRY(cudaGetDevice(&prev));
+  if (prev != device) CUDA_TRY(cudaSetDevice(device));
+  rc = launch_on_device<T>(c, device, static_cast<cudaStream_t>(stream));
+  if (rc == DRCVAR_OK && (flags & DRCVAR_FLAG_SYNC)) {
+    cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) rc = fail(DRCVAR_ERR_CUDA, "stream synchronize failed: %s", cudaGetErrorString(e));
+  }
+  if (prev != device) cudaSetDevice(prev);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int drcvar_version(void) { return DRCVAR_ABI_VERSION; }
+const char* drcvar_last_error(void) { return g_err; }
+int drcvar_reduction_lanes(void) { return drcvar::kLanes; }
+
+int drcvar_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int64_t drcvar_tail_count(double alpha, int64_t n_samples, double* k_f_out) {
+  double k_f;
+  long long kc;
+  if (!tail_count(alpha, n_samples, &k_f, &kc)) return fail(DRCVAR_ERR_INVALID, "alpha must be in (0,1] and N >= 1");
+  if (k_f_out) *k_f_out = k_f;
+  return kc;
+}
+
+int64_t drcvar_max_samples(int elem_bytes, int device) {
+  if (elem_bytes != 4 && elem_bytes != 8) return fail(DRCVAR_ERR_INVALID, "elem_bytes must be 4 or 8");
+  int dev = device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return fail(DRCVAR_ERR_CUDA, "no CUDA device");
+  DeviceInfo* di = nullptr;
+  int rc = device_info(dev, &di);
+  if (rc) return rc;
+  const size_t avail = static_cast<size_t>(di->max_smem_optin) - drcvar::fixed_smem_bytes();
+  return static_cast<int64_t>((avail & ~static_cast<size_t>(127)) / (2 * static_cast<size_t>(elem_bytes)));
+}
+
+int drcvar_halfspaces_f32(const float* samples, int64_t B, int64_t N, int64_t stride_b, int64_t stride_n,
+                          int64_t stride_c, const double* ego, const double* h_in, double alpha, double delta,
+                          double epsilon, double r_robot, double r_obs, uint32_t flags, double* h_out,
+                          double* h_mean_out, double* g_out, double* cvar_out, double* var_out, double* gstar_out,
+                          int32_t* status_out, int32_t* tail_idx_out, int device, void* stream) {
+  return entry<float>(samples, B, N, stride_b, stride_n, stride_c, ego, h_in, alpha, delta, epsilon, r_robot, r_obs,
+                      flags, h_out, h_mean_out, g_out, cvar_out, var_out, gstar_out, status_out, tail_idx_out, device,
+                      stream);
+}
+
+int drcvar_halfspaces_f64(const double* samples, int64_t B, int64_t N, int64_t stride_b, int64_t stride_n,
+                          int64_t stride_c, const double* ego, const double* h_in, double alpha, double delta,
+                          double epsilon, double r_robot, double r_obs, uint32_t flags, double* h_out,
+                          double* h_mean_out, double* g_out, double* cvar_out, double* var_out, double* gstar_out,
+                          int32_t* status_out, int32_t* tail_idx_out, int device, void* stream) {
+  return entry<double>(samples, B, N, stride_b, stride_n, stride_c, ego, h_in, alpha, delta, epsilon, r_robot, r_obs,
+                       flags, h_out, h_mean_out, g_out, cvar_out, var_out, gstar_out, status_out, tail_idx_out, device,
+                       stream);
+}
+
+int drcvar_trajectory_f64(const double* const* traj, int64_t n_obs, int64_t N, int64_t T1, int64_t n_steps,
+                          const double* ego_steps, double alpha, double delta, double epsilon, double r_robot,
+                          double r_obs, uint32_t flags, double* h_out, double* h_mean_out, double* g_out,
+                          int32_t* status_out) {
+  if (!traj || n_obs < 1 || N < 1 || T1 < 1 || n_steps < 0 || n_steps > T1 || !ego_steps || !h_out || !g_out)
+    return fail(DRCVAR_ERR_INVALID, "bad trajectory arguments");
+  // pack halfspace (t, i) = traj[i][:, t, :] into one [n_steps*n_obs, N, 2] batch, ego repeated per obstacle
+  const int64_t B = n_steps * n_obs;
+  if (B == 0) return DRCVAR_OK;
+  std::vector<double> pack(static_cast<size_t>(B) * N * 2), ego(static_cast<size_t>(B) * 2);
+  for (int64_t t = 0; t < n_steps; ++t)
+    for (int64_t i = 0; i < n_obs; ++i) {
+      if (!traj[i]) return fail(DRCVAR_ERR_INVALID, "null trajectory pointer");
+      double* dst = pack.data() + static_cast<size_t>(t * n_obs + i) * N * 2;
+      const double* src = traj[i] + t * 2;
+      for (int64_t s = 0; s < N; ++s) {
+        dst[2 * s] = src[s * T1 * 2];
+        dst[2 * s + 1] = src[s * T1 * 2 + 1];
+      }
+      ego[static_cast<size_t>(t * n_obs + i) * 2] = ego_steps[2 * t];
+      ego[static_cast<size_t>(t * n_obs + i) * 2 + 1] = ego_steps[2 * t + 1];
+    }
+  return drcvar_halfspaces_f64(pack.data(), B, N, N * 2, 2, 1, ego.data(), nullptr, alpha, delta, epsilon, r_robot,
+                               r_obs, flags, h_out, h_mean_out, g_out, nullptr, nullptr, nullptr, status_out, nullptr,
+                               DRCVAR_HOST, nullptr);
+}
+
+void* drcvar_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    fail(DRCVAR_ERR_NOMEM, "cudaMallocHost(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+void drcvar_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int64_t drcvar_launch_count(void) { return g_launches.load(); }
+
+int drcvar_last_host_call_stats(double* stage_ms, double* kernel_ms, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  if (stage_ms) *stage_ms = g_host.last_stage_ms;
+  if (kernel_ms) *kernel_ms = g_host.last_kernel_ms;
+  if (h2d_bytes) *h2d_bytes = g_host.last_h2d;
+  if (d2h_bytes) *d2h_bytes = g_host.last_d2h;
+  return DRCVAR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+/*
+ * drcvar.h — C ABI of libdrcvar.so: B200 (sm_100a) risk-bounded safe-halfspace engine.
+ *
+ * The reference (RJ-23YP/DR_CVaR_MPC_Safety_Filter_Motion_Planning_Collison_Avoidance) is pure Python and has
+ * NO FFI layer; its boundary for this path is the Python API of core/risk_metrics.py and core/halfspaces.py.
+ * Each entry point below names the reference interface it replaces (file:line relative to the reference root).
+ * The Python binding a maintainer adds is a ctypes stub (see INTEGRATION.md and
+ * dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200/_lib.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the library never frees or retains caller memory;
+ *   - every function returns DRCVAR_OK (0) or a negative DRCVAR_ERR_* code and never throws;
+ *     drcvar_last_error() returns a thread-local message for the last failure;
+ *   - `device >= 0`: all pointers are DEVICE pointers on that CUDA device; work is enqueued on `stream`
+ *     (a cudaStream_t, NULL = legacy default stream) and the call does not synchronise unless
+ *     DRCVAR_FLAG_SYNC is set;
+ *   - `device == DRCVAR_HOST (-1)`: all pointers are HOST pointers; the library stages host->device copies
+ *     (chunked and overlapped with the kernels), runs on the current device and returns after the
+ *     results are back in the caller's host arrays;
+ *   - strides are in ELEMENTS of the sample dtype: coordinate c of sample i of halfspace b lives at
+ *     samples[b*stride_b + i*stride_n + c*stride_c].  A C-contiguous [B,N,2] array is (2N, 2, 1); the
+ *     reference's per-step view traj[:, t, :] of a [N, T+1, 2] array (simulation/environment.py:88) is
+ *     (0, 2(T+1), 1) with the base pointer advanced by 2t.
+ *
+ * Per-halfspace math (closed form of the reference's two ECOS LPs; see DESIGN.md, oracle/closed_form.py):
+ *   m = mean(xi); h = unit(m - ego) (fallback [1,0] if |m-ego| < 1e-10)          core/geometry.py:35-53
+ *   L_i = -(h.xi_i); CVaR = (sum of the alpha*N largest L_i, fractional last weight) / (alpha*N)
+ *   g_cvar   = CVaR + (r_robot+r_obs)|h| - delta                                  core/risk_metrics.py:179-265,305-338
+ *   g_star   = CVaR + (r_robot+r_obs)|h| + epsilon/alpha - delta                  core/risk_metrics.py:84-177
+ *   g_drcvar = g_star - (r_robot+r_obs)|h|                                        core/risk_metrics.py:267-303
+ *   h_mean = unit(m - 0); g_mean = -(h_mean.m - (r_robot+r_obs)|h_mean|)          core/halfspaces.py:70-106
+ */
+#ifndef DRCVAR_H_
+#define DRCVAR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRCVAR_ABI_VERSION 1
+
+#define DRCVAR_OK 0
+#define DRCVAR_ERR_INVALID (-1)     /* bad argument (alpha not in (0,1], N < 1, null pointer, bad stride) */
+#define DRCVAR_ERR_CUDA (-2)        /* a CUDA runtime call failed; see drcvar_last_error() */
+#define DRCVAR_ERR_UNSUPPORTED (-3) /* N too large for the on-chip kernels of this build */
+#define DRCVAR_ERR_NOMEM (-4)
+
+#define DRCVAR_HOST (-1)
+
+/* flags */
+#define DRCVAR_FLAG_SYNC 1u          /* device pointers: synchronise the stream before returning */
+#define DRCVAR_FLAG_GENERAL_ONLY 2u  /* disable the statistical candidate window (always use the general select) */
+#define DRCVAR_FLAG_NO_BULK 4u       /* disable cp.async.bulk staging (use the generic strided loader) */
+#define DRCVAR_FLAG_FORCE_CLUSTER 8u /* use the cluster/DSMEM kernel even when one CTA could hold N samples */
+
+/* per-halfspace status bits written to status_out */
+#define DRCVAR_STATUS_NONFINITE 1   /* non-finite input: sentinel 100.0 emitted (core/risk_metrics.py:177,265,303,338) */
+#define DRCVAR_STATUS_GENERAL 2     /* the general (multi-sweep) select path was taken */
+#define DRCVAR_STATUS_DEGENERATE 4  /* |mean - ego| < 1e-10: fallback direction [1,0] (core/geometry.py:49-51) */
+
+int drcvar_version(void);
+const char* drcvar_last_error(void);
+int drcvar_device_count(void);
+
+/* Number of summation lanes of the canonical mean reduction (512); part of the arithmetic contract. */
+int drcvar_reduction_lanes(void);
+
+/*
+ * Tail size for (alpha, N): returns kc = ceil(alpha*N) (alpha*N snapped to an integer when within 1e-9
+ * relative), writes the fractional tail mass to *k_f_out when non-NULL.  Negative on invalid input.
+ * Replaces the implicit 1/(alpha*N) weighting of core/risk_metrics.py:110,209.
+ */
+int64_t drcvar_tail_count(double alpha, int64_t n_samples, double* k_f_out);
+
+/* Largest N the kernels of this build accept for a sample dtype of `elem_bytes` (4 or 8) on `device`. */
+int64_t drcvar_max_samples(int elem_bytes, int device);
+
+/*
+ * Batched safe halfspaces — replaces, for B (scenario, obstacle, step) triples at once,
+ *   MeanSafeHalfspace.create / CVaRSafeHalfspace.create / DRCVaRSafeHalfspace.create   core/halfspaces.py:70-194
+ *   cvar_halfspace / dr_cvar_halfspace (when h_in != NULL)                                core/risk_metrics.py:267-338
+ *   CVaROptimizer.solve / DRCVaROptimizer.solve                                           core/risk_metrics.py:127-177,215-265
+ *   compute_safe_halfspaces (loop over obstacles)                                         core/halfspaces.py:196-247
+ *
+ *   samples      [B] x [N] x [2], dtype float (f32) / double (f64), strides in elements (see above)
+ *   ego          [B,2] double ego reference positions, or NULL (= origin)
+ *   h_in         [B,2] double explicit normals, or NULL (derive h from the sample mean and ego)
+ *   h_out        [B,2] double  normal used by the CVaR / DR-CVaR halfspaces              (required)
+ *   h_mean_out   [B,2] double  normal of the mean halfspace (measured from the origin)   (may be NULL)
+ *   g_out        [B,3] double  (g_mean, g_cvar, g_drcvar) — the g-tilde of each metric   (required)
+ *   cvar_out     [B]   double  CVaR_alpha of the loss                                     (may be NULL)
+ *   var_out      [B]   double  ceil(alpha N)-th largest loss (VaR threshold T)           (may be NULL)
+ *   gstar_out    [B]   double  DR-CVaR LP optimum g* (before subtracting the radius)     (may be NULL)
+ *   status_out   [B]   int32   DRCVAR_STATUS_* bits                                       (may be NULL)
+ *   tail_idx_out [B, kc] int32 indices of the kc = drcvar_tail_count() largest losses, ascending,
+ *                ties -> lower index (parity mode; may be NULL; slows the kernel)
+ */
+int drcvar_halfspaces_f32(const float* samples, int64_t B, int64_t N,
+                          int64_t stride_b, int64_t stride_n, int64_t stride_c,
+                          const double* ego, const double* h_in,
+                          double alpha, double delta, double epsilon, double r_robot, double r_obs,
+                          uint32_t flags,
+                          double* h_out, double* h_mean_out, double* g_out,
+                          double* cvar_out, double* var_out, double* gstar_out,
+                          int32_t* status_out, int32_t* tail_idx_out,
+                          int device, void* stream);
+
+int drcvar_halfspaces_f64(const double* samples, int64_t B, int64_t N,
+                          int64_t stride_b, int64_t stride_n, int64_t stride_c,
+                          const double* ego, const double* h_in,
+                          double alpha, double delta, double epsilon, double r_robot, double r_obs,
+                          uint32_t flags,
+                          double* h_out, double* h_mean_out, double* g_out,
+                          double* cvar_out, double* var_out, double* gstar_out,
+                          int32_t* status_out, int32_t* tail_idx_out,
+                          int device, void* stream);
+
+/*
+ * One-launch trajectory entry — replaces the (t, obstacle) double loop of
+ * SafetyFilteringEnvironment.compute_safe_halfspaces_for_trajectory     simulation/environment.py:60-106.
+ * HOST pointers only.  traj[i] points at obstacle i's [N, T1, 2] double array (C-contiguous);
+ * halfspace (t, i) uses samples traj[i][:, t, :] and ego ego_steps[t].  Outputs are [n_steps, n_obs, ...]
+ * with the same meaning as above.
+ */
+int drcvar_trajectory_f64(const double* const* traj, int64_t n_obs, int64_t N, int64_t T1, int64_t n_steps,
+                          const double* ego_steps /* [n_steps,2] */,
+                          double alpha, double delta, double epsilon, double r_robot, double r_obs,
+                          uint32_t flags,
+                          double* h_out, double* h_mean_out, double* g_out, int32_t* status_out);
+
+/* Pinned host memory for callers that want full-speed host->device staging through DRCVAR_HOST calls. */
+void* drcvar_host_alloc(size_t bytes);
+void drcvar_host_free(void* p);
+
+/* Telemetry of this process: kernels launched so far; timings (ms) and bytes of the LAST DRCVAR_HOST call. */
+int64_t drcvar_launch_count(void);
+int drcvar_last_host_call_stats(double* stage_ms, double* kernel_ms, int64_t* h2d_bytes, int64_t* d2h_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRCVAR_H_ */

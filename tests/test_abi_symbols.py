@@ -1,0 +1,77 @@
+"""CPU tests: the C-ABI library loads without a GPU and exports every symbol include/drcvar.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = "dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    if not os.path.exists(os.path.join(ROOT, PKG, "libdrcvar.so")):
+        g.build()
+    from importlib import import_module
+    return import_module(PKG + "._lib")
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "drcvar.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(drcvar_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    names = _declared_symbols()
+    assert len(names) >= 12
+    cdll = ctypes.CDLL(lib.LIB_PATH)
+    for n in names:
+        assert hasattr(cdll, n), f"{n} declared in include/drcvar.h but not exported"
+        assert n in lib.SYMBOLS, f"{n} has no ctypes prototype in _lib.py"
+    assert sorted(lib.SYMBOLS) == names
+
+
+def test_host_logic_without_gpu(lib):
+    L = lib.load()
+    assert L.drcvar_version() == 1
+    assert L.drcvar_reduction_lanes() == 512
+    kf = ctypes.c_double()
+    assert L.drcvar_tail_count(0.1, 10000, ctypes.byref(kf)) == 1000 and kf.value == 1000.0
+    assert L.drcvar_tail_count(0.2, 23, ctypes.byref(kf)) == 5 and abs(kf.value - 4.6) < 1e-12
+    assert L.drcvar_tail_count(0.2, 3, None) == 1
+    assert L.drcvar_tail_count(1.0, 7, None) == 7
+    assert L.drcvar_tail_count(0.0, 7, None) == lib.ERR_INVALID
+    assert b"alpha" in L.drcvar_last_error()
+    assert L.drcvar_tail_count(0.5, 0, None) == lib.ERR_INVALID
+
+
+def test_tail_count_matches_oracle(lib):
+    from oracle import closed_form as cf
+    import numpy as np
+    L = lib.load()
+    rng = np.random.RandomState(0)
+    kf = ctypes.c_double()
+    for _ in range(2000):
+        n = int(rng.randint(1, 200000))
+        alpha = float(rng.choice([0.05, 0.1, 0.2, 0.25, 0.3, 0.5, 1.0, rng.uniform(1e-4, 1.0)]))
+        kc = L.drcvar_tail_count(alpha, n, ctypes.byref(kf))
+        assert (kf.value, kc) == cf.tail_count(alpha, n)
+
+
+def test_argument_validation_precedes_any_cuda_call(lib):
+    L = lib.load()
+    import numpy as np
+    s = np.zeros((1, 4, 2))
+    h = np.zeros((1, 2)); g = np.zeros((1, 3))
+    rc = L.drcvar_halfspaces_f64(s.ctypes.data, 1, 4, 8, 2, 1, None, None, 2.0, 0.1, 0.1, 0.3, 0.3, 0,
+                                 h.ctypes.data, None, g.ctypes.data, None, None, None, None, None, lib.HOST, None)
+    assert rc == lib.ERR_INVALID
+    rc = L.drcvar_halfspaces_f64(None, 1, 4, 8, 2, 1, None, None, 0.2, 0.1, 0.1, 0.3, 0.3, 0,
+                                 h.ctypes.data, None, g.ctypes.data, None, None, None, None, None, lib.HOST, None)
+    assert rc == lib.ERR_INVALID
+    rc = L.drcvar_halfspaces_f32(s.ctypes.data, 1, 0, 8, 2, 1, None, None, 0.2, 0.1, 0.1, 0.3, 0.3, 0,
+                                 h.ctypes.data, None, g.ctypes.data, None, None, None, None, None, lib.HOST, None)
+    assert rc == lib.ERR_INVALID

@@ -1,0 +1,227 @@
+"""
+GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(libdrcvar.so via ctypes); the checker is oracle/closed_form.py and the committed golden vectors
+that the reference's own modules produced (tests/golden/make_golden.py).
+
+Bars (BASELINE.json north_star):
+  * tail-index sets bit-exact (ties -> lower index);
+  * h, mean: bit-exact (canonical arithmetic contract);
+  * CVaR / offsets: <= 1e-9 relative for fp64 inputs; <= 1e-5 m for the fp32-input path vs the fp64 truth
+    (and <= 1e-9 relative vs the oracle applied to the promoted fp32 samples).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import closed_form as cf
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9
+PARAMS = dict(alpha=0.2, delta=0.1, epsilon=0.15, robot_radius=0.3, obstacle_radius=0.3)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 as pkg
+    return pkg
+
+
+def rel_close(a, b, tol=REL):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b)))
+
+
+def check_batch(res, samples, ego, p, h_in=None, tail=True, exact_h=True):
+    """Compare a HalfspaceBatch (numpy) with the oracle, halfspace by halfspace."""
+    B = samples.shape[0]
+    ego = np.broadcast_to(np.zeros(2) if ego is None else np.asarray(ego, dtype=np.float64), (B, 2))
+    for b in range(B):
+        o = cf.halfspace(samples[b], ego[b], p["alpha"], p["delta"], p["epsilon"], p["robot_radius"],
+                         p["obstacle_radius"], None if h_in is None else np.broadcast_to(h_in, (B, 2))[b])
+        if exact_h:
+            assert np.array_equal(res.h[b], o.h), (b, res.h[b], o.h)
+            assert np.array_equal(res.h_mean[b], o.h_mean), (b, res.h_mean[b], o.h_mean)
+        else:
+            assert np.abs(res.h[b] - o.h).max() < 1e-14
+        assert rel_close(res.g[b], [o.g_mean, o.g_cvar, o.g_dr]), (b, res.g[b], (o.g_mean, o.g_cvar, o.g_dr))
+        assert rel_close(res.cvar[b], o.cvar), (b, res.cvar[b], o.cvar)
+        assert res.var[b] == o.var, (b, res.var[b], o.var)          # the threshold is an order statistic: exact
+        assert rel_close(res.g_star[b], o.g_dr_star)
+        if tail and res.tail_idx is not None:
+            assert np.array_equal(res.tail_idx[b], o.tail_idx), b
+
+
+def test_golden_scenarios_through_abi(eng, golden_dir):
+    for name in ("head_on_seed42.npz", "multi_obstacle_seed42.npz"):
+        z = np.load(os.path.join(golden_dir, name))
+        alpha, delta, eps, rr, ro, horizon = z["params"]
+        traj = z["sample_trajectories"]                      # [n_obs, N, H+1, 2]
+        x_ref = z["x_ref"]
+        n_steps = z["g_mean"].shape[0]
+        n_obs = traj.shape[0]
+        # batch (t, i) -> strided views exactly like simulation/environment.py:88
+        samples = np.stack([traj[i][:, t, :] for t in range(n_steps) for i in range(n_obs)])
+        ego = np.stack([x_ref[t][:2] for t in range(n_steps) for i in range(n_obs)])
+        res = eng.compute_halfspaces(samples, ego, alpha=alpha, delta=delta, epsilon=eps, robot_radius=rr,
+                                     obstacle_radius=ro, want_tail=True)
+        g_ref = np.stack([z["g_mean"].reshape(-1), z["g_cvar"].reshape(-1), z["g_dr_cvar"].reshape(-1)], axis=1)
+        assert np.abs(res.g - g_ref).max() < 1e-9
+        assert np.abs(res.h - z["h_dr_cvar"].reshape(-1, 2)).max() < 1e-12
+        assert np.abs(res.h_mean - z["h_mean"].reshape(-1, 2)).max() < 1e-12
+        p = dict(alpha=alpha, delta=delta, epsilon=eps, robot_radius=rr, obstacle_radius=ro)
+        check_batch(res, samples, ego, p)
+        # one call per halfspace on the strided view itself (no host repacking by the caller)
+        t, i = 7, n_obs - 1
+        view = traj[i][:, t, :]
+        assert not view.flags["C_CONTIGUOUS"]
+        one = eng.compute_halfspaces(view, x_ref[t][:2], alpha=alpha, delta=delta, epsilon=eps, robot_radius=rr,
+                                     obstacle_radius=ro)
+        assert np.array_equal(one.g[0], res.g[t * n_obs + i])
+
+
+def test_golden_timing_sweep_and_explicit_h(eng, golden_dir):
+    z = np.load(os.path.join(golden_dir, "timing_sweep.npz"))
+    alpha, delta, eps, rr, ro = z["params"]
+    for n in z["sizes"]:
+        s = z[f"samples_{n}"]
+        ref = z[f"out_{n}"]
+        res = eng.compute_halfspaces(s, np.zeros(2), alpha=alpha, delta=delta, epsilon=eps, robot_radius=rr,
+                                     obstacle_radius=ro, want_tail=True)
+        assert np.abs(res.h[0] - ref[0:2]).max() < 1e-12
+        assert abs(res.g[0, 2] - ref[2]) < 1e-9 and abs(res.g[0, 1] - ref[5]) < 1e-9 and abs(res.g[0, 0] - ref[8]) < 1e-9
+        check_batch(res, s[None], np.zeros(2), dict(alpha=alpha, delta=delta, epsilon=eps, robot_radius=rr, obstacle_radius=ro))
+    z = np.load(os.path.join(golden_dir, "explicit_h.npz"))
+    for c in range(int(z["n_cases"])):
+        alpha, delta, eps, rr, ro, h0, h1 = z[f"in_{c}"]
+        g_star, g_tilde, g_cvar = z[f"out_{c}"]
+        s = z[f"samples_{c}"]
+        res = eng.compute_halfspaces(s, None, alpha=alpha, delta=delta, epsilon=eps, robot_radius=rr,
+                                     obstacle_radius=ro, h=(h0, h1), want_tail=True)
+        assert abs(res.g_star[0] - g_star) < 1e-9 and abs(res.g[0, 2] - g_tilde) < 1e-9 and abs(res.g[0, 1] - g_cvar) < 1e-9
+        check_batch(res, s[None], None, dict(alpha=alpha, delta=delta, epsilon=eps, robot_radius=rr, obstacle_radius=ro),
+                    h_in=np.array([h0, h1]))
+
+
+def test_golden_n10k(eng, golden_dir):
+    z = np.load(os.path.join(golden_dir, "n10k.npz"))
+    alpha, delta, eps, rr, ro = z["params"]
+    p = dict(alpha=alpha, delta=delta, epsilon=eps, robot_radius=rr, obstacle_radius=ro)
+    res = eng.compute_halfspaces(z["samples"], z["ego"], want_tail=True, **p)
+    ref = z["out"]
+    assert np.abs(res.h[0] - ref[0:2]).max() < 1e-12
+    assert abs(res.g[0, 2] - ref[2]) < 1e-9 and abs(res.g[0, 1] - ref[5]) < 1e-9 and abs(res.g[0, 0] - ref[8]) < 1e-9
+    check_batch(res, z["samples"][None], z["ego"], p)
+    assert res.status[0] == 0                                   # window path, no fallback
+    res32 = eng.compute_halfspaces(z["samples32"], z["ego"], want_tail=True, **p)
+    assert abs(res32.g[0, 2] - z["out32"][2]) < 1e-9
+    assert abs(res32.g[0, 2] - ref[2]) < 1e-5                   # fp32-input path vs fp64 truth: 1e-5 m
+    check_batch(res32, z["samples32"][None], z["ego"], p)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n,alpha", [(10000, 0.1), (4096, 0.05), (2500, 0.3), (1500, 0.2), (1025, 0.5), (777, 0.2),
+                                      (512, 0.1), (33, 0.2), (20, 0.2), (2, 0.5), (1, 1.0), (1000, 1.0), (3000, 0.0123)])
+def test_random_batches(eng, dtype, n, alpha):
+    rng = np.random.RandomState(n * 7 + int(alpha * 1000))
+    B = 24 if n >= 1000 else 64
+    mu = rng.uniform(-5, 5, size=(B, 1, 2))
+    s = (mu + 0.1 * rng.standard_normal((B, n, 2))).astype(dtype)
+    ego = rng.uniform(-1, 1, size=(B, 2))
+    p = dict(PARAMS, alpha=alpha, epsilon=0.01)
+    res = eng.compute_halfspaces(s, ego, want_tail=True, **p)
+    check_batch(res, s, ego, p)
+    # without the tail output (the timed configuration) results are identical
+    res2 = eng.compute_halfspaces(s, ego, **p)
+    assert np.array_equal(res2.g, res.g) and np.array_equal(res2.h, res.h) and np.array_equal(res2.cvar, res.cvar)
+    # forcing the general select or the generic loader changes nothing but the last-bit summation order
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    res3 = eng.compute_halfspaces(s, ego, want_tail=True, flags=_lib.FLAG_GENERAL_ONLY | _lib.FLAG_NO_BULK, **p)
+    assert np.array_equal(res3.tail_idx, res.tail_idx) and np.array_equal(res3.var, res.var)
+    assert np.array_equal(res3.h, res.h) and rel_close(res3.g, res.g, 1e-12)
+    assert np.all(res3.status & _lib.STATUS_GENERAL)
+
+
+def test_window_miss_falls_back_exactly(eng):
+    """Non-Gaussian data (bimodal, heavy tails, constants) defeats the statistical window; result must not change."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    rng = np.random.RandomState(3)
+    n, B = 6000, 12
+    s = np.empty((B, n, 2))
+    for b in range(B):
+        kind = b % 4
+        if kind == 0:      # bimodal
+            s[b] = np.where(rng.rand(n, 1) < 0.15, 6.0, 2.0) + 0.05 * rng.standard_normal((n, 2))
+        elif kind == 1:    # heavy tails
+            s[b] = 3.0 + 0.1 * rng.standard_cauchy((n, 2)).clip(-1e3, 1e3)
+        elif kind == 2:    # few distinct values (massive ties)
+            s[b] = 2.0 + rng.randint(0, 4, size=(n, 2)) * 0.25
+        else:              # all identical (obstacle at t = 0, simulation/obstacles.py:63)
+            s[b] = np.array([4.0, -1.0])
+    ego = np.zeros((B, 2))
+    p = dict(PARAMS, alpha=0.1, epsilon=0.01)
+    res = eng.compute_halfspaces(s, ego, want_tail=True, **p)
+    check_batch(res, s, ego, p)
+    assert (res.status[3::4] & _lib.STATUS_GENERAL).all()
+    assert np.array_equal(res.tail_idx[3], np.arange(600))
+
+
+def test_degenerate_direction_and_nonfinite(eng):
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    s = np.tile(np.array([[4.0, 0.0]]), (3, 20, 1))
+    ego = np.array([[-4.0, 0.0], [4.0, 0.0], [0.0, 0.0]])
+    s[2, 5, 0] = np.nan
+    res = eng.compute_halfspaces(s, ego, want_tail=True, **PARAMS)
+    assert res.g[0, 2] == pytest.approx(-3.35, abs=1e-15) and res.g[0, 1] == pytest.approx(-3.5, abs=1e-15)
+    assert np.array_equal(res.tail_idx[0], np.arange(4))
+    assert np.array_equal(res.h[1], [1.0, 0.0]) and (res.status[1] & _lib.STATUS_DEGENERATE)
+    assert res.status[2] & _lib.STATUS_NONFINITE and res.g[2, 1] == 100.0 and np.all(res.tail_idx[2] == -1)
+
+
+def test_device_path_matches_host_path(eng):
+    import torch
+    rng = np.random.RandomState(11)
+    for dtype in (np.float32, np.float64):
+        s = (np.array([2.0, 1.0]) + 0.1 * rng.standard_normal((40, 5000, 2))).astype(dtype)
+        ego = rng.uniform(-1, 1, size=(40, 2))
+        p = dict(PARAMS, alpha=0.1, epsilon=0.01)
+        host = eng.compute_halfspaces(s, ego, want_tail=True, **p)
+        dev = eng.compute_halfspaces(torch.from_numpy(s).cuda(), torch.from_numpy(ego).cuda(), want_tail=True, **p)
+        torch.cuda.synchronize()
+        assert np.array_equal(dev.g.cpu().numpy(), host.g)
+        assert np.array_equal(dev.h.cpu().numpy(), host.h)
+        assert np.array_equal(dev.tail_idx.cpu().numpy(), host.tail_idx)
+        # strided device view [N, T, 2] -> [:, t, :]
+        big = torch.from_numpy(np.ascontiguousarray(np.repeat(s[0][:, None, :], 5, axis=1))).cuda()
+        big[:, 3, :] = torch.from_numpy(s[1]).cuda()
+        one = eng.compute_halfspaces(big[:, 3, :], torch.from_numpy(ego[1]).cuda(), **p)
+        torch.cuda.synchronize()
+        assert np.array_equal(one.g.cpu().numpy()[0], host.g[1])
+
+
+def test_bad_arguments_raise(eng):
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    s = np.zeros((1, 8, 2))
+    with pytest.raises(_lib.DrcvarError):
+        eng.compute_halfspaces(s, None, **dict(PARAMS, alpha=0.0))
+    with pytest.raises(_lib.DrcvarError):
+        eng.compute_halfspaces(s, None, **dict(PARAMS, alpha=1.5))
+    big = np.zeros((1, eng.max_samples(np.float64) + 64, 2))
+    with pytest.raises(_lib.DrcvarError) as ei:
+        eng.compute_halfspaces(big, None, **PARAMS)
+    assert ei.value.code == _lib.ERR_UNSUPPORTED
+
+
+def test_run_to_run_determinism(eng):
+    rng = np.random.RandomState(5)
+    s = (np.array([1.0, 3.0]) + 0.1 * rng.standard_normal((300, 10000, 2))).astype(np.float32)
+    p = dict(PARAMS, alpha=0.1, epsilon=0.01)
+    a = eng.compute_halfspaces(s, None, **p)
+    b = eng.compute_halfspaces(s, None, **p)
+    assert np.array_equal(a.g, b.g) and np.array_equal(a.h, b.h) and np.array_equal(a.cvar, b.cvar)
+    assert (a.status == 0).all()
