@@ -86,7 +86,7 @@ bool plan_window(long long n, long long kc, double* z_lo, double* z_hi) {
   const double sq = std::sqrt(p * (1.0 - p) / static_cast<double>(n)) / phi;  // std of the sample quantile
   const double w = 6.0 * sq + 0.03 + 0.02 * std::fabs(z);
   const double expect = static_cast<double>(n) * 2.0 * w * phi;
-  if (expect > 0.25 * drcvar::kCandCap * drcvar::kThreads) return false;
+  if (expect > 0.5 * drcvar::kWarpCand * drcvar::kWarps) return false;  // per-warp lists: 8 sigma headroom
   *z_lo = z - w;
   *z_hi = z + w;
   return true;

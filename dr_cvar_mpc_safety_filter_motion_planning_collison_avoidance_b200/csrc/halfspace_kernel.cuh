@@ -1,13 +1,17 @@
 // halfspace_kernel.cuh — sm_100a device code of the risk-bounded safe-halfspace path.
 //
-// One CTA per (scenario, obstacle, step) halfspace, persistent over the batch.  Per halfspace:
+// One CTA (512 threads) per (scenario, obstacle, step) halfspace, persistent over the batch.  Per halfspace:
 //   stage   N samples -> shared memory with cp.async.bulk (TMA bulk copy, mbarrier completion) or a strided loader
-//   sweep A canonical 512-lane fp64 sums of x,y (+ heuristic second moments)         -> mean m
+//   sweep A canonical 512-lane fp64 sums of x,y (+ heuristic second moments, max |coordinate|)  -> mean m
 //   h       = unit(m - ego)                                                            core/geometry.py:35-53
-//   sweep B L_i = -(h.xi_i) (no FMA), count/sum losses above a statistical window, keep window candidates
+//   sweep B fp32 inputs: a rigorous fp32 screen keeps only samples that can reach the candidate window, then
+//           the survivors get the canonical fp64 loss L_i = -(h.xi_i) (no FMA); losses above the window are
+//           counted/summed, losses inside it go to warp-private candidate lists
 //   select  exact kc-th largest loss T by adaptive range-narrowing radix select on order-preserving u64 keys
 //   finish  CVaR = (sum_{L>T} L + (k_f - #{L>T}) T) / k_f  and the three offsets        core/risk_metrics.py:84-338
-// The arithmetic contract (what must be bit-identical to oracle/closed_form.py) is described in DESIGN.md.
+// The window and the screen only decide HOW FAST the exact answer is found; a miss is detected and the general
+// multi-sweep select runs instead.  The arithmetic contract (what is bit-identical to oracle/closed_form.py) is
+// in DESIGN.md.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -15,12 +19,13 @@
 
 namespace drcvar {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kLanes = 512;          // canonical summation lanes (2 per thread)
-constexpr int kCandCap = 12;         // private candidate slots per thread (window path)
-constexpr int kHistBuckets = 1024;
+constexpr int kLanes = 512;          // canonical summation lanes (one per thread)
+constexpr int kWarpCand = 128;       // candidate slots per warp (window path)
+constexpr int kHistBuckets = 256;
 constexpr int kResolveMax = 32;      // a bucket this small is resolved by one warp
+constexpr int kMaxPerThread = 64;    // screening mask is 64 bits: N <= 64 * 512
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kBulkChunk = 32768;
 
@@ -54,8 +59,9 @@ struct Ctl {
   unsigned long long mbar;
   double T;
   double h0, h1, t_lo, t_hi, m0, m1;
+  float h0f, h1f, screen_thr, pad0;
   int bstar, rprime, cnt_in, small_n;
-  int window_ok, nonfinite, degenerate, pad;
+  int window_ok, nonfinite, degenerate, pad1;
 };
 
 template <typename T> struct Vec2;
@@ -66,10 +72,11 @@ template <> struct Vec2<double> { using type = double2; };
 __host__ __device__ inline size_t slot_bytes_for(long long n, size_t elem_bytes) {
   return (static_cast<size_t>(n) * 2 * elem_bytes + 127) & ~static_cast<size_t>(127);
 }
+constexpr int kRedDoubles = kWarps * 8;  // per buffer
 __host__ __device__ inline size_t fixed_smem_bytes() {
-  return sizeof(double) * kCandCap * kThreads      // cand
+  return sizeof(double) * kWarpCand * kWarps        // cand
          + sizeof(unsigned) * kHistBuckets          // hist
-         + sizeof(double) * 2 * kWarps * 8          // red (double-buffered)
+         + sizeof(double) * 2 * kRedDoubles         // red (double-buffered)
          + sizeof(double) * kResolveMax             // small
          + sizeof(int) * 4 * kWarps                 // ired
          + sizeof(Ctl);
@@ -133,6 +140,11 @@ __device__ __forceinline__ double warp_sum_any(double v) {
   for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_d(v, m);
   return v;
 }
+__device__ __forceinline__ float warp_sum_any(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(kFull, v, m);
+  return v;
+}
 __device__ __forceinline__ double warp_sum_canon(double v) {  // xor 1,2,4,8,16 — part of the arithmetic contract
 #pragma unroll
   for (int m = 1; m <= 16; m <<= 1) v = __dadd_rn(v, shfl_xor_d(v, m));
@@ -141,27 +153,31 @@ __device__ __forceinline__ double warp_sum_canon(double v) {  // xor 1,2,4,8,16 
 
 // Exact r-th largest (1-based) among the enumerated losses whose keys lie in [lo, hi].
 // for_each(f) must call f(L) for every candidate owned by the calling thread; all threads must call this.
+// `hist` must be zero on entry (it is left dirty).
 template <class ForEach>
 __device__ double select_rank(ForEach&& for_each, unsigned long long lo, unsigned long long hi, int r,
-                              unsigned* hist, double* small, Ctl* ctl) {
+                              unsigned* hist, double* small, Ctl* ctl, bool hist_clean) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (;;) {
     const unsigned long long span = hi - lo;
     if (span == 0) return value_of(lo);
     const int bits = 64 - __clzll(static_cast<long long>(span));
-    const int shift = bits > 10 ? bits - 10 : 0;  // (span >> shift) < 1024
-    for (int i = tid; i < kHistBuckets; i += kThreads) hist[i] = 0;
-    if (tid == 0) ctl->small_n = 0;
-    __syncthreads();
+    const int shift = bits > 8 ? bits - 8 : 0;  // (span >> shift) < 256
+    if (!hist_clean) {
+      if (tid < kHistBuckets) hist[tid] = 0;
+      if (tid == 0) ctl->small_n = 0;
+      __syncthreads();
+    }
+    hist_clean = false;
     for_each([&](double L) {
       const unsigned long long k = key_of(L);
       if (k >= lo && k <= hi) atomicAdd(&hist[static_cast<unsigned>((k - lo) >> shift)], 1u);
     });
     __syncthreads();
     if (warp == 0) {
-      // rows of 32 buckets, row 0 = top; lane l of row i is bucket 1023 - (32 i + l)
+      // rows of 32 buckets, row 0 = top; lane l of row i is bucket 255 - (32 i + l)
       int run = 0, row = -1, r_row = 0;
-#pragma unroll 4
+#pragma unroll
       for (int i = 0; i < kHistBuckets / 32; ++i) {
         const int tot = __reduce_add_sync(kFull, static_cast<int>(hist[kHistBuckets - 1 - (32 * i + lane)]));
         if (row < 0 && run + tot >= r) {
@@ -170,8 +186,7 @@ __device__ double select_rank(ForEach&& for_each, unsigned long long lo, unsigne
         }
         run += tot;
       }
-      // row >= 0 is guaranteed by the caller (r <= number of candidates in range)
-      if (row < 0) { row = kHistBuckets / 32 - 1; r_row = 1; }
+      if (row < 0) { row = kHistBuckets / 32 - 1; r_row = 1; }  // unreachable when r <= #candidates in range
       const int bucket = kHistBuckets - 1 - (32 * row + lane);
       const int c = static_cast<int>(hist[bucket]);
       int incl = c;
@@ -222,7 +237,7 @@ __device__ double select_rank(ForEach&& for_each, unsigned long long lo, unsigne
 
 // ---------------------------------------------------------------------------------------------- the kernel
 template <typename T, bool kTail>
-__global__ void __launch_bounds__(kThreads) halfspace_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs a) {
   using V2 = typename Vec2<T>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -230,11 +245,12 @@ __global__ void __launch_bounds__(kThreads) halfspace_kernel(const KernelArgs a)
   const size_t slot_bytes = slot_bytes_for(N, sizeof(T));
   V2* sm = reinterpret_cast<V2*>(smem_raw);
   double* cand = reinterpret_cast<double*>(smem_raw + slot_bytes);
-  unsigned* hist = reinterpret_cast<unsigned*>(cand + kCandCap * kThreads);
+  unsigned* hist = reinterpret_cast<unsigned*>(cand + kWarpCand * kWarps);
   double* red_base = reinterpret_cast<double*>(hist + kHistBuckets);
-  double* small = red_base + 2 * kWarps * 8;
+  double* small = red_base + 2 * kRedDoubles;
   int* ired = reinterpret_cast<int*>(small + kResolveMax);
   Ctl* ctl = reinterpret_cast<Ctl*>(ired + 4 * kWarps);
+  double* wcand = cand + warp * kWarpCand;
 
   const uint32_t copy_bytes = static_cast<uint32_t>(static_cast<size_t>(N) * sizeof(V2));
   auto issue_bulk = [&](long long b) {
@@ -259,7 +275,7 @@ __global__ void __launch_bounds__(kThreads) halfspace_kernel(const KernelArgs a)
   int iter = 0;
 
   for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
-    double* red = red_base + (iter & 1) * kWarps * 8;
+    double* red = red_base + (iter & 1) * kRedDoubles;
     bool next_issued = false;
     const long long b_next = b + gridDim.x;
 
@@ -279,67 +295,80 @@ __global__ void __launch_bounds__(kThreads) halfspace_kernel(const KernelArgs a)
       __syncthreads();
     }
 
-    // ------------------------------------------------------------------ sweep A: canonical lane sums + moments
-    double sx0 = 0.0, sy0 = 0.0, sx1 = 0.0, sy1 = 0.0;
-    T qdx = 0, qdy = 0, qxx = 0, qxy = 0, qyy = 0;  // heuristic, shifted by the first sample
+    // ------------------------------------------------------------------ sweep A: canonical lane sums (+ heuristics)
+    double sx = 0.0, sy = 0.0;
+    T qdx = 0, qdy = 0, qxx = 0, qxy = 0, qyy = 0;  // second moments on every 4th tile, shifted by the first sample
+    T amax = 0;                                     // max |coordinate| (bounds the fp32 screening error)
     const V2 first = sm[0];
-    int base = 0;
-#pragma unroll 2
-    for (; base + kLanes <= N; base += kLanes) {
-      const V2 v0 = sm[base + tid];
-      const V2 v1 = sm[base + kThreads + tid];
-      sx0 = __dadd_rn(sx0, static_cast<double>(v0.x));
-      sy0 = __dadd_rn(sy0, static_cast<double>(v0.y));
-      sx1 = __dadd_rn(sx1, static_cast<double>(v1.x));
-      sy1 = __dadd_rn(sy1, static_cast<double>(v1.y));
-      const T dx = v0.x - first.x, dy = v0.y - first.y;
-      qdx += dx;
-      qdy += dy;
-      qxx += dx * dx;
-      qxy += dx * dy;
-      qyy += dy * dy;
-    }
-    if (base + tid < N) {
-      const V2 v0 = sm[base + tid];
-      sx0 = __dadd_rn(sx0, static_cast<double>(v0.x));
-      sy0 = __dadd_rn(sy0, static_cast<double>(v0.y));
-      const T dx = v0.x - first.x, dy = v0.y - first.y;
-      qdx += dx;
-      qdy += dy;
-      qxx += dx * dx;
-      qxy += dx * dy;
-      qyy += dy * dy;
-    }
-    if (base + kThreads + tid < N) {
-      const V2 v1 = sm[base + kThreads + tid];
-      sx1 = __dadd_rn(sx1, static_cast<double>(v1.x));
-      sy1 = __dadd_rn(sy1, static_cast<double>(v1.y));
+    {
+      auto moments = [&](const V2 v) {
+        const T dx = v.x - first.x, dy = v.y - first.y;
+        qdx += dx;
+        qdy += dy;
+        qxx = fma(dx, dx, qxx);
+        qxy = fma(dx, dy, qxy);
+        qyy = fma(dy, dy, qyy);
+      };
+      auto accum = [&](const V2 v) {
+        sx = __dadd_rn(sx, static_cast<double>(v.x));
+        sy = __dadd_rn(sy, static_cast<double>(v.y));
+        amax = fmax(amax, fmax(fabs(v.x), fabs(v.y)));
+      };
+      int i = tid;
+      for (; i + 3 * kThreads < N; i += 4 * kThreads) {
+        const V2 v0 = sm[i], v1 = sm[i + kThreads], v2 = sm[i + 2 * kThreads], v3 = sm[i + 3 * kThreads];
+        accum(v0);
+        accum(v1);
+        accum(v2);
+        accum(v3);
+        moments(v0);
+      }
+      bool lead = true;
+      for (; i < N; i += kThreads) {
+        const V2 v = sm[i];
+        accum(v);
+        if (lead) moments(v);
+        lead = false;
+      }
     }
     {
-      // canonical: t[l] = s[l] + s[l+256]; xor-butterfly in each warp; ((w0+w1)+(w2+w3))+((w4+w5)+(w6+w7))
-      const double tx = warp_sum_canon(__dadd_rn(sx0, sx1));
-      const double ty = warp_sum_canon(__dadd_rn(sy0, sy1));
-      const double mdx = warp_sum_any(static_cast<double>(qdx));
-      const double mdy = warp_sum_any(static_cast<double>(qdy));
-      const double mxx = warp_sum_any(static_cast<double>(qxx));
-      const double mxy = warp_sum_any(static_cast<double>(qxy));
-      const double myy = warp_sum_any(static_cast<double>(qyy));
+      // canonical: xor-butterfly inside each warp (= group of 32 lanes); the 16 warp totals are tree-added below
+      const double tx = warp_sum_canon(sx);
+      const double ty = warp_sum_canon(sy);
+      const float mdx = warp_sum_any(static_cast<float>(qdx)), mdy = warp_sum_any(static_cast<float>(qdy));
+      const float mxx = warp_sum_any(static_cast<float>(qxx)), mxy = warp_sum_any(static_cast<float>(qxy));
+      const float myy = warp_sum_any(static_cast<float>(qyy));
+      float mx = static_cast<float>(amax);
+      if (static_cast<T>(mx) < amax) mx = __uint_as_float(__float_as_uint(mx) + 1);  // round up (T = double)
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, m));
       if (lane == 0) {
         double* w = red + warp * 8;
-        w[0] = tx; w[1] = ty; w[2] = mdx; w[3] = mdy; w[4] = mxx; w[5] = mxy; w[6] = myy;
+        w[0] = tx; w[1] = ty; w[2] = mdx; w[3] = mdy; w[4] = mxx; w[5] = mxy; w[6] = myy; w[7] = mx;
+      }
+      if (warp == 1 && lane < kHistBuckets / 32) {
+        // nothing: hist is cleared below by warps that do not compute the direction
       }
     }
     __syncthreads();
 
-    // ------------------------------------------------------------------ direction + window (warp 0, lane-redundant)
+    // ------------------------------------------------------------------ direction + window (warp 0); others clear hist
     if (warp == 0) {
       double w[7];
 #pragma unroll
       for (int j = 0; j < 7; ++j) {
-        const double a0 = red[0 * 8 + j], a1 = red[1 * 8 + j], a2 = red[2 * 8 + j], a3 = red[3 * 8 + j];
-        const double a4 = red[4 * 8 + j], a5 = red[5 * 8 + j], a6 = red[6 * 8 + j], a7 = red[7 * 8 + j];
-        w[j] = __dadd_rn(__dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3)), __dadd_rn(__dadd_rn(a4, a5), __dadd_rn(a6, a7)));
+        double t[kWarps];
+#pragma unroll
+        for (int q = 0; q < kWarps; ++q) t[q] = red[q * 8 + j];
+#pragma unroll
+        for (int n = kWarps; n > 1; n >>= 1)
+#pragma unroll
+          for (int q = 0; q < n / 2; ++q) t[q] = __dadd_rn(t[2 * q], t[2 * q + 1]);  // adjacent-pair tree
+        w[j] = t[0];
       }
+      float mx = 0.f;
+#pragma unroll
+      for (int q = 0; q < kWarps; ++q) mx = fmaxf(mx, static_cast<float>(red[q * 8 + 7]));
       const double m0 = __ddiv_rn(w[0], static_cast<double>(N));
       const double m1 = __ddiv_rn(w[1], static_cast<double>(N));
       int nonfinite = !(isfinite(m0) && isfinite(m1));
@@ -348,7 +377,6 @@ __global__ void __launch_bounds__(kThreads) halfspace_kernel(const KernelArgs a)
       if (a.h_in != nullptr) {
         h0 = a.h_in[2 * b];
         h1 = a.h_in[2 * b + 1];
-        nonfinite |= !(isfinite(h0) && isfinite(h1));
       } else {
         const double e0 = a.ego ? a.ego[2 * b] : 0.0, e1 = a.ego ? a.ego[2 * b + 1] : 0.0;
         const double d0 = __dsub_rn(m0, e0), d1 = __dsub_rn(m1, e1);
@@ -361,25 +389,36 @@ __global__ void __launch_bounds__(kThreads) halfspace_kernel(const KernelArgs a)
           h0 = __ddiv_rn(d0, nrm);
           h1 = __ddiv_rn(d1, nrm);
         }
-        nonfinite |= !(isfinite(h0) && isfinite(h1));
       }
+      nonfinite |= !(isfinite(h0) && isfinite(h1));
       // heuristic window around the expected kc-th largest loss (affects speed only, never the result)
-      const int full_tiles = N / kLanes, rem = N - full_tiles * kLanes;
-      const double n_sub = static_cast<double>(full_tiles * kThreads + (rem < kThreads ? rem : kThreads));
+      const int groups = N / (4 * kThreads), rem = N - groups * 4 * kThreads;
+      const double n_sub = static_cast<double>(groups * kThreads + (rem < kThreads ? rem : kThreads));
       const double ex = w[2] / n_sub, ey = w[3] / n_sub;
       const double cxx = w[4] / n_sub - ex * ex, cxy = w[5] / n_sub - ex * ey, cyy = w[6] / n_sub - ey * ey;
       const double var_l = h0 * h0 * cxx + 2.0 * h0 * h1 * cxy + h1 * h1 * cyy;
       const double mu_l = -(h0 * m0 + h1 * m1);
       const double sigma = static_cast<double>(sqrtf(static_cast<float>(var_l)));
-      const int window_ok = a.use_window && (var_l > 0.0) && isfinite(sigma) && !nonfinite;
+      const int window_ok = a.use_window && (var_l > 0.0) && isfinite(sigma) && !nonfinite && (N <= kMaxPerThread * kThreads);
+      const double t_lo = __dadd_rn(mu_l + a.z_lo * sigma, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
+      const double t_hi = __dadd_rn(mu_l + a.z_hi * sigma, 0.0);
+      // fp32 screen: keep sample iff p32 <= thr, where p32 = fma(h1f, y, h0f*x) approximates p = h.xi = -L.
+      // |p32 - p| <= 4 * 2^-24 * (|h0| + |h1|) * max|coord|; we allow 2^-19 (32x) plus the rounding of -t_lo.
+      const float h0f = static_cast<float>(h0), h1f = static_cast<float>(h1);
+      const float bound = (fabsf(h0f) + fabsf(h1f)) * mx * 1.9073486e-06f + fabsf(static_cast<float>(t_lo)) * 2.3841858e-07f;
+      const float thr = static_cast<float>(-t_lo) + bound + 1.1754944e-38f;
       if (lane == 0) {
         ctl->h0 = h0; ctl->h1 = h1; ctl->m0 = m0; ctl->m1 = m1;
-        ctl->t_lo = __dadd_rn(mu_l + a.z_lo * sigma, 0.0);  // +0.0: never -0.0 (keys of canonical losses are +0)
-        ctl->t_hi = __dadd_rn(mu_l + a.z_hi * sigma, 0.0);
-        ctl->window_ok = window_ok;
+        ctl->t_lo = t_lo;
+        ctl->t_hi = t_hi;
+        ctl->h0f = h0f; ctl->h1f = h1f; ctl->screen_thr = thr;
+        ctl->window_ok = window_ok && isfinite(thr);
         ctl->nonfinite = nonfinite;
         ctl->degenerate = degenerate;
+        ctl->small_n = 0;
       }
+    } else if (warp >= kWarps - kHistBuckets / 32) {
+      hist[tid - (kThreads - kHistBuckets)] = 0;  // last 8 warps clear the 256-bucket histogram
     }
     __syncthreads();
     const double h0 = ctl->h0, h1 = ctl->h1;
@@ -395,35 +434,84 @@ __global__ void __launch_bounds__(kThreads) halfspace_kernel(const KernelArgs a)
 
     if (!nonfinite) {
       // ---------------------------------------------------------------- sweep B (window path)
-      int nc = 0;
       if (window) {
-        auto visit = [&](const V2 v) {
-          const double L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
-          if (L > t_hi) {
+        int nc = 0;  // candidates of this warp (warp-uniform)
+        auto classify = [&](bool active, double L) {
+          const bool hi = active && (L > t_hi);
+          const bool cd = active && !hi && (L >= t_lo);
+          if (hi) {
             ++c_gt;
             s_gt += L;
-          } else if (L >= t_lo) {
-            if (nc < kCandCap) cand[nc * kThreads + tid] = L;
-            ++nc;
+          }
+          const unsigned bal = __ballot_sync(kFull, cd);
+          if (bal) {
+            const int pos = nc + __popc(bal & ((1u << lane) - 1u));
+            if (cd && pos < kWarpCand) wcand[pos] = L;
+            nc += __popc(bal);
           }
         };
-        int bb = 0;
-#pragma unroll 2
-        for (; bb + kLanes <= N; bb += kLanes) {
-          const V2 v0 = sm[bb + tid];
-          const V2 v1 = sm[bb + kThreads + tid];
-          visit(v0);
-          visit(v1);
+        if constexpr (sizeof(T) == 4) {
+          // phase 1: fp32 screen -> per-thread survivor mask (bit j <-> sample tid + 512 j)
+          const float h0f = ctl->h0f, h1f = ctl->h1f, thr = ctl->screen_thr;
+          unsigned mlo = 0, mhi = 0;
+          {
+            int i = tid;
+            unsigned bit = 1u;
+            int j = 0;
+            for (; i + 3 * kThreads < N && j < 32; i += 4 * kThreads, j += 4, bit <<= 4) {
+              const V2 v0 = sm[i], v1 = sm[i + kThreads], v2 = sm[i + 2 * kThreads], v3 = sm[i + 3 * kThreads];
+              if (fmaf(h1f, v0.y, h0f * v0.x) <= thr) mlo |= bit;
+              if (fmaf(h1f, v1.y, h0f * v1.x) <= thr) mlo |= bit << 1;
+              if (fmaf(h1f, v2.y, h0f * v2.x) <= thr) mlo |= bit << 2;
+              if (fmaf(h1f, v3.y, h0f * v3.x) <= thr) mlo |= bit << 3;
+            }
+            for (; i < N && j < 32; i += kThreads, ++j, bit <<= 1)
+              if (fmaf(h1f, sm[i].y, h0f * sm[i].x) <= thr) mlo |= bit;
+            bit = 1u;
+            for (; i + 3 * kThreads < N; i += 4 * kThreads, bit <<= 4) {
+              const V2 v0 = sm[i], v1 = sm[i + kThreads], v2 = sm[i + 2 * kThreads], v3 = sm[i + 3 * kThreads];
+              if (fmaf(h1f, v0.y, h0f * v0.x) <= thr) mhi |= bit;
+              if (fmaf(h1f, v1.y, h0f * v1.x) <= thr) mhi |= bit << 1;
+              if (fmaf(h1f, v2.y, h0f * v2.x) <= thr) mhi |= bit << 2;
+              if (fmaf(h1f, v3.y, h0f * v3.x) <= thr) mhi |= bit << 3;
+            }
+            for (; i < N; i += kThreads, bit <<= 1)
+              if (fmaf(h1f, sm[i].y, h0f * sm[i].x) <= thr) mhi |= bit;
+          }
+          // phase 2: canonical fp64 loss of the survivors, warp-lockstep over each lane's k-th survivor
+          for (int word = 0; word < 2; ++word) {
+            unsigned m = word ? mhi : mlo;
+            while (__any_sync(kFull, m != 0)) {
+              const bool active = m != 0;
+              double L = 0.0;
+              if (active) {
+                const int j = __ffs(m) - 1 + 32 * word;
+                m &= m - 1;
+                const V2 v = sm[tid + kThreads * j];
+                L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
+              }
+              classify(active, L);
+            }
+          }
+        } else {
+          // fp64 inputs: no conversions to save, every sample takes the canonical path
+          for (int base = 0; base < N; base += kThreads) {
+            const int i = base + tid;
+            const bool active = i < N;
+            double L = 0.0;
+            if (active) {
+              const V2 v = sm[i];
+              L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
+            }
+            classify(active, L);
+          }
         }
-        if (bb + tid < N) visit(sm[bb + tid]);
-        if (bb + kThreads + tid < N) visit(sm[bb + kThreads + tid]);
         const int wc = __reduce_add_sync(kFull, c_gt);
-        const int wn = __reduce_add_sync(kFull, nc < kCandCap ? nc : kCandCap);
         if (lane == 0) {
           ired[warp * 2] = wc;
-          ired[warp * 2 + 1] = wn;
+          ired[warp * 2 + 1] = nc < kWarpCand ? nc : kWarpCand;
         }
-        const int ovf = __syncthreads_or(nc > kCandCap);
+        const int ovf = __syncthreads_or(nc > kWarpCand);
         int cnt_hi = 0, ncand = 0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
@@ -435,14 +523,13 @@ __global__ void __launch_bounds__(kThreads) halfspace_kernel(const KernelArgs a)
           // the sample slot is dead from here on: prefetch the next halfspace under the select phase
           if (!kTail && a.bulk && tid == 0 && b_next < a.B) issue_bulk(b_next);
           next_issued = !kTail && a.bulk;
-          const int mine = nc;
           T_thr = select_rank(
               [&](auto&& f) {
-                for (int j = 0; j < mine; ++j) f(cand[j * kThreads + tid]);
+                for (int j = lane; j < nc; j += 32) f(wcand[j]);
               },
-              key_of(t_lo), key_of(t_hi), a.kc - cnt_hi, hist, small, ctl);
-          for (int j = 0; j < mine; ++j) {
-            const double L = cand[j * kThreads + tid];
+              key_of(t_lo), key_of(t_hi), a.kc - cnt_hi, hist, small, ctl, true);
+          for (int j = lane; j < nc; j += 32) {
+            const double L = wcand[j];
             if (L > T_thr) {
               ++c_gt;
               s_gt += L;
@@ -485,7 +572,7 @@ __global__ void __launch_bounds__(kThreads) halfspace_kernel(const KernelArgs a)
                 f(loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y)));
               }
             },
-            kmin, kmax, a.kc, hist, small, ctl);
+            kmin, kmax, a.kc, hist, small, ctl, false);
         c_gt = 0;
         s_gt = 0.0;
         for (int i = tid; i < N; i += kThreads) {

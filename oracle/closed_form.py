@@ -26,8 +26,9 @@ What is restated (reference file:line, relative to /root/reference):
 CANONICAL ARITHMETIC (the reference's BLAS matvec / np.mean are not bit-reproducible, so the
 oracle DEFINES the arithmetic the CUDA path must reproduce bit-for-bit where order matters):
   * sums for the sample mean: 512 lanes, lane l accumulates samples i = l (mod 512) in
-    increasing i; lanes are combined by   t[l] = s[l] + s[l+256]  (l < 256), an xor-butterfly
-    (1,2,4,8,16) inside each group of 32, then ((w0+w1)+(w2+w3))+((w4+w5)+(w6+w7)).
+    increasing i; each group of 32 consecutive lanes is combined by an xor-butterfly
+    (1,2,4,8,16); the 16 group totals w0..w15 are combined by an adjacent-pair tree
+    (((w0+w1)+(w2+w3))+((w4+w5)+(w6+w7))) + (((w8+w9)+(w10+w11))+((w12+w13)+(w14+w15))).
   * projection  p_i = rn(rn(h0*x_i) + rn(h1*y_i))  (no FMA);  loss  L_i = -p_i.
   * tail: k_f = alpha*N (snapped to the nearest integer when within 1e-9 relative),
     kc = ceil(k_f); T = kc-th largest loss; index set = {L_i > T} U lowest-index ties, |set| = kc
@@ -62,12 +63,13 @@ def canonical_sum(v) -> float:
     s = np.zeros(LANES, dtype=np.float64)
     for r in range(rows):  # sequential per lane, increasing sample index
         s = s + a[r]
-    t = s[:256] + s[256:]
-    w = t.reshape(8, 32)
+    w = s.reshape(LANES // 32, 32)
     for x in (1, 2, 4, 8, 16):
         w = w + w[:, _XOR_IDX[x]]
     w = w[:, 0]
-    return float(((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7])))
+    while w.shape[0] > 1:          # adjacent-pair tree over the 16 group totals
+        w = w[0::2] + w[1::2]
+    return float(w[0])
 
 
 def canonical_mean(samples) -> np.ndarray:
