@@ -2,16 +2,20 @@
 //
 // One CTA (512 threads) per (scenario, obstacle, step) halfspace, persistent over the batch.  Per halfspace:
 //   stage   N samples -> shared memory with cp.async.bulk (TMA bulk copy, mbarrier completion) or a strided loader
-//   sweep A canonical 512-lane fp64 sums of x,y (+ heuristic second moments, max |coordinate|)  -> mean m
+//   sweep A canonical lane sums of x,y (fp32 inputs: packed fp32 lane partials, fp64 cross-lane tree;
+//           fp64 inputs: fp64 throughout) + heuristic second moments + max |coordinate|          -> mean m
 //   h       = unit(m - ego)                                                            core/geometry.py:35-53
-//   sweep B fp32 inputs: a rigorous fp32 screen keeps only samples that can reach the candidate window, then
-//           the survivors get the canonical fp64 loss L_i = -(h.xi_i) (no FMA); losses above the window are
-//           counted/summed, losses inside it go to warp-private candidate lists
-//   select  exact kc-th largest loss T by adaptive range-narrowing radix select on order-preserving u64 keys
+//   sweep B classify every sample against a statistical window [t_lo, t_hi] around the expected kc-th largest
+//           loss.  fp32 inputs: a rigorous fp32 bound decides "surely above" (count + raw coordinate sums; the
+//           loss sum follows from linearity), "surely below" (ignored) or "needs the exact fp64 loss" (a bit in a
+//           per-thread mask).  fp64 inputs: exact canonical loss for every sample.
+//   phase 2 masked samples get the canonical fp64 loss L_i = -(h.xi_i) (no FMA); window losses go to warp-private
+//           candidate lists and a 256-bucket histogram over the window
+//   select  exact kc-th largest loss T: histogram scan -> bucket -> rank resolve by one warp (general fallback:
+//           adaptive range-narrowing radix select on order-preserving u64 keys over all samples)
 //   finish  CVaR = (sum_{L>T} L + (k_f - #{L>T}) T) / k_f  and the three offsets        core/risk_metrics.py:84-338
-// The window and the screen only decide HOW FAST the exact answer is found; a miss is detected and the general
-// multi-sweep select runs instead.  The arithmetic contract (what is bit-identical to oracle/closed_form.py) is
-// in DESIGN.md.
+// The window and the fp32 bound only decide HOW FAST the exact threshold is found; a miss is detected and the
+// general multi-sweep select runs instead.  The arithmetic contract is in DESIGN.md / oracle/closed_form.py.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -21,11 +25,11 @@ namespace drcvar {
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kLanes = 512;          // canonical summation lanes (one per thread)
-constexpr int kWarpCand = 128;       // candidate slots per warp (window path)
+constexpr int kLanes = 512;          // canonical cross-lane tree width (fp32 inputs: 1024 fp32 lanes, paired)
+constexpr int kWarpCand = 96;        // candidate losses per warp (window path)
+constexpr int kWarpList = 160;       // masked sample indices per warp (window path)
 constexpr int kHistBuckets = 256;
 constexpr int kResolveMax = 32;      // a bucket this small is resolved by one warp
-constexpr int kMaxPerThread = 64;    // screening mask is 64 bits: N <= 64 * 512
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kBulkChunk = 32768;
 
@@ -57,11 +61,13 @@ struct KernelArgs {
 
 struct Ctl {
   unsigned long long mbar;
+  unsigned long long key_lo;       // key(t_lo): histogram origin
   double T;
   double h0, h1, t_lo, t_hi, m0, m1;
-  float h0f, h1f, screen_thr, pad0;
+  float h0f, h1f, thr_above, thr_keep;
+  int hist_shift;
   int bstar, rprime, cnt_in, small_n;
-  int window_ok, nonfinite, degenerate, pad1;
+  int window_ok, nonfinite, degenerate, c_tot, pad;
 };
 
 template <typename T> struct Vec2;
@@ -74,12 +80,14 @@ __host__ __device__ inline size_t slot_bytes_for(long long n, size_t elem_bytes)
 }
 constexpr int kRedDoubles = kWarps * 8;  // per buffer
 __host__ __device__ inline size_t fixed_smem_bytes() {
-  return sizeof(double) * kWarpCand * kWarps        // cand
-         + sizeof(unsigned) * kHistBuckets          // hist
-         + sizeof(double) * 2 * kRedDoubles         // red (double-buffered)
-         + sizeof(double) * kResolveMax             // small
-         + sizeof(int) * 4 * kWarps                 // ired
-         + sizeof(Ctl);
+  return sizeof(double) * kWarpCand * kWarps          // cand
+         + sizeof(unsigned short) * kWarpList * kWarps  // list
+         + sizeof(unsigned) * kHistBuckets            // hist
+         + sizeof(double) * 2 * kRedDoubles           // red (double-buffered by iteration parity)
+         + sizeof(double) * 2 * kRedDoubles           // fin (double-buffered): per-warp finals
+         + sizeof(double) * 2 * kResolveMax           // small (double-buffered)
+         + sizeof(int) * 4 * kWarps                   // ired
+         + 2 * sizeof(Ctl);                           // ctl (double-buffered)
 }
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -150,32 +158,28 @@ __device__ __forceinline__ double warp_sum_canon(double v) {  // xor 1,2,4,8,16 
   for (int m = 1; m <= 16; m <<= 1) v = __dadd_rn(v, shfl_xor_d(v, m));
   return v;
 }
+__device__ __forceinline__ float absmax3(float m, float a, float b) { return fmaxf(m, fmaxf(fabsf(a), fabsf(b))); }
 
-// Exact r-th largest (1-based) among the enumerated losses whose keys lie in [lo, hi].
+// Exact r-th largest (1-based) among the enumerated losses whose keys lie in [lo, hi] (general machinery).
 // for_each(f) must call f(L) for every candidate owned by the calling thread; all threads must call this.
-// `hist` must be zero on entry (it is left dirty).
 template <class ForEach>
 __device__ double select_rank(ForEach&& for_each, unsigned long long lo, unsigned long long hi, int r,
-                              unsigned* hist, double* small, Ctl* ctl, bool hist_clean) {
+                              unsigned* hist, double* small, Ctl* ctl) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (;;) {
     const unsigned long long span = hi - lo;
     if (span == 0) return value_of(lo);
     const int bits = 64 - __clzll(static_cast<long long>(span));
     const int shift = bits > 8 ? bits - 8 : 0;  // (span >> shift) < 256
-    if (!hist_clean) {
-      if (tid < kHistBuckets) hist[tid] = 0;
-      if (tid == 0) ctl->small_n = 0;
-      __syncthreads();
-    }
-    hist_clean = false;
+    if (tid < kHistBuckets) hist[tid] = 0;
+    if (tid == 0) ctl->small_n = 0;
+    __syncthreads();
     for_each([&](double L) {
       const unsigned long long k = key_of(L);
       if (k >= lo && k <= hi) atomicAdd(&hist[static_cast<unsigned>((k - lo) >> shift)], 1u);
     });
     __syncthreads();
     if (warp == 0) {
-      // rows of 32 buckets, row 0 = top; lane l of row i is bucket 255 - (32 i + l)
       int run = 0, row = -1, r_row = 0;
 #pragma unroll
       for (int i = 0; i < kHistBuckets / 32; ++i) {
@@ -239,33 +243,42 @@ __device__ double select_rank(ForEach&& for_each, unsigned long long lo, unsigne
 template <typename T, bool kTail>
 __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs a) {
   using V2 = typename Vec2<T>::type;
+  constexpr bool kF32 = sizeof(T) == 4;
+  // samples one thread touches per row: fp32 -> one float4 = samples (2t, 2t+1) of a 1024-sample tile;
+  // fp64 -> one double2 = sample t of a 512-sample tile
+  constexpr int kPerRow = kF32 ? 2 : 1;
+  constexpr int kTile = kThreads * kPerRow;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
   const size_t slot_bytes = slot_bytes_for(N, sizeof(T));
   V2* sm = reinterpret_cast<V2*>(smem_raw);
   double* cand = reinterpret_cast<double*>(smem_raw + slot_bytes);
-  unsigned* hist = reinterpret_cast<unsigned*>(cand + kWarpCand * kWarps);
+  unsigned short* list = reinterpret_cast<unsigned short*>(cand + kWarpCand * kWarps);
+  unsigned* hist = reinterpret_cast<unsigned*>(list + kWarpList * kWarps);
   double* red_base = reinterpret_cast<double*>(hist + kHistBuckets);
-  double* small = red_base + 2 * kRedDoubles;
-  int* ired = reinterpret_cast<int*>(small + kResolveMax);
-  Ctl* ctl = reinterpret_cast<Ctl*>(ired + 4 * kWarps);
+  double* fin_base = red_base + 2 * kRedDoubles;
+  double* small_base = fin_base + 2 * kRedDoubles;
+  int* ired = reinterpret_cast<int*>(small_base + 2 * kResolveMax);
+  Ctl* ctl_base = reinterpret_cast<Ctl*>(ired + 4 * kWarps);
+  unsigned long long* mbar = &ctl_base[0].mbar;
   double* wcand = cand + warp * kWarpCand;
+  unsigned short* wlist = list + warp * kWarpList;
 
   const uint32_t copy_bytes = static_cast<uint32_t>(static_cast<size_t>(N) * sizeof(V2));
   auto issue_bulk = [&](long long b) {
     const unsigned char* src =
         reinterpret_cast<const unsigned char*>(a.samples) + static_cast<size_t>(b) * a.stride_b * sizeof(T);
-    mbar_expect_tx(&ctl->mbar, copy_bytes);
+    mbar_expect_tx(mbar, copy_bytes);
     for (uint32_t off = 0; off < copy_bytes; off += kBulkChunk) {
       const uint32_t n = copy_bytes - off < kBulkChunk ? copy_bytes - off : kBulkChunk;
-      bulk_g2s(smem_raw + off, src + off, n, &ctl->mbar);
+      bulk_g2s(smem_raw + off, src + off, n, mbar);
     }
   };
 
   if (a.bulk) {
     if (tid == 0) {
-      mbar_init(&ctl->mbar, 1);
+      mbar_init(mbar, 1);
       mbar_fence_init();
     }
     __syncthreads();
@@ -275,13 +288,17 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   int iter = 0;
 
   for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
-    double* red = red_base + (iter & 1) * kRedDoubles;
+    const int par = iter & 1;
+    double* red = red_base + par * kRedDoubles;
+    double* fin = fin_base + par * kRedDoubles;
+    double* small = small_base + par * kResolveMax;
+    Ctl* ctl = ctl_base + par;
     bool next_issued = false;
     const long long b_next = b + gridDim.x;
 
     // ------------------------------------------------------------------ stage
     if (a.bulk) {
-      mbar_wait(&ctl->mbar, phase);
+      mbar_wait(mbar, phase);
       phase ^= 1u;
     } else {
       const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
@@ -296,11 +313,57 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     }
 
     // ------------------------------------------------------------------ sweep A: canonical lane sums (+ heuristics)
-    double sx = 0.0, sy = 0.0;
-    T qdx = 0, qdy = 0, qxx = 0, qxy = 0, qyy = 0;  // second moments on every 4th tile, shifted by the first sample
-    T amax = 0;                                     // max |coordinate| (bounds the fp32 screening error)
+    const int rows = (N + kTile - 1) / kTile;
+    const int full_rows = N / kTile;
+    double sx, sy;                                  // this thread's contribution to the 512-wide fp64 tree
+    T qdx = 0, qdy = 0, qxx = 0, qxy = 0, qyy = 0;  // second moments (warps 0-3 only), shifted by the first sample
+    float amax = 0.f;                               // max |coordinate| (bounds the fp32 classification error)
     const V2 first = sm[0];
-    {
+    if constexpr (kF32) {
+      const float4* sm4 = reinterpret_cast<const float4*>(smem_raw);
+      float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);  // lanes 2t and 2t+1, fp32 partial sums
+      auto accum = [&](const float4 v) {
+        a0 = __fadd2_rn(a0, make_float2(v.x, v.y));
+        a1 = __fadd2_rn(a1, make_float2(v.z, v.w));
+        amax = absmax3(absmax3(amax, v.x, v.y), v.z, v.w);
+      };
+      auto moments = [&](const float4 v) {
+        const float dx0 = v.x - first.x, dy0 = v.y - first.y, dx1 = v.z - first.x, dy1 = v.w - first.y;
+        qdx += dx0 + dx1;
+        qdy += dy0 + dy1;
+        qxx = fmaf(dx0, dx0, fmaf(dx1, dx1, qxx));
+        qxy = fmaf(dx0, dy0, fmaf(dx1, dy1, qxy));
+        qyy = fmaf(dy0, dy0, fmaf(dy1, dy1, qyy));
+      };
+      if (warp < 4) {
+#pragma unroll 2
+        for (int m = 0; m < full_rows; ++m) {
+          const float4 v = sm4[m * kThreads + tid];
+          accum(v);
+          moments(v);
+        }
+      } else {
+#pragma unroll 4
+        for (int m = 0; m < full_rows; ++m) accum(sm4[m * kThreads + tid]);
+      }
+      if (full_rows < rows) {  // ragged last tile: element-wise
+        const int i0 = full_rows * kTile + 2 * tid;
+        if (i0 < N) {
+          const float2 v = sm[i0];
+          a0 = __fadd2_rn(a0, v);
+          amax = absmax3(amax, v.x, v.y);
+        }
+        if (i0 + 1 < N) {
+          const float2 v = sm[i0 + 1];
+          a1 = __fadd2_rn(a1, v);
+          amax = absmax3(amax, v.x, v.y);
+        }
+      }
+      sx = __dadd_rn(static_cast<double>(a0.x), static_cast<double>(a1.x));  // adjacent lanes, in fp64
+      sy = __dadd_rn(static_cast<double>(a0.y), static_cast<double>(a1.y));
+    } else {
+      sx = 0.0;
+      sy = 0.0;
       auto moments = [&](const V2 v) {
         const T dx = v.x - first.x, dy = v.y - first.y;
         qdx += dx;
@@ -309,54 +372,48 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         qxy = fma(dx, dy, qxy);
         qyy = fma(dy, dy, qyy);
       };
-      auto accum = [&](const V2 v) {
-        sx = __dadd_rn(sx, static_cast<double>(v.x));
-        sy = __dadd_rn(sy, static_cast<double>(v.y));
-        amax = fmax(amax, fmax(fabs(v.x), fabs(v.y)));
-      };
-      int i = tid;
-      for (; i + 3 * kThreads < N; i += 4 * kThreads) {
-        const V2 v0 = sm[i], v1 = sm[i + kThreads], v2 = sm[i + 2 * kThreads], v3 = sm[i + 3 * kThreads];
-        accum(v0);
-        accum(v1);
-        accum(v2);
-        accum(v3);
-        moments(v0);
-      }
-      bool lead = true;
-      for (; i < N; i += kThreads) {
-        const V2 v = sm[i];
-        accum(v);
-        if (lead) moments(v);
-        lead = false;
+      if (warp < 4) {
+#pragma unroll 2
+        for (int i = tid; i < N; i += kThreads) {
+          const V2 v = sm[i];
+          sx = __dadd_rn(sx, v.x);
+          sy = __dadd_rn(sy, v.y);
+          moments(v);
+        }
+      } else {
+#pragma unroll 4
+        for (int i = tid; i < N; i += kThreads) {
+          const V2 v = sm[i];
+          sx = __dadd_rn(sx, v.x);
+          sy = __dadd_rn(sy, v.y);
+        }
       }
     }
     {
-      // canonical: xor-butterfly inside each warp (= group of 32 lanes); the 16 warp totals are tree-added below
+      // canonical: xor-butterfly inside each warp (= group of 32 values); the 16 warp totals are tree-added below
       const double tx = warp_sum_canon(sx);
       const double ty = warp_sum_canon(sy);
-      const float mdx = warp_sum_any(static_cast<float>(qdx)), mdy = warp_sum_any(static_cast<float>(qdy));
-      const float mxx = warp_sum_any(static_cast<float>(qxx)), mxy = warp_sum_any(static_cast<float>(qxy));
-      const float myy = warp_sum_any(static_cast<float>(qyy));
-      float mx = static_cast<float>(amax);
-      if (static_cast<T>(mx) < amax) mx = __uint_as_float(__float_as_uint(mx) + 1);  // round up (T = double)
-#pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, m));
-      if (lane == 0) {
-        double* w = red + warp * 8;
-        w[0] = tx; w[1] = ty; w[2] = mdx; w[3] = mdy; w[4] = mxx; w[5] = mxy; w[6] = myy; w[7] = mx;
+      const unsigned mxb = __reduce_max_sync(kFull, __float_as_uint(amax));
+      double* w = red + warp * 8;
+      if (warp < 4) {
+        const float mdx = warp_sum_any(static_cast<float>(qdx)), mdy = warp_sum_any(static_cast<float>(qdy));
+        const float mxx = warp_sum_any(static_cast<float>(qxx)), mxy = warp_sum_any(static_cast<float>(qxy));
+        const float myy = warp_sum_any(static_cast<float>(qyy));
+        if (lane == 0) {
+          w[2] = mdx; w[3] = mdy; w[4] = mxx; w[5] = mxy; w[6] = myy;
+        }
       }
-      if (warp == 1 && lane < kHistBuckets / 32) {
-        // nothing: hist is cleared below by warps that do not compute the direction
+      if (lane == 0) {
+        w[0] = tx; w[1] = ty; w[7] = static_cast<double>(__uint_as_float(mxb));
       }
     }
-    __syncthreads();
+    __syncthreads();  // S1
 
-    // ------------------------------------------------------------------ direction + window (warp 0); others clear hist
+    // ------------------------------------------------------------------ direction + window (warp 0); warps 8-15 clear hist
     if (warp == 0) {
-      double w[7];
+      double w[2];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) {
+      for (int j = 0; j < 2; ++j) {
         double t[kWarps];
 #pragma unroll
         for (int q = 0; q < kWarps; ++q) t[q] = red[q * 8 + j];
@@ -366,9 +423,12 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           for (int q = 0; q < n / 2; ++q) t[q] = __dadd_rn(t[2 * q], t[2 * q + 1]);  // adjacent-pair tree
         w[j] = t[0];
       }
+      double q[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) q[j] = (red[0 * 8 + 2 + j] + red[1 * 8 + 2 + j]) + (red[2 * 8 + 2 + j] + red[3 * 8 + 2 + j]);
       float mx = 0.f;
 #pragma unroll
-      for (int q = 0; q < kWarps; ++q) mx = fmaxf(mx, static_cast<float>(red[q * 8 + 7]));
+      for (int qq = 0; qq < kWarps; ++qq) mx = fmaxf(mx, static_cast<float>(red[qq * 8 + 7]));
       const double m0 = __ddiv_rn(w[0], static_cast<double>(N));
       const double m1 = __ddiv_rn(w[1], static_cast<double>(N));
       int nonfinite = !(isfinite(m0) && isfinite(m1));
@@ -392,27 +452,38 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       }
       nonfinite |= !(isfinite(h0) && isfinite(h1));
       // heuristic window around the expected kc-th largest loss (affects speed only, never the result)
-      const int groups = N / (4 * kThreads), rem = N - groups * 4 * kThreads;
-      const double n_sub = static_cast<double>(groups * kThreads + (rem < kThreads ? rem : kThreads));
-      const double ex = w[2] / n_sub, ey = w[3] / n_sub;
-      const double cxx = w[4] / n_sub - ex * ex, cxy = w[5] / n_sub - ex * ey, cyy = w[6] / n_sub - ey * ey;
+      // samples that entered the moments: warps 0-3 (threads 0..127), full rows only for fp32 inputs
+      const int n_sub_i = kF32 ? full_rows * 128 * 2
+                               : 128 * (N / kThreads) + ((N % kThreads) < 128 ? (N % kThreads) : 128);
+      const double n_sub = static_cast<double>(n_sub_i > 0 ? n_sub_i : 1);
+      const double ex = q[0] / n_sub, ey = q[1] / n_sub;
+      const double cxx = q[2] / n_sub - ex * ex, cxy = q[3] / n_sub - ex * ey, cyy = q[4] / n_sub - ey * ey;
       const double var_l = h0 * h0 * cxx + 2.0 * h0 * h1 * cxy + h1 * h1 * cyy;
       const double mu_l = -(h0 * m0 + h1 * m1);
       const double sigma = static_cast<double>(sqrtf(static_cast<float>(var_l)));
-      const int window_ok = a.use_window && (var_l > 0.0) && isfinite(sigma) && !nonfinite && (N <= kMaxPerThread * kThreads);
+      int window_ok = a.use_window && (n_sub_i >= 256) && (var_l > 0.0) && isfinite(sigma) && !nonfinite &&
+                      (rows * kPerRow <= 64);
       const double t_lo = __dadd_rn(mu_l + a.z_lo * sigma, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
       const double t_hi = __dadd_rn(mu_l + a.z_hi * sigma, 0.0);
-      // fp32 screen: keep sample iff p32 <= thr, where p32 = fma(h1f, y, h0f*x) approximates p = h.xi = -L.
-      // |p32 - p| <= 4 * 2^-24 * (|h0| + |h1|) * max|coord|; we allow 2^-19 (32x) plus the rounding of -t_lo.
+      // fp32 classification of p32 = fma(h1f, y, h0f*x)  (p = h.xi = -L):
+      //   |p32 - p| <= 4 * 2^-24 * (|h0| + |h1|) * max|coord|; we allow 2^-19 (32x) plus the rounding of the thresholds.
+      //   p32 <  thr_above  =>  L > t_hi  for sure;    p32 > thr_keep  =>  L < t_lo  for sure.
       const float h0f = static_cast<float>(h0), h1f = static_cast<float>(h1);
-      const float bound = (fabsf(h0f) + fabsf(h1f)) * mx * 1.9073486e-06f + fabsf(static_cast<float>(t_lo)) * 2.3841858e-07f;
-      const float thr = static_cast<float>(-t_lo) + bound + 1.1754944e-38f;
+      const float bound = (fabsf(h0f) + fabsf(h1f)) * mx * 1.9073486e-06f + 1.1754944e-38f;
+      const float thr_keep = static_cast<float>(-t_lo) + (bound + fabsf(static_cast<float>(t_lo)) * 2.3841858e-07f);
+      const float thr_above = static_cast<float>(-t_hi) - (bound + fabsf(static_cast<float>(t_hi)) * 2.3841858e-07f);
+      const unsigned long long klo = key_of(t_lo), khi = key_of(t_hi);
+      const unsigned long long span = khi - klo;
+      const int bits = span ? 64 - __clzll(static_cast<long long>(span)) : 0;
+      window_ok = window_ok && isfinite(thr_keep) && isfinite(thr_above) && (khi >= klo);
       if (lane == 0) {
         ctl->h0 = h0; ctl->h1 = h1; ctl->m0 = m0; ctl->m1 = m1;
         ctl->t_lo = t_lo;
         ctl->t_hi = t_hi;
-        ctl->h0f = h0f; ctl->h1f = h1f; ctl->screen_thr = thr;
-        ctl->window_ok = window_ok && isfinite(thr);
+        ctl->h0f = h0f; ctl->h1f = h1f; ctl->thr_keep = thr_keep; ctl->thr_above = thr_above;
+        ctl->key_lo = klo;
+        ctl->hist_shift = bits > 8 ? bits - 8 : 0;
+        ctl->window_ok = window_ok;
         ctl->nonfinite = nonfinite;
         ctl->degenerate = degenerate;
         ctl->small_n = 0;
@@ -420,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     } else if (warp >= kWarps - kHistBuckets / 32) {
       hist[tid - (kThreads - kHistBuckets)] = 0;  // last 8 warps clear the 256-bucket histogram
     }
-    __syncthreads();
+    __syncthreads();  // S2
     const double h0 = ctl->h0, h1 = ctl->h1;
     const bool nonfinite = ctl->nonfinite != 0;
     const bool window = ctl->window_ok != 0;
@@ -428,90 +499,142 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     int status = (nonfinite ? kStatusNonfinite : 0) | (ctl->degenerate ? kStatusDegenerate : 0);
 
     double T_thr = 0.0;
-    int c_gt = 0;
-    double s_gt = 0.0;
+    int c_gt = 0;        // exact-classified losses above the threshold (this thread)
+    double s_gt = 0.0;   // their sum
     bool fast = false;
+    bool finished_by_warp0 = false;
 
     if (!nonfinite) {
-      // ---------------------------------------------------------------- sweep B (window path)
       if (window) {
-        int nc = 0;  // candidates of this warp (warp-uniform)
-        auto classify = [&](bool active, double L) {
-          const bool hi = active && (L > t_hi);
-          const bool cd = active && !hi && (L >= t_lo);
-          if (hi) {
-            ++c_gt;
-            s_gt += L;
-          }
-          const unsigned bal = __ballot_sync(kFull, cd);
-          if (bal) {
-            const int pos = nc + __popc(bal & ((1u << lane) - 1u));
-            if (cd && pos < kWarpCand) wcand[pos] = L;
-            nc += __popc(bal);
-          }
-        };
-        if constexpr (sizeof(T) == 4) {
-          // phase 1: fp32 screen -> per-thread survivor mask (bit j <-> sample tid + 512 j)
-          const float h0f = ctl->h0f, h1f = ctl->h1f, thr = ctl->screen_thr;
-          unsigned mlo = 0, mhi = 0;
-          {
-            int i = tid;
-            unsigned bit = 1u;
-            int j = 0;
-            for (; i + 3 * kThreads < N && j < 32; i += 4 * kThreads, j += 4, bit <<= 4) {
-              const V2 v0 = sm[i], v1 = sm[i + kThreads], v2 = sm[i + 2 * kThreads], v3 = sm[i + 3 * kThreads];
-              if (fmaf(h1f, v0.y, h0f * v0.x) <= thr) mlo |= bit;
-              if (fmaf(h1f, v1.y, h0f * v1.x) <= thr) mlo |= bit << 1;
-              if (fmaf(h1f, v2.y, h0f * v2.x) <= thr) mlo |= bit << 2;
-              if (fmaf(h1f, v3.y, h0f * v3.x) <= thr) mlo |= bit << 3;
+        // -------------------------------------------------------------- sweep B: classify, build the exact-needed mask
+        unsigned mlo = 0, mhi = 0;
+        int c32 = 0;                                 // "surely above" by the fp32 bound
+        float2 ab = make_float2(0.f, 0.f);           // their raw coordinate sums (loss sum follows by linearity)
+        if constexpr (kF32) {
+          const float4* sm4 = reinterpret_cast<const float4*>(smem_raw);
+          const float h0f = ctl->h0f, h1f = ctl->h1f, thr_keep = ctl->thr_keep, thr_above = ctl->thr_above;
+          auto classify2 = [&](const float4 v, unsigned& mask, const unsigned bit) {
+            const float p0 = fmaf(h1f, v.y, h0f * v.x), p1 = fmaf(h1f, v.w, h0f * v.z);
+            const bool up0 = p0 < thr_above, up1 = p1 < thr_above;
+            if (up0) { ab = __fadd2_rn(ab, make_float2(v.x, v.y)); ++c32; }
+            if (up1) { ab = __fadd2_rn(ab, make_float2(v.z, v.w)); ++c32; }
+            if (!up0 && p0 <= thr_keep) mask |= bit;
+            if (!up1 && p1 <= thr_keep) mask |= bit << 1;
+          };
+          int m = 0;
+          const int lo_rows = full_rows < 16 ? full_rows : 16;
+          unsigned bit = 1u;
+#pragma unroll 4
+          for (; m < lo_rows; ++m, bit <<= 2) classify2(sm4[m * kThreads + tid], mlo, bit);
+          bit = 1u;
+#pragma unroll 4
+          for (; m < full_rows; ++m, bit <<= 2) classify2(sm4[m * kThreads + tid], mhi, bit);
+          if (full_rows < rows) {  // ragged last tile
+            const int i0 = full_rows * kTile + 2 * tid;
+            const unsigned bitr = 1u << (2 * (full_rows & 15));
+            unsigned& mask = full_rows < 16 ? mlo : mhi;
+            if (i0 < N) {
+              const float2 v = sm[i0];
+              const float p = fmaf(h1f, v.y, h0f * v.x);
+              if (p < thr_above) { ab = __fadd2_rn(ab, v); ++c32; }
+              else if (p <= thr_keep) mask |= bitr;
             }
-            for (; i < N && j < 32; i += kThreads, ++j, bit <<= 1)
-              if (fmaf(h1f, sm[i].y, h0f * sm[i].x) <= thr) mlo |= bit;
-            bit = 1u;
-            for (; i + 3 * kThreads < N; i += 4 * kThreads, bit <<= 4) {
-              const V2 v0 = sm[i], v1 = sm[i + kThreads], v2 = sm[i + 2 * kThreads], v3 = sm[i + 3 * kThreads];
-              if (fmaf(h1f, v0.y, h0f * v0.x) <= thr) mhi |= bit;
-              if (fmaf(h1f, v1.y, h0f * v1.x) <= thr) mhi |= bit << 1;
-              if (fmaf(h1f, v2.y, h0f * v2.x) <= thr) mhi |= bit << 2;
-              if (fmaf(h1f, v3.y, h0f * v3.x) <= thr) mhi |= bit << 3;
-            }
-            for (; i < N; i += kThreads, bit <<= 1)
-              if (fmaf(h1f, sm[i].y, h0f * sm[i].x) <= thr) mhi |= bit;
-          }
-          // phase 2: canonical fp64 loss of the survivors, warp-lockstep over each lane's k-th survivor
-          for (int word = 0; word < 2; ++word) {
-            unsigned m = word ? mhi : mlo;
-            while (__any_sync(kFull, m != 0)) {
-              const bool active = m != 0;
-              double L = 0.0;
-              if (active) {
-                const int j = __ffs(m) - 1 + 32 * word;
-                m &= m - 1;
-                const V2 v = sm[tid + kThreads * j];
-                L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
-              }
-              classify(active, L);
+            if (i0 + 1 < N) {
+              const float2 v = sm[i0 + 1];
+              const float p = fmaf(h1f, v.y, h0f * v.x);
+              if (p < thr_above) { ab = __fadd2_rn(ab, v); ++c32; }
+              else if (p <= thr_keep) mask |= bitr << 1;
             }
           }
         } else {
-          // fp64 inputs: no conversions to save, every sample takes the canonical path
-          for (int base = 0; base < N; base += kThreads) {
-            const int i = base + tid;
-            const bool active = i < N;
-            double L = 0.0;
-            if (active) {
-              const V2 v = sm[i];
-              L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
+          unsigned bit = 1u;
+          int m = 0;
+          for (int i = tid; i < N; i += kThreads, ++m, bit = (bit << 1) | (bit >> 31)) {
+            const V2 v = sm[i];
+            const double L = loss_of(h0, h1, v.x, v.y);
+            if (L > t_hi) {
+              ++c_gt;
+              s_gt += L;
+            } else if (L >= t_lo) {
+              if (m < 32) mlo |= bit; else mhi |= bit;
             }
-            classify(active, L);
           }
         }
-        const int wc = __reduce_add_sync(kFull, c_gt);
-        if (lane == 0) {
-          ired[warp * 2] = wc;
-          ired[warp * 2 + 1] = nc < kWarpCand ? nc : kWarpCand;
+
+        // -------------------------------------------------------------- phase 2: compact the masked samples per warp
+        const int mine_n = __popc(mlo) + __popc(mhi);
+        int incl = mine_n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(kFull, incl, d);
+          if (lane >= d) incl += t;
         }
-        const int ovf = __syncthreads_or(nc > kWarpCand);
+        const int n_list = __shfl_sync(kFull, incl, 31);
+        bool overflow = n_list > kWarpList;
+        if (!overflow) {
+          int pos = incl - mine_n;
+          unsigned mm = mlo;
+          while (mm) {
+            const int bitpos = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const int i = kF32 ? ((bitpos >> 1) * kTile + 2 * tid + (bitpos & 1)) : (bitpos * kThreads + tid);
+            wlist[pos++] = static_cast<unsigned short>(i);
+          }
+          mm = mhi;
+          while (mm) {
+            const int bitpos = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const int i = kF32 ? (((bitpos >> 1) + 16) * kTile + 2 * tid + (bitpos & 1)) : ((bitpos + 32) * kThreads + tid);
+            wlist[pos++] = static_cast<unsigned short>(i);
+          }
+        }
+        __syncwarp();
+        // exact canonical loss of the listed samples, dense over the warp; window losses -> candidates + histogram
+        int nc = 0;  // candidates of this warp (warp-uniform)
+        const unsigned long long klo = ctl->key_lo;
+        const int hshift = ctl->hist_shift;
+        if (!overflow) {
+          for (int k0 = 0; k0 < n_list; k0 += 32) {
+            const int k = k0 + lane;
+            const bool active = k < n_list;
+            double L = 0.0;
+            if (active) {
+              const V2 v = sm[wlist[k]];
+              L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
+            }
+            const bool up = active && (L > t_hi);
+            const bool cd = active && !up && (L >= t_lo);
+            if (kF32 && up) {  // (fp64 inputs were classified exactly in sweep B; the list holds candidates only)
+              ++c_gt;
+              s_gt += L;
+            }
+            const unsigned bal = __ballot_sync(kFull, cd);
+            if (bal) {
+              const int pos = nc + __popc(bal & ((1u << lane) - 1u));
+              if (cd && pos < kWarpCand) {
+                wcand[pos] = L;
+                atomicAdd(&hist[static_cast<unsigned>((key_of(L) - klo) >> hshift)], 1u);
+              }
+              nc += __popc(bal);
+            }
+          }
+          overflow = nc > kWarpCand;
+        }
+        // per-warp partials -> fin[]: {exact sum, raw x sum, raw y sum}, ired[]: {exact count + fp32 count, candidates}
+        {
+          const int wc = __reduce_add_sync(kFull, c_gt + c32);
+          const double ws = warp_sum_any(s_gt);
+          const double wx = warp_sum_any(static_cast<double>(ab.x));
+          const double wy = warp_sum_any(static_cast<double>(ab.y));
+          if (lane == 0) {
+            ired[warp * 2] = wc;
+            ired[warp * 2 + 1] = nc;
+            fin[warp * 8 + 0] = ws;
+            fin[warp * 8 + 1] = wx;
+            fin[warp * 8 + 2] = wy;
+          }
+        }
+        const int ovf = __syncthreads_or(overflow);  // S3
         int cnt_hi = 0, ncand = 0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
@@ -520,20 +643,131 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         }
         fast = !ovf && cnt_hi < a.kc && a.kc <= cnt_hi + ncand;
         if (fast) {
-          // the sample slot is dead from here on: prefetch the next halfspace under the select phase
+          // the sample slot is dead from here on (unless tail indices are wanted): prefetch the next halfspace
           if (!kTail && a.bulk && tid == 0 && b_next < a.B) issue_bulk(b_next);
           next_issued = !kTail && a.bulk;
-          T_thr = select_rank(
-              [&](auto&& f) {
-                for (int j = lane; j < nc; j += 32) f(wcand[j]);
-              },
-              key_of(t_lo), key_of(t_hi), a.kc - cnt_hi, hist, small, ctl, true);
-          for (int j = lane; j < nc; j += 32) {
-            const double L = wcand[j];
-            if (L > T_thr) {
-              ++c_gt;
-              s_gt += L;
+          // warp 0: scan the histogram from the top for the bucket holding rank r
+          if (warp == 0) {
+            const int r = a.kc - cnt_hi;
+            int run = 0, row = -1, r_row = 0;
+#pragma unroll
+            for (int i = 0; i < kHistBuckets / 32; ++i) {
+              const int tot = __reduce_add_sync(kFull, static_cast<int>(hist[kHistBuckets - 1 - (32 * i + lane)]));
+              if (row < 0 && run + tot >= r) {
+                row = i;
+                r_row = r - run;
+              }
+              run += tot;
             }
+            if (row < 0) { row = kHistBuckets / 32 - 1; r_row = 1; }
+            const int bucket = kHistBuckets - 1 - (32 * row + lane);
+            const int c = static_cast<int>(hist[bucket]);
+            int inc2 = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const int t = __shfl_up_sync(kFull, inc2, d);
+              if (lane >= d) inc2 += t;
+            }
+            const int excl = inc2 - c;
+            if (excl < r_row && r_row <= inc2) {
+              ctl->bstar = bucket;
+              ctl->rprime = r_row - excl;
+              ctl->cnt_in = c;
+            }
+          }
+          __syncthreads();  // S4
+          const int bstar = ctl->bstar, cnt_in = ctl->cnt_in;
+          if (cnt_in <= kResolveMax) {
+            // candidates above bucket b* are above T; bucket b* goes to one warp for exact ranking
+            double s3 = 0.0;
+            int c3 = 0;
+            for (int j = lane; j < nc; j += 32) {
+              const double L = wcand[j];
+              const int bk = static_cast<int>((key_of(L) - klo) >> hshift);
+              if (bk > bstar) {
+                ++c3;
+                s3 += L;
+              } else if (bk == bstar) {
+                const int pos = atomicAdd(&ctl->small_n, 1);
+                if (pos < kResolveMax) small[pos] = L;
+              }
+            }
+            const int wc3 = __reduce_add_sync(kFull, c3);
+            const double ws3 = warp_sum_any(s3);
+            if (lane == 0) {
+              ired[2 * kWarps + warp] = wc3;
+              fin[warp * 8 + 3] = ws3;
+            }
+            __syncthreads();  // S5
+            finished_by_warp0 = true;
+            if (warp == 0) {
+              // resolve T inside bucket b*: all-pairs rank; then sum the bucket members above T in rank order
+              const int r = ctl->rprime;
+              const double mineL = lane < cnt_in ? small[lane] : 0.0;
+              const unsigned long long mine = lane < cnt_in ? key_of(mineL) : 0ull;
+              int rank = 0;
+              for (int j = 0; j < cnt_in; ++j) {
+                const unsigned long long other = __shfl_sync(kFull, mine, j);
+                rank += (other > mine) || (other == mine && j < lane);
+              }
+              const unsigned owner = __ballot_sync(kFull, lane < cnt_in && rank == r - 1);
+              const double Tval = __shfl_sync(kFull, mineL, __ffs(owner) - 1);
+              // deterministic: place by rank, then butterfly
+              __syncwarp();
+              if (lane < cnt_in) small[rank] = mineL;
+              __syncwarp();
+              const double byrank = (lane < cnt_in && lane < r - 1) ? small[lane] : 0.0;  // ranks 0..r-2 are > or == T
+              const bool strictly = (lane < cnt_in && lane < r - 1) && (key_of(byrank) > key_of(Tval));
+              const double s4 = warp_sum_any(strictly ? byrank : 0.0);
+              const int c4 = __popc(__ballot_sync(kFull, strictly));
+              T_thr = Tval;
+              // totals
+              double s_exact = 0.0, s_x = 0.0, s_y = 0.0, s_c = 0.0;
+              int c_all = cnt_hi + c4;
+#pragma unroll
+              for (int w = 0; w < kWarps; ++w) {
+                s_exact += fin[w * 8 + 0];
+                s_x += fin[w * 8 + 1];
+                s_y += fin[w * 8 + 2];
+                s_c += fin[w * 8 + 3];
+                c_all += ired[2 * kWarps + w];
+              }
+              // loss sum of the "surely above" set by linearity: sum_i -(h.xi_i) = -(h0 sum x + h1 sum y)
+              const double s_lin = -(h0 * s_x + h1 * s_y);
+              s_gt = ((s_exact + s_lin) + s_c) + s4;
+              c_gt = c_all;
+              if (kTail && lane == 0) {
+                ctl->T = T_thr;
+                ctl->c_tot = c_all;
+              }
+            }
+          } else {
+            // a dense / heavily tied bucket: finish with the general narrowing loop on the candidates
+            const unsigned long long lo2 = klo + (static_cast<unsigned long long>(bstar) << hshift);
+            unsigned long long hi2 = lo2 + ((1ull << hshift) - 1ull);
+            const unsigned long long khi = key_of(t_hi);
+            if (hi2 > khi || hi2 < lo2) hi2 = khi;
+            // everything above bucket b* is above T
+            int above_b = 0;
+            for (int j = lane; j < nc; j += 32) above_b += static_cast<int>((key_of(wcand[j]) - klo) >> hshift) > bstar;
+            (void)above_b;
+            T_thr = select_rank(
+                [&](auto&& f) {
+                  for (int j = lane; j < nc; j += 32) f(wcand[j]);
+                },
+                lo2, hi2, ctl->rprime, hist, small, ctl);
+            for (int j = lane; j < nc; j += 32) {
+              const double L = wcand[j];
+              if (L > T_thr) {
+                ++c_gt;
+                s_gt += L;
+              }
+            }
+            // fold the fp32 "surely above" set in (thread 0 of each warp carries the warp's linear part)
+            c_gt += c32;
+            const double wx = warp_sum_any(static_cast<double>(ab.x));
+            const double wy = warp_sum_any(static_cast<double>(ab.y));
+            if (lane == 0) s_gt += -(h0 * wx + h1 * wy);
           }
         }
       }
@@ -572,7 +806,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
                 f(loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y)));
               }
             },
-            kmin, kmax, a.kc, hist, small, ctl, false);
+            kmin, kmax, a.kc, hist, small, ctl);
         c_gt = 0;
         s_gt = 0.0;
         for (int i = tid; i < N; i += kThreads) {
@@ -586,20 +820,30 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       }
     }
 
-    // ------------------------------------------------------------------ block totals of (c_gt, s_gt)
-    {
+    // ------------------------------------------------------------------ block totals of (c_gt, s_gt) unless warp 0 has them
+    int c_tot = c_gt;
+    double s_tot = s_gt;
+    if (!finished_by_warp0) {
       const int wc = __reduce_add_sync(kFull, c_gt);
       const double ws = warp_sum_any(s_gt);
-      __syncthreads();  // protects ired / red reuse
+      __syncthreads();  // protects ired / fin reuse
       if (lane == 0) {
-        ired[2 * kWarps + warp] = wc;
-        red[warp] = ws;
+        ired[3 * kWarps + warp] = wc;
+        fin[warp * 8 + 4] = ws;
       }
       __syncthreads();
-    }
-    int c_tot = 0;
+      c_tot = 0;
+      s_tot = 0.0;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) c_tot += ired[2 * kWarps + w];
+      for (int w = 0; w < kWarps; ++w) {
+        c_tot += ired[3 * kWarps + w];
+        s_tot += fin[w * 8 + 4];
+      }
+    } else if (kTail) {
+      __syncthreads();  // T and the total count were produced by warp 0
+      T_thr = ctl->T;
+      c_tot = ctl->c_tot;
+    }
 
     // ------------------------------------------------------------------ tail indices (parity mode only)
     if (kTail && a.tail_idx_out != nullptr) {
@@ -611,6 +855,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         int run_eq = 0, run_out = 0;
         int* weq = ired;           // [kWarps]
         int* wsel = ired + kWarps; // [kWarps]
+        __syncthreads();
         for (int bb = 0; bb < N; bb += kThreads) {
           const int i = bb + tid;
           const bool valid = i < N;
@@ -651,9 +896,6 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     // ------------------------------------------------------------------ epilogue (one thread)
     if (tid == 0) {
       const double m0 = ctl->m0, m1 = ctl->m1;
-      double s_tot = red[0];
-#pragma unroll
-      for (int w = 1; w < kWarps; ++w) s_tot += red[w];
       const double hn = norm2_canon(h0, h1);
       const double r = __dmul_rn(a.R, hn);
       double cvar, g_cvar, g_star, g_dr, var_t;

@@ -25,16 +25,20 @@ What is restated (reference file:line, relative to /root/reference):
 
 CANONICAL ARITHMETIC (the reference's BLAS matvec / np.mean are not bit-reproducible, so the
 oracle DEFINES the arithmetic the CUDA path must reproduce bit-for-bit where order matters):
-  * sums for the sample mean: 512 lanes, lane l accumulates samples i = l (mod 512) in
-    increasing i; each group of 32 consecutive lanes is combined by an xor-butterfly
-    (1,2,4,8,16); the 16 group totals w0..w15 are combined by an adjacent-pair tree
-    (((w0+w1)+(w2+w3))+((w4+w5)+(w6+w7))) + (((w8+w9)+(w10+w11))+((w12+w13)+(w14+w15))).
+  * sums for the sample mean (per coordinate):
+      fp64 inputs: 512 lanes, lane l accumulates samples i = l (mod 512) in increasing i, in fp64;
+      fp32 inputs: 1024 lanes, lane l accumulates samples i = l (mod 1024) in increasing i IN FP32
+                   (like numpy's own float32 mean), the 1024 lane sums are widened to fp64 and adjacent
+                   lanes (2j, 2j+1) are added, giving 512 values;
+      then each group of 32 consecutive values is combined by an xor-butterfly (1,2,4,8,16) and the 16
+      group totals w0..w15 by an adjacent-pair tree  ((w0+w1)+(w2+w3))+... ; mean = sum / N in fp64.
   * projection  p_i = rn(rn(h0*x_i) + rn(h1*y_i))  (no FMA);  loss  L_i = -p_i.
   * tail: k_f = alpha*N (snapped to the nearest integer when within 1e-9 relative),
     kc = ceil(k_f); T = kc-th largest loss; index set = {L_i > T} U lowest-index ties, |set| = kc
     (== np.argsort(-L, kind='stable')[:kc]); CVaR = (sum_{L_i>T} L_i + (k_f - #{L_i>T}) T) / k_f,
     which equals the LP optimum (1/(aN)) [sum_{j<=floor(aN)} L_(j) + (aN - floor(aN)) L_(floor(aN)+1)].
-  * fp32 inputs are promoted exactly to fp64 first; everything after is the same arithmetic.
+  * fp32 inputs: only the lane partial sums of the mean are fp32 (above); the projection, the tail
+    selection and every offset use the samples promoted exactly to fp64.
 """
 from __future__ import annotations
 
@@ -50,19 +54,27 @@ _XOR_IDX = {x: (np.arange(32) ^ x) for x in (1, 2, 4, 8, 16)}
 
 
 def canonical_sum(v) -> float:
-    """Deterministic 512-lane sum (see module docstring). v: 1-D array-like, promoted to fp64."""
-    v = np.ascontiguousarray(v, dtype=np.float64).ravel()
+    """Deterministic lane-structured sum (see module docstring); the lane layout depends on v's dtype."""
+    v = np.ascontiguousarray(v).ravel()
+    if v.dtype == np.float32:
+        lanes, acc_t = 2 * LANES, np.float32
+    else:
+        v = v.astype(np.float64, copy=False)
+        lanes, acc_t = LANES, np.float64
     n = v.shape[0]
-    rows = (n + LANES - 1) // LANES
+    rows = (n + lanes - 1) // lanes
     if rows == 0:
         return 0.0
-    pad = rows * LANES - n
+    pad = rows * lanes - n
     if pad:
-        v = np.concatenate([v, np.zeros(pad, dtype=np.float64)])
-    a = v.reshape(rows, LANES)
-    s = np.zeros(LANES, dtype=np.float64)
-    for r in range(rows):  # sequential per lane, increasing sample index
+        v = np.concatenate([v, np.zeros(pad, dtype=v.dtype)])
+    a = v.reshape(rows, lanes)
+    s = np.zeros(lanes, dtype=acc_t)
+    for r in range(rows):  # sequential per lane, increasing sample index, in the accumulation dtype
         s = s + a[r]
+    s = s.astype(np.float64)
+    if lanes == 2 * LANES:
+        s = s[0::2] + s[1::2]      # adjacent lanes, in fp64
     w = s.reshape(LANES // 32, 32)
     for x in (1, 2, 4, 8, 16):
         w = w + w[:, _XOR_IDX[x]]

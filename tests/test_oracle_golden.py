@@ -91,10 +91,10 @@ def test_n10k_matches_reference(golden_dir):
     assert abs(o.g_cvar - ref[5]) < TOL_G
     assert abs(o.g_mean - ref[8]) < TOL_G
     assert len(o.tail_idx) == 1000
-    # fp32-input path: promoted samples, same arithmetic
+    # fp32-input path: fp32 lane partial sums for the mean (canonical contract), everything else on promoted samples
     o32 = cf.halfspace(z["samples32"], z["ego"], alpha, delta, eps, rr, ro)
-    assert np.abs(o32.h - z["out32"][0:2]).max() < TOL_H
-    assert abs(o32.g_dr - z["out32"][2]) < TOL_G
+    assert np.abs(o32.h - z["out32"][0:2]).max() < 1e-7
+    assert abs(o32.g_dr - z["out32"][2]) < 1e-7           # reference run on the same (promoted) fp32 samples
     # and the fp32-input result is within 1e-5 m of the fp64 one (north-star tolerance)
     assert abs(o32.g_dr - o.g_dr) < 1e-5
 
