@@ -86,7 +86,7 @@ bool plan_window(long long n, long long kc, double* z_lo, double* z_hi) {
   const double sq = std::sqrt(p * (1.0 - p) / static_cast<double>(n)) / phi;  // std of the sample quantile
   const double w = 6.0 * sq + 0.03 + 0.02 * std::fabs(z);
   const double expect = static_cast<double>(n) * 2.0 * w * phi;
-  if (expect > 0.5 * drcvar::kWarpCand * drcvar::kWarps) return false;  // per-warp lists: 8 sigma headroom
+  if (expect > 0.6 * drcvar::kWarpCand * drcvar::kSweepWarps) return false;  // per-warp lists: ~6 sigma headroom
   *z_lo = z - w;
   *z_hi = z + w;
   return true;
@@ -401,7 +401,7 @@ extern "C" {
 
 int drcvar_version(void) { return DRCVAR_ABI_VERSION; }
 const char* drcvar_last_error(void) { return g_err; }
-int drcvar_reduction_lanes(void) { return drcvar::kLanes; }
+int drcvar_reduction_lanes(void) { return drcvar::kSlots; }
 
 int drcvar_device_count(void) {
   int n = 0;

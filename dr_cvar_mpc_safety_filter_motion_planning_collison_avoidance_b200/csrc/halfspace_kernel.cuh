@@ -1,6 +1,11 @@
 // halfspace_kernel.cuh — sm_100a device code of the risk-bounded safe-halfspace path.
 //
-// One CTA (512 threads) per (scenario, obstacle, step) halfspace, persistent over the batch.  Per halfspace:
+// One CTA per (scenario, obstacle, step) halfspace, persistent over the batch; two CTAs per SM.
+// A CTA is a team of 8 "sweep" warps plus 1 "finisher" warp, pipelined over consecutive halfspaces through two
+// parity buffers and shared-memory mbarriers (full / empty), so the select + epilogue of halfspace j overlaps the
+// load and sweeps of halfspace j+1.
+//
+// sweep team, per halfspace:
 //   stage   N samples -> shared memory with cp.async.bulk (TMA bulk copy, mbarrier completion) or a strided loader
 //   sweep A canonical lane sums of x,y (fp32 inputs: packed fp32 lane partials, fp64 cross-lane tree;
 //           fp64 inputs: fp64 throughout) + heuristic second moments + max |coordinate|          -> mean m
@@ -10,12 +15,13 @@
 //           loss sum follows from linearity), "surely below" (ignored) or "needs the exact fp64 loss" (a bit in a
 //           per-thread mask).  fp64 inputs: exact canonical loss for every sample.
 //   phase 2 masked samples get the canonical fp64 loss L_i = -(h.xi_i) (no FMA); window losses go to warp-private
-//           candidate lists and a 256-bucket histogram over the window
-//   select  exact kc-th largest loss T: histogram scan -> bucket -> rank resolve by one warp (general fallback:
-//           adaptive range-narrowing radix select on order-preserving u64 keys over all samples)
+//           candidate lists and a 256-bucket histogram over the window; the sample slot is released and the
+//           next halfspace's bulk copy is issued
+// finisher warp, per halfspace:
+//   select  exact kc-th largest loss T: histogram scan -> bucket -> all-pairs rank inside the bucket
 //   finish  CVaR = (sum_{L>T} L + (k_f - #{L>T}) T) / k_f  and the three offsets        core/risk_metrics.py:84-338
 // The window and the fp32 bound only decide HOW FAST the exact threshold is found; a miss is detected and the
-// general multi-sweep select runs instead.  The arithmetic contract is in DESIGN.md / oracle/closed_form.py.
+// general multi-sweep radix select (sweep team, all samples) runs instead.  Arithmetic contract: DESIGN.md.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -23,19 +29,25 @@
 
 namespace drcvar {
 
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
-constexpr int kLanes = 512;          // canonical cross-lane tree width (fp32 inputs: 1024 fp32 lanes, paired)
-constexpr int kWarpCand = 96;        // candidate losses per warp (window path)
-constexpr int kWarpList = 160;       // masked sample indices per warp (window path)
+constexpr int kSweepWarps = 8;
+constexpr int kSweepThreads = kSweepWarps * 32;      // 256
+constexpr int kThreads = kSweepThreads + 32;         // + finisher warp
+constexpr int kSlots = 512;                          // canonical cross-lane tree width
+constexpr int kQ = kSlots / kSweepThreads;           // tree slots per sweep thread (2)
+constexpr int kGroups = kSlots / 32;                 // 16 butterfly groups
+constexpr int kWarpCand = 128;                       // candidate losses per sweep warp (window path)
 constexpr int kHistBuckets = 256;
-constexpr int kResolveMax = 32;      // a bucket this small is resolved by one warp
+constexpr int kResolveMax = 32;                      // a bucket this small is ranked by one warp
+constexpr int kMaskWords = 4;                        // per-thread "needs exact loss" mask: 128 bits
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kBulkChunk = 32768;
 
 constexpr int kStatusNonfinite = 1;
 constexpr int kStatusGeneral = 2;
 constexpr int kStatusDegenerate = 4;
+
+constexpr int kModeFinish = 0;   // finisher computes the result from the candidate lists
+constexpr int kModeSkip = 1;     // the sweep team already wrote the result (general path / non-finite input)
 
 struct KernelArgs {
   const void* samples;
@@ -59,15 +71,21 @@ struct KernelArgs {
   int* tail_idx_out;
 };
 
-struct Ctl {
-  unsigned long long mbar;
+struct Ctl {                        // one per parity buffer
   unsigned long long key_lo;       // key(t_lo): histogram origin
   double T;
   double h0, h1, t_lo, t_hi, m0, m1;
   float h0f, h1f, thr_above, thr_keep;
   int hist_shift;
   int bstar, rprime, cnt_in, small_n;
-  int window_ok, nonfinite, degenerate, c_tot, pad;
+  int window_ok, nonfinite, degenerate, c_tot;
+  int mode, cnt_hi, status, pad;
+};
+
+struct Bars {
+  unsigned long long data;         // bulk copy landed
+  unsigned long long full[2];      // sweep team -> finisher
+  unsigned long long empty[2];     // finisher -> sweep team
 };
 
 template <typename T> struct Vec2;
@@ -78,16 +96,17 @@ template <> struct Vec2<double> { using type = double2; };
 __host__ __device__ inline size_t slot_bytes_for(long long n, size_t elem_bytes) {
   return (static_cast<size_t>(n) * 2 * elem_bytes + 127) & ~static_cast<size_t>(127);
 }
-constexpr int kRedDoubles = kWarps * 8;  // per buffer
+constexpr int kRedDoubles = kGroups * 2 + 2 * 8 + kSweepWarps;   // group totals, moments of 2 warps, amax per warp
+constexpr int kFinDoubles = kSweepWarps * 4;                     // per parity: {sum x, sum y, exact sum, -}
 __host__ __device__ inline size_t fixed_smem_bytes() {
-  return sizeof(double) * kWarpCand * kWarps          // cand
-         + sizeof(unsigned short) * kWarpList * kWarps  // list
-         + sizeof(unsigned) * kHistBuckets            // hist
-         + sizeof(double) * 2 * kRedDoubles           // red (double-buffered by iteration parity)
-         + sizeof(double) * 2 * kRedDoubles           // fin (double-buffered): per-warp finals
-         + sizeof(double) * 2 * kResolveMax           // small (double-buffered)
-         + sizeof(int) * 4 * kWarps                   // ired
-         + 2 * sizeof(Ctl);                           // ctl (double-buffered)
+  return sizeof(double) * 2 * kWarpCand * kSweepWarps   // cand   [2][warps][kWarpCand]
+         + sizeof(unsigned) * 2 * kHistBuckets          // hist   [2][256]
+         + sizeof(double) * kRedDoubles                 // red
+         + sizeof(double) * 2 * kFinDoubles             // fin    [2]
+         + sizeof(double) * 2 * kResolveMax             // small  [2]
+         + sizeof(int) * 2 * 2 * kSweepWarps            // ired   [2][warps][2]
+         + sizeof(int) * 4 * kSweepWarps                // iscr   (team scratch)
+         + 2 * sizeof(Ctl) + sizeof(Bars);
 }
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -102,6 +121,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
   uint32_t ok;
@@ -124,6 +146,43 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// barrier 1: the sweep team only (the finisher warp never joins it)
+__device__ __forceinline__ void team_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kSweepThreads) : "memory"); }
+__device__ __forceinline__ int team_sync_or(int pred) {
+  int r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.s32 p, %1, 0;\n\t"
+      "bar.red.or.pred q, 1, %2, p;\n\t"
+      "selp.s32 %0, 1, 0, q;\n\t}"
+      : "=r"(r)
+      : "r"(pred), "n"(kSweepThreads)
+      : "memory");
+  return r;
+}
+// fp32 classification of one sample (p = h.xi in fp32):  up = p < thr_above;  keep = !up && p <= thr_keep.
+// up: packed add of (x, y) into acc and count; keep: set `bit` in mask.  5 instructions.
+__device__ __forceinline__ unsigned long long pack2(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ void classify_f32(float p, float thr_above, float thr_keep, unsigned long long xy,
+                                             unsigned long long& acc, int& cnt, unsigned& mask, unsigned bit) {
+  asm("{\n\t.reg .pred u, k;\n\t"
+      "setp.lt.f32 u, %3, %4;\n\t"
+      "setp.le.and.f32 k, %3, %5, !u;\n\t"
+      "@u add.rn.f32x2 %0, %0, %6;\n\t"
+      "@u add.s32 %1, %1, 1;\n\t"
+      "@k or.b32 %2, %2, %7;\n\t}"
+      : "+l"(acc), "+r"(cnt), "+r"(mask)
+      : "f"(p), "f"(thr_above), "f"(thr_keep), "l"(xy), "r"(bit));
 }
 
 // ---------------------------------------------------------------------------------------------- small helpers
@@ -160,53 +219,65 @@ __device__ __forceinline__ double warp_sum_canon(double v) {  // xor 1,2,4,8,16 
 }
 __device__ __forceinline__ float absmax3(float m, float a, float b) { return fmaxf(m, fmaxf(fabsf(a), fabsf(b))); }
 
-// Exact r-th largest (1-based) among the enumerated losses whose keys lie in [lo, hi] (general machinery).
-// for_each(f) must call f(L) for every candidate owned by the calling thread; all threads must call this.
-template <class ForEach>
-__device__ double select_rank(ForEach&& for_each, unsigned long long lo, unsigned long long hi, int r,
-                              unsigned* hist, double* small, Ctl* ctl) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Histogram scan by ONE warp: finds the bucket (from the top) that holds rank r (1-based).
+__device__ __forceinline__ void scan_hist_warp(const unsigned* hist, int r, int lane, int& bstar, int& rprime, int& cnt_in) {
+  int run = 0, row = -1, r_row = 0;
+#pragma unroll
+  for (int i = 0; i < kHistBuckets / 32; ++i) {
+    const int tot = __reduce_add_sync(kFull, static_cast<int>(hist[kHistBuckets - 1 - (32 * i + lane)]));
+    if (row < 0 && run + tot >= r) {
+      row = i;
+      r_row = r - run;
+    }
+    run += tot;
+  }
+  if (row < 0) { row = kHistBuckets / 32 - 1; r_row = 1; }  // unreachable when r <= #candidates in range
+  const int bucket = kHistBuckets - 1 - (32 * row + lane);
+  const int c = static_cast<int>(hist[bucket]);
+  int incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const int excl = incl - c;
+  const unsigned hit = __ballot_sync(kFull, excl < r_row && r_row <= incl);
+  const int src = __ffs(hit) - 1;
+  bstar = __shfl_sync(kFull, bucket, src);
+  rprime = __shfl_sync(kFull, r_row - excl, src);
+  cnt_in = __shfl_sync(kFull, c, src);
+}
+
+// Exact r-th largest (1-based) among the enumerated losses whose keys lie in [lo, hi] — generic narrowing loop.
+// SYNC() synchronises the participating threads (team barrier, or __syncwarp for one warp); `leader` is true for
+// the first warp of the group, `gtid`/`gsize` index the group.  for_each(f) enumerates this thread's candidates.
+template <class ForEach, class Sync>
+__device__ double select_rank(ForEach&& for_each, Sync&& SYNC, bool leader, int gtid, int gsize, unsigned long long lo,
+                              unsigned long long hi, int r, unsigned* hist, double* small, Ctl* ctl) {
+  const int lane = threadIdx.x & 31;
   for (;;) {
     const unsigned long long span = hi - lo;
     if (span == 0) return value_of(lo);
     const int bits = 64 - __clzll(static_cast<long long>(span));
     const int shift = bits > 8 ? bits - 8 : 0;  // (span >> shift) < 256
-    if (tid < kHistBuckets) hist[tid] = 0;
-    if (tid == 0) ctl->small_n = 0;
-    __syncthreads();
+    for (int i = gtid; i < kHistBuckets; i += gsize) hist[i] = 0;
+    if (gtid == 0) ctl->small_n = 0;
+    SYNC();
     for_each([&](double L) {
       const unsigned long long k = key_of(L);
       if (k >= lo && k <= hi) atomicAdd(&hist[static_cast<unsigned>((k - lo) >> shift)], 1u);
     });
-    __syncthreads();
-    if (warp == 0) {
-      int run = 0, row = -1, r_row = 0;
-#pragma unroll
-      for (int i = 0; i < kHistBuckets / 32; ++i) {
-        const int tot = __reduce_add_sync(kFull, static_cast<int>(hist[kHistBuckets - 1 - (32 * i + lane)]));
-        if (row < 0 && run + tot >= r) {
-          row = i;
-          r_row = r - run;
-        }
-        run += tot;
-      }
-      if (row < 0) { row = kHistBuckets / 32 - 1; r_row = 1; }  // unreachable when r <= #candidates in range
-      const int bucket = kHistBuckets - 1 - (32 * row + lane);
-      const int c = static_cast<int>(hist[bucket]);
-      int incl = c;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(kFull, incl, d);
-        if (lane >= d) incl += t;
-      }
-      const int excl = incl - c;
-      if (excl < r_row && r_row <= incl) {
-        ctl->bstar = bucket;
-        ctl->rprime = r_row - excl;
-        ctl->cnt_in = c;
+    SYNC();
+    if (leader) {
+      int bstar, rprime, cnt_in;
+      scan_hist_warp(hist, r, lane, bstar, rprime, cnt_in);
+      if (lane == 0) {
+        ctl->bstar = bstar;
+        ctl->rprime = rprime;
+        ctl->cnt_in = cnt_in;
       }
     }
-    __syncthreads();
+    SYNC();
     const int bstar = ctl->bstar;
     r = ctl->rprime;
     const int cnt_in = ctl->cnt_in;
@@ -223,8 +294,8 @@ __device__ double select_rank(ForEach&& for_each, unsigned long long lo, unsigne
           if (pos < kResolveMax) small[pos] = L;
         }
       });
-      __syncthreads();
-      if (warp == 0) {
+      SYNC();
+      if (leader) {
         const unsigned long long mine = lane < cnt_in ? key_of(small[lane]) : 0ull;
         int rank = 0;
         for (int j = 0; j < cnt_in; ++j) {
@@ -233,10 +304,59 @@ __device__ double select_rank(ForEach&& for_each, unsigned long long lo, unsigne
         }
         if (lane < cnt_in && rank == r - 1) ctl->T = value_of(mine);
       }
-      __syncthreads();
+      SYNC();
       return ctl->T;
     }
   }
+}
+
+// Offsets of one halfspace from (h, mean, CVaR ingredients); one thread.            core/risk_metrics.py, core/halfspaces.py
+__device__ __forceinline__ void write_outputs(const KernelArgs& a, long long b, const Ctl* ctl, bool nonfinite, double s_tot,
+                                              int c_tot, double T_thr, int status) {
+  const double h0 = ctl->h0, h1 = ctl->h1, m0 = ctl->m0, m1 = ctl->m1;
+  const double hn = norm2_canon(h0, h1);
+  const double r = __dmul_rn(a.R, hn);
+  double cvar, g_cvar, g_star, g_dr, var_t;
+  if (nonfinite) {
+    cvar = __longlong_as_double(0x7ff8000000000000ll);
+    var_t = cvar;
+    g_cvar = 100.0;  // solver-failure sentinel, core/risk_metrics.py:177,265,303,338
+    g_star = 100.0;
+    g_dr = __dsub_rn(100.0, r);
+  } else {
+    const double S = __dadd_rn(s_tot, __dmul_rn(__dsub_rn(a.k_f, static_cast<double>(c_tot)), T_thr));
+    cvar = __ddiv_rn(S, a.k_f);
+    var_t = T_thr;
+    const double cr = __dadd_rn(cvar, r);
+    g_cvar = __dsub_rn(cr, a.delta);
+    g_star = __dsub_rn(__dadd_rn(cr, a.eoa), a.delta);
+    g_dr = __dsub_rn(g_star, r);
+  }
+  // mean halfspace: direction from the ORIGIN (core/halfspaces.py:88)
+  double hm0, hm1;
+  const double mn = norm2_canon(m0, m1);
+  if (mn < 1e-10) {
+    hm0 = 1.0;
+    hm1 = 0.0;
+  } else {
+    hm0 = __ddiv_rn(m0, mn);
+    hm1 = __ddiv_rn(m1, mn);
+  }
+  const double hmn = norm2_canon(hm0, hm1);
+  const double g_mean = -__dsub_rn(__dadd_rn(__dmul_rn(hm0, m0), __dmul_rn(hm1, m1)), __dmul_rn(a.R, hmn));
+  a.h_out[2 * b] = h0;
+  a.h_out[2 * b + 1] = h1;
+  if (a.h_mean_out) {
+    a.h_mean_out[2 * b] = hm0;
+    a.h_mean_out[2 * b + 1] = hm1;
+  }
+  a.g_out[3 * b] = g_mean;
+  a.g_out[3 * b + 1] = g_cvar;
+  a.g_out[3 * b + 2] = g_dr;
+  if (a.cvar_out) a.cvar_out[b] = cvar;
+  if (a.var_out) a.var_out[b] = var_t;
+  if (a.gstar_out) a.gstar_out[b] = g_star;
+  if (a.status_out) a.status_out[b] = status;
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -244,89 +364,211 @@ template <typename T, bool kTail>
 __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs a) {
   using V2 = typename Vec2<T>::type;
   constexpr bool kF32 = sizeof(T) == 4;
-  // samples one thread touches per row: fp32 -> one float4 = samples (2t, 2t+1) of a 1024-sample tile;
-  // fp64 -> one double2 = sample t of a 512-sample tile
-  constexpr int kPerRow = kF32 ? 2 : 1;
-  constexpr int kTile = kThreads * kPerRow;
+  constexpr int kPerLoad = kF32 ? 2 : 1;          // samples per 16-byte shared load
+  constexpr int kTile = kSlots * kPerLoad;        // samples per canonical tile (1024 fp32 / 512 fp64)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
   const size_t slot_bytes = slot_bytes_for(N, sizeof(T));
   V2* sm = reinterpret_cast<V2*>(smem_raw);
-  double* cand = reinterpret_cast<double*>(smem_raw + slot_bytes);
-  unsigned short* list = reinterpret_cast<unsigned short*>(cand + kWarpCand * kWarps);
-  unsigned* hist = reinterpret_cast<unsigned*>(list + kWarpList * kWarps);
-  double* red_base = reinterpret_cast<double*>(hist + kHistBuckets);
-  double* fin_base = red_base + 2 * kRedDoubles;
-  double* small_base = fin_base + 2 * kRedDoubles;
-  int* ired = reinterpret_cast<int*>(small_base + 2 * kResolveMax);
-  Ctl* ctl_base = reinterpret_cast<Ctl*>(ired + 4 * kWarps);
-  unsigned long long* mbar = &ctl_base[0].mbar;
-  double* wcand = cand + warp * kWarpCand;
-  unsigned short* wlist = list + warp * kWarpList;
+  double* cand_base = reinterpret_cast<double*>(smem_raw + slot_bytes);
+  unsigned* hist_base = reinterpret_cast<unsigned*>(cand_base + 2 * kWarpCand * kSweepWarps);
+  double* red = reinterpret_cast<double*>(hist_base + 2 * kHistBuckets);
+  double* fin_base = red + kRedDoubles;
+  double* small_base = fin_base + 2 * kFinDoubles;
+  int* ired_base = reinterpret_cast<int*>(small_base + 2 * kResolveMax);
+  int* iscr = ired_base + 2 * 2 * kSweepWarps;
+  Ctl* ctl_base = reinterpret_cast<Ctl*>(iscr + 4 * kSweepWarps);
+  Bars* bars = reinterpret_cast<Bars*>(ctl_base + 2);
 
+  if (tid == 0) {
+    mbar_init(&bars->data, 1);
+    mbar_init(&bars->full[0], 1);
+    mbar_init(&bars->full[1], 1);
+    mbar_init(&bars->empty[0], 1);
+    mbar_init(&bars->empty[1], 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < 2 * kHistBuckets; i += kThreads) hist_base[i] = 0;
+  if (tid < 2) ctl_base[tid].small_n = 0;
+  __syncthreads();
+
+  // ============================================================================================ finisher warp
+  if (warp == kSweepWarps) {
+    int iter = 0;
+    for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
+      const int par = iter & 1, use = iter >> 1;
+      Ctl* ctl = ctl_base + par;
+      unsigned* hist = hist_base + par * kHistBuckets;
+      const double* cand = cand_base + par * kWarpCand * kSweepWarps;
+      const double* fin = fin_base + par * kFinDoubles;
+      const int* ired = ired_base + par * 2 * kSweepWarps;
+      double* small = small_base + par * kResolveMax;
+      mbar_wait(&bars->full[par], use & 1);
+      if (ctl->mode == kModeFinish) {
+        const int cnt_hi = ctl->cnt_hi;
+        const unsigned long long klo = ctl->key_lo;
+        const int hshift = ctl->hist_shift;
+        int bstar, r, cnt_in;
+        scan_hist_warp(hist, a.kc - cnt_hi, lane, bstar, r, cnt_in);
+        // pass over all candidates: above bucket b* -> counted/summed; bucket b* -> gathered for exact ranking
+        double s3 = 0.0;
+        int c3 = 0, n_small = 0;
+        for (int w = 0; w < kSweepWarps; ++w) {
+          const int nc = ired[w * 2 + 1];
+          const double* wc = cand + w * kWarpCand;
+          for (int j0 = 0; j0 < nc; j0 += 32) {
+            const int j = j0 + lane;
+            bool in_b = false;
+            double L = 0.0;
+            if (j < nc) {
+              L = wc[j];
+              const int bk = static_cast<int>((key_of(L) - klo) >> hshift);
+              if (bk > bstar) {
+                ++c3;
+                s3 += L;
+              }
+              in_b = bk == bstar;
+            }
+            const unsigned bal = __ballot_sync(kFull, in_b);
+            if (bal) {
+              const int pos = n_small + __popc(bal & ((1u << lane) - 1u));
+              if (in_b && pos < kResolveMax) small[pos] = L;
+              n_small += __popc(bal);
+            }
+          }
+        }
+        __syncwarp();
+        double T_thr, s4 = 0.0;
+        int c4 = 0;
+        if (cnt_in <= kResolveMax) {
+          // all-pairs rank inside bucket b*; members above T are summed in rank order (deterministic)
+          const double mineL = lane < cnt_in ? small[lane] : 0.0;
+          const unsigned long long mine = lane < cnt_in ? key_of(mineL) : 0ull;
+          int rank = 0;
+          for (int j = 0; j < cnt_in; ++j) {
+            const unsigned long long other = __shfl_sync(kFull, mine, j);
+            rank += (other > mine) || (other == mine && j < lane);
+          }
+          const unsigned owner = __ballot_sync(kFull, lane < cnt_in && rank == r - 1);
+          T_thr = __shfl_sync(kFull, mineL, __ffs(owner) - 1);
+          __syncwarp();
+          if (lane < cnt_in) small[rank] = mineL;
+          __syncwarp();
+          const bool mineAbove = lane < cnt_in && lane < r - 1 && key_of(small[lane]) > key_of(T_thr);
+          s4 = warp_sum_any(mineAbove ? small[lane] : 0.0);
+          c4 = __popc(__ballot_sync(kFull, mineAbove));
+        } else {
+          // dense / heavily tied bucket: narrow further inside the finisher warp
+          const unsigned long long lo2 = klo + (static_cast<unsigned long long>(bstar) << hshift);
+          unsigned long long hi2 = lo2 + ((1ull << hshift) - 1ull);
+          const unsigned long long khi = key_of(ctl->t_hi);
+          if (hi2 > khi || hi2 < lo2) hi2 = khi;
+          auto each = [&](auto&& f) {
+            for (int w = 0; w < kSweepWarps; ++w) {
+              const int nc = ired[w * 2 + 1];
+              for (int j = lane; j < nc; j += 32) f(cand[w * kWarpCand + j]);
+            }
+          };
+          T_thr = select_rank(each, [] { __syncwarp(); }, true, lane, 32, lo2, hi2, r, hist, small, ctl);
+          // members of bucket b* above T
+          each([&](double L) {
+            const int bk = static_cast<int>((key_of(L) - klo) >> hshift);
+            if (bk == bstar && L > T_thr) {
+              ++c4;
+              s4 += L;
+            }
+          });
+          c4 = __reduce_add_sync(kFull, c4);
+          s4 = warp_sum_any(s4);
+        }
+        const int c3t = __reduce_add_sync(kFull, c3);
+        const double s3t = warp_sum_any(s3);
+        if (lane == 0) {
+          double s_x = 0.0, s_y = 0.0, s_e = 0.0;
+#pragma unroll
+          for (int w = 0; w < kSweepWarps; ++w) {
+            s_x += fin[w * 4 + 0];
+            s_y += fin[w * 4 + 1];
+            s_e += fin[w * 4 + 2];
+          }
+          // loss sum of the "surely above" set by linearity: sum_i -(h.xi_i) = -(h0 sum x + h1 sum y)
+          const double s_lin = -(ctl->h0 * s_x + ctl->h1 * s_y);
+          const double s_tot = ((s_e + s_lin) + s3t) + s4;
+          const int c_tot = cnt_hi + c3t + c4;
+          write_outputs(a, b, ctl, false, s_tot, c_tot, T_thr, ctl->status);
+          if (kTail) {
+            ctl->T = T_thr;
+            ctl->c_tot = c_tot;
+          }
+        }
+      }
+      // hand the parity buffers back: histogram zeroed, counters reset
+      for (int i = lane; i < kHistBuckets; i += 32) hist[i] = 0;
+      if (lane == 0) ctl->small_n = 0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->empty[par]);
+    }
+    return;
+  }
+
+  // ============================================================================================ sweep team
   const uint32_t copy_bytes = static_cast<uint32_t>(static_cast<size_t>(N) * sizeof(V2));
   auto issue_bulk = [&](long long b) {
     const unsigned char* src =
         reinterpret_cast<const unsigned char*>(a.samples) + static_cast<size_t>(b) * a.stride_b * sizeof(T);
-    mbar_expect_tx(mbar, copy_bytes);
+    mbar_expect_tx(&bars->data, copy_bytes);
     for (uint32_t off = 0; off < copy_bytes; off += kBulkChunk) {
       const uint32_t n = copy_bytes - off < kBulkChunk ? copy_bytes - off : kBulkChunk;
-      bulk_g2s(smem_raw + off, src + off, n, mbar);
+      bulk_g2s(smem_raw + off, src + off, n, &bars->data);
     }
   };
-
-  if (a.bulk) {
-    if (tid == 0) {
-      mbar_init(mbar, 1);
-      mbar_fence_init();
-    }
-    __syncthreads();
-    if (tid == 0 && static_cast<long long>(blockIdx.x) < a.B) issue_bulk(blockIdx.x);
-  }
+  if (a.bulk && tid == 0 && static_cast<long long>(blockIdx.x) < a.B) issue_bulk(blockIdx.x);
   uint32_t phase = 0;
   int iter = 0;
+  const int tiles = (N + kTile - 1) / kTile;
+  const int full_tiles = N / kTile;
 
   for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
-    const int par = iter & 1;
-    double* red = red_base + par * kRedDoubles;
-    double* fin = fin_base + par * kRedDoubles;
-    double* small = small_base + par * kResolveMax;
+    const int par = iter & 1, use = iter >> 1;
     Ctl* ctl = ctl_base + par;
+    unsigned* hist = hist_base + par * kHistBuckets;
+    double* wcand = cand_base + par * kWarpCand * kSweepWarps + warp * kWarpCand;
+    double* fin = fin_base + par * kFinDoubles;
+    int* ired = ired_base + par * 2 * kSweepWarps;
+    double* small = small_base + par * kResolveMax;
     bool next_issued = false;
     const long long b_next = b + gridDim.x;
 
     // ------------------------------------------------------------------ stage
     if (a.bulk) {
-      mbar_wait(mbar, phase);
+      mbar_wait(&bars->data, phase);
       phase ^= 1u;
     } else {
       const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
-      for (int i = tid; i < N; i += kThreads) {
+      for (int i = tid; i < N; i += kSweepThreads) {
         const T* p = base + static_cast<long long>(i) * a.stride_n;
         V2 v;
         v.x = p[0];
         v.y = p[a.stride_c];
         sm[i] = v;
       }
-      __syncthreads();
+      team_sync();
     }
+    // parity buffers must have been handed back by the finisher (two iterations ago)
+    if (use > 0) mbar_wait(&bars->empty[par], (use - 1) & 1);
 
     // ------------------------------------------------------------------ sweep A: canonical lane sums (+ heuristics)
-    const int rows = (N + kTile - 1) / kTile;
-    const int full_rows = N / kTile;
-    double sx, sy;                                  // this thread's contribution to the 512-wide fp64 tree
-    T qdx = 0, qdy = 0, qxx = 0, qxy = 0, qyy = 0;  // second moments (warps 0-3 only), shifted by the first sample
+    double sx[kQ], sy[kQ];                          // this thread's kQ slots of the 512-wide fp64 tree (slot = tid + 256 q)
+    T qdx = 0, qdy = 0, qxx = 0, qxy = 0, qyy = 0;  // second moments (warps 0-1 only), shifted by the first sample
     float amax = 0.f;                               // max |coordinate| (bounds the fp32 classification error)
     const V2 first = sm[0];
+    const bool mom_warp = warp < 2;
     if constexpr (kF32) {
       const float4* sm4 = reinterpret_cast<const float4*>(smem_raw);
-      float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);  // lanes 2t and 2t+1, fp32 partial sums
-      auto accum = [&](const float4 v) {
-        a0 = __fadd2_rn(a0, make_float2(v.x, v.y));
-        a1 = __fadd2_rn(a1, make_float2(v.z, v.w));
-        amax = absmax3(absmax3(amax, v.x, v.y), v.z, v.w);
-      };
+      float2 acc[kQ][2];
+#pragma unroll
+      for (int q = 0; q < kQ; ++q) acc[q][0] = acc[q][1] = make_float2(0.f, 0.f);
       auto moments = [&](const float4 v) {
         const float dx0 = v.x - first.x, dy0 = v.y - first.y, dx1 = v.z - first.x, dy1 = v.w - first.y;
         qdx += dx0 + dx1;
@@ -335,35 +577,41 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         qxy = fmaf(dx0, dy0, fmaf(dx1, dy1, qxy));
         qyy = fmaf(dy0, dy0, fmaf(dy1, dy1, qyy));
       };
-      if (warp < 4) {
 #pragma unroll 2
-        for (int m = 0; m < full_rows; ++m) {
-          const float4 v = sm4[m * kThreads + tid];
-          accum(v);
-          moments(v);
-        }
-      } else {
-#pragma unroll 4
-        for (int m = 0; m < full_rows; ++m) accum(sm4[m * kThreads + tid]);
-      }
-      if (full_rows < rows) {  // ragged last tile: element-wise
-        const int i0 = full_rows * kTile + 2 * tid;
-        if (i0 < N) {
-          const float2 v = sm[i0];
-          a0 = __fadd2_rn(a0, v);
-          amax = absmax3(amax, v.x, v.y);
-        }
-        if (i0 + 1 < N) {
-          const float2 v = sm[i0 + 1];
-          a1 = __fadd2_rn(a1, v);
-          amax = absmax3(amax, v.x, v.y);
+      for (int m = 0; m < full_tiles; ++m) {
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) {
+          const float4 v = sm4[m * kSlots + q * kSweepThreads + tid];   // samples 1024 m + 2 slot, +1
+          acc[q][0] = __fadd2_rn(acc[q][0], make_float2(v.x, v.y));
+          acc[q][1] = __fadd2_rn(acc[q][1], make_float2(v.z, v.w));
+          amax = absmax3(absmax3(amax, v.x, v.y), v.z, v.w);
+          if (mom_warp) moments(v);
         }
       }
-      sx = __dadd_rn(static_cast<double>(a0.x), static_cast<double>(a1.x));  // adjacent lanes, in fp64
-      sy = __dadd_rn(static_cast<double>(a0.y), static_cast<double>(a1.y));
+      if (full_tiles < tiles) {  // ragged last tile: element-wise
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) {
+          const int i0 = full_tiles * kTile + 2 * (q * kSweepThreads + tid);
+          if (i0 < N) {
+            const float2 v = sm[i0];
+            acc[q][0] = __fadd2_rn(acc[q][0], v);
+            amax = absmax3(amax, v.x, v.y);
+          }
+          if (i0 + 1 < N) {
+            const float2 v = sm[i0 + 1];
+            acc[q][1] = __fadd2_rn(acc[q][1], v);
+            amax = absmax3(amax, v.x, v.y);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kQ; ++q) {  // adjacent fp32 lanes (2 slot, 2 slot + 1), widened, added in fp64
+        sx[q] = __dadd_rn(static_cast<double>(acc[q][0].x), static_cast<double>(acc[q][1].x));
+        sy[q] = __dadd_rn(static_cast<double>(acc[q][0].y), static_cast<double>(acc[q][1].y));
+      }
     } else {
-      sx = 0.0;
-      sy = 0.0;
+#pragma unroll
+      for (int q = 0; q < kQ; ++q) sx[q] = sy[q] = 0.0;
       auto moments = [&](const V2 v) {
         const T dx = v.x - first.x, dy = v.y - first.y;
         qdx += dx;
@@ -372,63 +620,74 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         qxy = fma(dx, dy, qxy);
         qyy = fma(dy, dy, qyy);
       };
-      if (warp < 4) {
 #pragma unroll 2
-        for (int i = tid; i < N; i += kThreads) {
-          const V2 v = sm[i];
-          sx = __dadd_rn(sx, v.x);
-          sy = __dadd_rn(sy, v.y);
-          moments(v);
+      for (int m = 0; m < full_tiles; ++m) {
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) {
+          const V2 v = sm[m * kSlots + q * kSweepThreads + tid];
+          sx[q] = __dadd_rn(sx[q], v.x);
+          sy[q] = __dadd_rn(sy[q], v.y);
+          if (mom_warp) moments(v);
         }
-      } else {
-#pragma unroll 4
-        for (int i = tid; i < N; i += kThreads) {
-          const V2 v = sm[i];
-          sx = __dadd_rn(sx, v.x);
-          sy = __dadd_rn(sy, v.y);
+      }
+      if (full_tiles < tiles) {
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) {
+          const int i = full_tiles * kTile + q * kSweepThreads + tid;
+          if (i < N) {
+            const V2 v = sm[i];
+            sx[q] = __dadd_rn(sx[q], v.x);
+            sy[q] = __dadd_rn(sy[q], v.y);
+          }
         }
       }
     }
     {
-      // canonical: xor-butterfly inside each warp (= group of 32 values); the 16 warp totals are tree-added below
-      const double tx = warp_sum_canon(sx);
-      const double ty = warp_sum_canon(sy);
+      // canonical: xor-butterfly inside each group of 32 slots; the 16 group totals are tree-added by warp 0
+#pragma unroll
+      for (int q = 0; q < kQ; ++q) {
+        const double tx = warp_sum_canon(sx[q]);
+        const double ty = warp_sum_canon(sy[q]);
+        if (lane == 0) {
+          const int g = q * kSweepWarps + warp;   // slots [32 g, 32 g + 32)
+          red[2 * g] = tx;
+          red[2 * g + 1] = ty;
+        }
+      }
       const unsigned mxb = __reduce_max_sync(kFull, __float_as_uint(amax));
-      double* w = red + warp * 8;
-      if (warp < 4) {
+      if (mom_warp) {
         const float mdx = warp_sum_any(static_cast<float>(qdx)), mdy = warp_sum_any(static_cast<float>(qdy));
         const float mxx = warp_sum_any(static_cast<float>(qxx)), mxy = warp_sum_any(static_cast<float>(qxy));
         const float myy = warp_sum_any(static_cast<float>(qyy));
         if (lane == 0) {
-          w[2] = mdx; w[3] = mdy; w[4] = mxx; w[5] = mxy; w[6] = myy;
+          double* w = red + 2 * kGroups + warp * 8;
+          w[0] = mdx; w[1] = mdy; w[2] = mxx; w[3] = mxy; w[4] = myy;
         }
       }
-      if (lane == 0) {
-        w[0] = tx; w[1] = ty; w[7] = static_cast<double>(__uint_as_float(mxb));
-      }
+      if (lane == 0) red[2 * kGroups + 16 + warp] = static_cast<double>(__uint_as_float(mxb));
     }
-    __syncthreads();  // S1
+    team_sync();  // S1
 
-    // ------------------------------------------------------------------ direction + window (warp 0); warps 8-15 clear hist
+    // ------------------------------------------------------------------ direction + window (warp 0)
     if (warp == 0) {
       double w[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        double t[kWarps];
+        double t[kGroups];
 #pragma unroll
-        for (int q = 0; q < kWarps; ++q) t[q] = red[q * 8 + j];
+        for (int g = 0; g < kGroups; ++g) t[g] = red[2 * g + j];
 #pragma unroll
-        for (int n = kWarps; n > 1; n >>= 1)
+        for (int n = kGroups; n > 1; n >>= 1)
 #pragma unroll
-          for (int q = 0; q < n / 2; ++q) t[q] = __dadd_rn(t[2 * q], t[2 * q + 1]);  // adjacent-pair tree
+          for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);  // adjacent-pair tree
         w[j] = t[0];
       }
       double q[5];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) q[j] = (red[0 * 8 + 2 + j] + red[1 * 8 + 2 + j]) + (red[2 * 8 + 2 + j] + red[3 * 8 + 2 + j]);
+      for (int j = 0; j < 5; ++j) q[j] = red[2 * kGroups + j] + red[2 * kGroups + 8 + j];
       float mx = 0.f;
 #pragma unroll
-      for (int qq = 0; qq < kWarps; ++qq) mx = fmaxf(mx, static_cast<float>(red[qq * 8 + 7]));
+      for (int ww = 0; ww < kSweepWarps; ++ww) mx = fmaxf(mx, static_cast<float>(red[2 * kGroups + 16 + ww]));
       const double m0 = __ddiv_rn(w[0], static_cast<double>(N));
       const double m1 = __ddiv_rn(w[1], static_cast<double>(N));
       int nonfinite = !(isfinite(m0) && isfinite(m1));
@@ -451,10 +710,9 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         }
       }
       nonfinite |= !(isfinite(h0) && isfinite(h1));
-      // heuristic window around the expected kc-th largest loss (affects speed only, never the result)
-      // samples that entered the moments: warps 0-3 (threads 0..127), full rows only for fp32 inputs
-      const int n_sub_i = kF32 ? full_rows * 128 * 2
-                               : 128 * (N / kThreads) + ((N % kThreads) < 128 ? (N % kThreads) : 128);
+      // heuristic window around the expected kc-th largest loss (affects speed only, never the result).
+      // moments came from warps 0-1: slots {tid, tid + 256} for tid < 64, full tiles only.
+      const int n_sub_i = full_tiles * 64 * kQ * kPerLoad;
       const double n_sub = static_cast<double>(n_sub_i > 0 ? n_sub_i : 1);
       const double ex = q[0] / n_sub, ey = q[1] / n_sub;
       const double cxx = q[2] / n_sub - ex * ex, cxy = q[3] / n_sub - ex * ey, cyy = q[4] / n_sub - ey * ey;
@@ -462,7 +720,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       const double mu_l = -(h0 * m0 + h1 * m1);
       const double sigma = static_cast<double>(sqrtf(static_cast<float>(var_l)));
       int window_ok = a.use_window && (n_sub_i >= 256) && (var_l > 0.0) && isfinite(sigma) && !nonfinite &&
-                      (rows * kPerRow <= 64);
+                      (tiles * kQ * kPerLoad <= 32 * kMaskWords);
       const double t_lo = __dadd_rn(mu_l + a.z_lo * sigma, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
       const double t_hi = __dadd_rn(mu_l + a.z_hi * sigma, 0.0);
       // fp32 classification of p32 = fma(h1f, y, h0f*x)  (p = h.xi = -L):
@@ -475,7 +733,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       const unsigned long long klo = key_of(t_lo), khi = key_of(t_hi);
       const unsigned long long span = khi - klo;
       const int bits = span ? 64 - __clzll(static_cast<long long>(span)) : 0;
-      window_ok = window_ok && isfinite(thr_keep) && isfinite(thr_above) && (khi >= klo);
+      window_ok = window_ok && isfinite(thr_keep) && isfinite(thr_above) && (khi >= klo) && (thr_above <= thr_keep);
       if (lane == 0) {
         ctl->h0 = h0; ctl->h1 = h1; ctl->m0 = m0; ctl->m1 = m1;
         ctl->t_lo = t_lo;
@@ -486,12 +744,9 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         ctl->window_ok = window_ok;
         ctl->nonfinite = nonfinite;
         ctl->degenerate = degenerate;
-        ctl->small_n = 0;
       }
-    } else if (warp >= kWarps - kHistBuckets / 32) {
-      hist[tid - (kThreads - kHistBuckets)] = 0;  // last 8 warps clear the 256-bucket histogram
     }
-    __syncthreads();  // S2
+    team_sync();  // S2
     const double h0 = ctl->h0, h1 = ctl->h1;
     const bool nonfinite = ctl->nonfinite != 0;
     const bool window = ctl->window_ok != 0;
@@ -502,280 +757,168 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     int c_gt = 0;        // exact-classified losses above the threshold (this thread)
     double s_gt = 0.0;   // their sum
     bool fast = false;
-    bool finished_by_warp0 = false;
 
-    if (!nonfinite) {
-      if (window) {
-        // -------------------------------------------------------------- sweep B: classify, build the exact-needed mask
-        unsigned mlo = 0, mhi = 0;
-        int c32 = 0;                                 // "surely above" by the fp32 bound
-        float2 ab = make_float2(0.f, 0.f);           // their raw coordinate sums (loss sum follows by linearity)
-        if constexpr (kF32) {
-          const float4* sm4 = reinterpret_cast<const float4*>(smem_raw);
-          const float h0f = ctl->h0f, h1f = ctl->h1f, thr_keep = ctl->thr_keep, thr_above = ctl->thr_above;
-          auto classify2 = [&](const float4 v, unsigned& mask, const unsigned bit) {
-            const float p0 = fmaf(h1f, v.y, h0f * v.x), p1 = fmaf(h1f, v.w, h0f * v.z);
-            const bool up0 = p0 < thr_above, up1 = p1 < thr_above;
-            if (up0) { ab = __fadd2_rn(ab, make_float2(v.x, v.y)); ++c32; }
-            if (up1) { ab = __fadd2_rn(ab, make_float2(v.z, v.w)); ++c32; }
-            if (!up0 && p0 <= thr_keep) mask |= bit;
-            if (!up1 && p1 <= thr_keep) mask |= bit << 1;
-          };
-          int m = 0;
-          const int lo_rows = full_rows < 16 ? full_rows : 16;
+    if (!nonfinite && window) {
+      // ---------------------------------------------------------------- sweep B: classify, build the exact-needed mask
+      unsigned mask[kMaskWords] = {0u, 0u, 0u, 0u};   // bit (kQ kPerLoad m + kPerLoad q + e) of the concatenation
+      int c32 = 0;                                    // "surely above" by the fp32 bound
+      unsigned long long ab64 = 0ull;                 // packed (sum x, sum y) of their raw fp32 coordinates
+      constexpr int kBitsPerTile = kQ * kPerLoad;     // 4 (fp32) / 2 (fp64)
+      constexpr int kTilesPerWord = 32 / kBitsPerTile;
+      if constexpr (kF32) {
+        const float4* sm4 = reinterpret_cast<const float4*>(smem_raw);
+        const float h0f = ctl->h0f, h1f = ctl->h1f, thr_keep = ctl->thr_keep, thr_above = ctl->thr_above;
+#pragma unroll
+        for (int wd = 0; wd < kMaskWords; ++wd) {
+          const int m_lo = wd * kTilesPerWord;
+          const int m_hi = full_tiles < m_lo + kTilesPerWord ? full_tiles : m_lo + kTilesPerWord;
           unsigned bit = 1u;
-#pragma unroll 4
-          for (; m < lo_rows; ++m, bit <<= 2) classify2(sm4[m * kThreads + tid], mlo, bit);
-          bit = 1u;
-#pragma unroll 4
-          for (; m < full_rows; ++m, bit <<= 2) classify2(sm4[m * kThreads + tid], mhi, bit);
-          if (full_rows < rows) {  // ragged last tile
-            const int i0 = full_rows * kTile + 2 * tid;
-            const unsigned bitr = 1u << (2 * (full_rows & 15));
-            unsigned& mask = full_rows < 16 ? mlo : mhi;
+#pragma unroll 2
+          for (int m = m_lo; m < m_hi; ++m) {
+#pragma unroll
+            for (int q = 0; q < kQ; ++q) {
+              const float4 v = sm4[m * kSlots + q * kSweepThreads + tid];
+              const float p0 = fmaf(h1f, v.y, h0f * v.x), p1 = fmaf(h1f, v.w, h0f * v.z);
+              classify_f32(p0, thr_above, thr_keep, pack2(v.x, v.y), ab64, c32, mask[wd], bit << (2 * q));
+              classify_f32(p1, thr_above, thr_keep, pack2(v.z, v.w), ab64, c32, mask[wd], bit << (2 * q + 1));
+            }
+            bit <<= kBitsPerTile;
+          }
+        }
+        if (full_tiles < tiles) {  // ragged last tile
+          const int wd = full_tiles / kTilesPerWord;
+          const unsigned bit0 = 1u << ((full_tiles % kTilesPerWord) * kBitsPerTile);
+          unsigned mk = 0;
+#pragma unroll
+          for (int q = 0; q < kQ; ++q) {
+            const int i0 = full_tiles * kTile + 2 * (q * kSweepThreads + tid);
             if (i0 < N) {
               const float2 v = sm[i0];
-              const float p = fmaf(h1f, v.y, h0f * v.x);
-              if (p < thr_above) { ab = __fadd2_rn(ab, v); ++c32; }
-              else if (p <= thr_keep) mask |= bitr;
+              classify_f32(fmaf(h1f, v.y, h0f * v.x), thr_above, thr_keep, pack2(v.x, v.y), ab64, c32, mk, bit0 << (2 * q));
             }
             if (i0 + 1 < N) {
               const float2 v = sm[i0 + 1];
-              const float p = fmaf(h1f, v.y, h0f * v.x);
-              if (p < thr_above) { ab = __fadd2_rn(ab, v); ++c32; }
-              else if (p <= thr_keep) mask |= bitr << 1;
+              classify_f32(fmaf(h1f, v.y, h0f * v.x), thr_above, thr_keep, pack2(v.x, v.y), ab64, c32, mk, bit0 << (2 * q + 1));
             }
           }
-        } else {
+#pragma unroll
+          for (int w2 = 0; w2 < kMaskWords; ++w2)
+            if (w2 == wd) mask[w2] |= mk;
+        }
+      } else {
+#pragma unroll
+        for (int wd = 0; wd < kMaskWords; ++wd) {
+          const int m_lo = wd * kTilesPerWord;
+          const int m_hi = tiles < m_lo + kTilesPerWord ? tiles : m_lo + kTilesPerWord;
           unsigned bit = 1u;
-          int m = 0;
-          for (int i = tid; i < N; i += kThreads, ++m, bit = (bit << 1) | (bit >> 31)) {
-            const V2 v = sm[i];
-            const double L = loss_of(h0, h1, v.x, v.y);
-            if (L > t_hi) {
-              ++c_gt;
-              s_gt += L;
-            } else if (L >= t_lo) {
-              if (m < 32) mlo |= bit; else mhi |= bit;
-            }
-          }
-        }
-
-        // -------------------------------------------------------------- phase 2: compact the masked samples per warp
-        const int mine_n = __popc(mlo) + __popc(mhi);
-        int incl = mine_n;
+          for (int m = m_lo; m < m_hi; ++m) {
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int t = __shfl_up_sync(kFull, incl, d);
-          if (lane >= d) incl += t;
-        }
-        const int n_list = __shfl_sync(kFull, incl, 31);
-        bool overflow = n_list > kWarpList;
-        if (!overflow) {
-          int pos = incl - mine_n;
-          unsigned mm = mlo;
-          while (mm) {
-            const int bitpos = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const int i = kF32 ? ((bitpos >> 1) * kTile + 2 * tid + (bitpos & 1)) : (bitpos * kThreads + tid);
-            wlist[pos++] = static_cast<unsigned short>(i);
-          }
-          mm = mhi;
-          while (mm) {
-            const int bitpos = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const int i = kF32 ? (((bitpos >> 1) + 16) * kTile + 2 * tid + (bitpos & 1)) : ((bitpos + 32) * kThreads + tid);
-            wlist[pos++] = static_cast<unsigned short>(i);
-          }
-        }
-        __syncwarp();
-        // exact canonical loss of the listed samples, dense over the warp; window losses -> candidates + histogram
-        int nc = 0;  // candidates of this warp (warp-uniform)
-        const unsigned long long klo = ctl->key_lo;
-        const int hshift = ctl->hist_shift;
-        if (!overflow) {
-          for (int k0 = 0; k0 < n_list; k0 += 32) {
-            const int k = k0 + lane;
-            const bool active = k < n_list;
-            double L = 0.0;
-            if (active) {
-              const V2 v = sm[wlist[k]];
-              L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
-            }
-            const bool up = active && (L > t_hi);
-            const bool cd = active && !up && (L >= t_lo);
-            if (kF32 && up) {  // (fp64 inputs were classified exactly in sweep B; the list holds candidates only)
-              ++c_gt;
-              s_gt += L;
-            }
-            const unsigned bal = __ballot_sync(kFull, cd);
-            if (bal) {
-              const int pos = nc + __popc(bal & ((1u << lane) - 1u));
-              if (cd && pos < kWarpCand) {
-                wcand[pos] = L;
-                atomicAdd(&hist[static_cast<unsigned>((key_of(L) - klo) >> hshift)], 1u);
-              }
-              nc += __popc(bal);
-            }
-          }
-          overflow = nc > kWarpCand;
-        }
-        // per-warp partials -> fin[]: {exact sum, raw x sum, raw y sum}, ired[]: {exact count + fp32 count, candidates}
-        {
-          const int wc = __reduce_add_sync(kFull, c_gt + c32);
-          const double ws = warp_sum_any(s_gt);
-          const double wx = warp_sum_any(static_cast<double>(ab.x));
-          const double wy = warp_sum_any(static_cast<double>(ab.y));
-          if (lane == 0) {
-            ired[warp * 2] = wc;
-            ired[warp * 2 + 1] = nc;
-            fin[warp * 8 + 0] = ws;
-            fin[warp * 8 + 1] = wx;
-            fin[warp * 8 + 2] = wy;
-          }
-        }
-        const int ovf = __syncthreads_or(overflow);  // S3
-        int cnt_hi = 0, ncand = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-          cnt_hi += ired[w * 2];
-          ncand += ired[w * 2 + 1];
-        }
-        fast = !ovf && cnt_hi < a.kc && a.kc <= cnt_hi + ncand;
-        if (fast) {
-          // the sample slot is dead from here on (unless tail indices are wanted): prefetch the next halfspace
-          if (!kTail && a.bulk && tid == 0 && b_next < a.B) issue_bulk(b_next);
-          next_issued = !kTail && a.bulk;
-          // warp 0: scan the histogram from the top for the bucket holding rank r
-          if (warp == 0) {
-            const int r = a.kc - cnt_hi;
-            int run = 0, row = -1, r_row = 0;
-#pragma unroll
-            for (int i = 0; i < kHistBuckets / 32; ++i) {
-              const int tot = __reduce_add_sync(kFull, static_cast<int>(hist[kHistBuckets - 1 - (32 * i + lane)]));
-              if (row < 0 && run + tot >= r) {
-                row = i;
-                r_row = r - run;
-              }
-              run += tot;
-            }
-            if (row < 0) { row = kHistBuckets / 32 - 1; r_row = 1; }
-            const int bucket = kHistBuckets - 1 - (32 * row + lane);
-            const int c = static_cast<int>(hist[bucket]);
-            int inc2 = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-              const int t = __shfl_up_sync(kFull, inc2, d);
-              if (lane >= d) inc2 += t;
-            }
-            const int excl = inc2 - c;
-            if (excl < r_row && r_row <= inc2) {
-              ctl->bstar = bucket;
-              ctl->rprime = r_row - excl;
-              ctl->cnt_in = c;
-            }
-          }
-          __syncthreads();  // S4
-          const int bstar = ctl->bstar, cnt_in = ctl->cnt_in;
-          if (cnt_in <= kResolveMax) {
-            // candidates above bucket b* are above T; bucket b* goes to one warp for exact ranking
-            double s3 = 0.0;
-            int c3 = 0;
-            for (int j = lane; j < nc; j += 32) {
-              const double L = wcand[j];
-              const int bk = static_cast<int>((key_of(L) - klo) >> hshift);
-              if (bk > bstar) {
-                ++c3;
-                s3 += L;
-              } else if (bk == bstar) {
-                const int pos = atomicAdd(&ctl->small_n, 1);
-                if (pos < kResolveMax) small[pos] = L;
+            for (int q = 0; q < kQ; ++q) {
+              const int i = m * kSlots + q * kSweepThreads + tid;
+              if (i < N) {
+                const V2 v = sm[i];
+                const double L = loss_of(h0, h1, v.x, v.y);
+                if (L > t_hi) {
+                  ++c_gt;
+                  s_gt += L;
+                } else if (L >= t_lo) {
+                  mask[wd] |= bit << q;
+                }
               }
             }
-            const int wc3 = __reduce_add_sync(kFull, c3);
-            const double ws3 = warp_sum_any(s3);
-            if (lane == 0) {
-              ired[2 * kWarps + warp] = wc3;
-              fin[warp * 8 + 3] = ws3;
-            }
-            __syncthreads();  // S5
-            finished_by_warp0 = true;
-            if (warp == 0) {
-              // resolve T inside bucket b*: all-pairs rank; then sum the bucket members above T in rank order
-              const int r = ctl->rprime;
-              const double mineL = lane < cnt_in ? small[lane] : 0.0;
-              const unsigned long long mine = lane < cnt_in ? key_of(mineL) : 0ull;
-              int rank = 0;
-              for (int j = 0; j < cnt_in; ++j) {
-                const unsigned long long other = __shfl_sync(kFull, mine, j);
-                rank += (other > mine) || (other == mine && j < lane);
-              }
-              const unsigned owner = __ballot_sync(kFull, lane < cnt_in && rank == r - 1);
-              const double Tval = __shfl_sync(kFull, mineL, __ffs(owner) - 1);
-              // deterministic: place by rank, then butterfly
-              __syncwarp();
-              if (lane < cnt_in) small[rank] = mineL;
-              __syncwarp();
-              const double byrank = (lane < cnt_in && lane < r - 1) ? small[lane] : 0.0;  // ranks 0..r-2 are > or == T
-              const bool strictly = (lane < cnt_in && lane < r - 1) && (key_of(byrank) > key_of(Tval));
-              const double s4 = warp_sum_any(strictly ? byrank : 0.0);
-              const int c4 = __popc(__ballot_sync(kFull, strictly));
-              T_thr = Tval;
-              // totals
-              double s_exact = 0.0, s_x = 0.0, s_y = 0.0, s_c = 0.0;
-              int c_all = cnt_hi + c4;
-#pragma unroll
-              for (int w = 0; w < kWarps; ++w) {
-                s_exact += fin[w * 8 + 0];
-                s_x += fin[w * 8 + 1];
-                s_y += fin[w * 8 + 2];
-                s_c += fin[w * 8 + 3];
-                c_all += ired[2 * kWarps + w];
-              }
-              // loss sum of the "surely above" set by linearity: sum_i -(h.xi_i) = -(h0 sum x + h1 sum y)
-              const double s_lin = -(h0 * s_x + h1 * s_y);
-              s_gt = ((s_exact + s_lin) + s_c) + s4;
-              c_gt = c_all;
-              if (kTail && lane == 0) {
-                ctl->T = T_thr;
-                ctl->c_tot = c_all;
-              }
-            }
-          } else {
-            // a dense / heavily tied bucket: finish with the general narrowing loop on the candidates
-            const unsigned long long lo2 = klo + (static_cast<unsigned long long>(bstar) << hshift);
-            unsigned long long hi2 = lo2 + ((1ull << hshift) - 1ull);
-            const unsigned long long khi = key_of(t_hi);
-            if (hi2 > khi || hi2 < lo2) hi2 = khi;
-            // everything above bucket b* is above T
-            int above_b = 0;
-            for (int j = lane; j < nc; j += 32) above_b += static_cast<int>((key_of(wcand[j]) - klo) >> hshift) > bstar;
-            (void)above_b;
-            T_thr = select_rank(
-                [&](auto&& f) {
-                  for (int j = lane; j < nc; j += 32) f(wcand[j]);
-                },
-                lo2, hi2, ctl->rprime, hist, small, ctl);
-            for (int j = lane; j < nc; j += 32) {
-              const double L = wcand[j];
-              if (L > T_thr) {
-                ++c_gt;
-                s_gt += L;
-              }
-            }
-            // fold the fp32 "surely above" set in (thread 0 of each warp carries the warp's linear part)
-            c_gt += c32;
-            const double wx = warp_sum_any(static_cast<double>(ab.x));
-            const double wy = warp_sum_any(static_cast<double>(ab.y));
-            if (lane == 0) s_gt += -(h0 * wx + h1 * wy);
+            bit <<= kBitsPerTile;
           }
         }
       }
-      if (!fast) {
+
+      // -------------------------------------------------------------- phase 2: exact loss of the masked samples
+      // warp-lockstep over each lane's k-th masked sample; window losses -> candidates + histogram
+      int nc = 0;  // candidates of this warp (warp-uniform)
+      const unsigned long long klo = ctl->key_lo;
+      const int hshift = ctl->hist_shift;
+#pragma unroll
+      for (int wd = 0; wd < kMaskWords; ++wd) {
+        unsigned mm = mask[wd];
+        while (__any_sync(kFull, mm != 0)) {
+          const bool active = mm != 0;
+          double L = 0.0;
+          if (active) {
+            const int bp = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const int m = wd * kTilesPerWord + bp / kBitsPerTile;
+            const int within = bp % kBitsPerTile;
+            const int slot = (within / kPerLoad) * kSweepThreads + tid;
+            const int i = m * kTile + slot * kPerLoad + (within % kPerLoad);
+            const V2 v = sm[i];
+            L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
+          }
+          const bool up = active && (L > t_hi);
+          const bool cd = active && !up && (L >= t_lo);
+          if (kF32 && up) {  // inside the fp32 uncertainty band but exactly above the window
+            ++c_gt;
+            s_gt += L;
+          }
+          const unsigned bal = __ballot_sync(kFull, cd);
+          if (bal) {
+            const int pos = nc + __popc(bal & ((1u << lane) - 1u));
+            if (cd && pos < kWarpCand) {
+              wcand[pos] = L;
+              atomicAdd(&hist[static_cast<unsigned>((key_of(L) - klo) >> hshift)], 1u);
+            }
+            nc += __popc(bal);
+          }
+        }
+      }
+      // per-warp partials
+      {
+        const int wc = __reduce_add_sync(kFull, c_gt + c32);
+        const double ws = warp_sum_any(s_gt);
+        // packed fp32 warp sum of the raw coordinate sums, widened at the end
+        float2 t = unpack2(ab64);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1)
+          t = __fadd2_rn(t, make_float2(__shfl_xor_sync(kFull, t.x, m), __shfl_xor_sync(kFull, t.y, m)));
+        if (lane == 0) {
+          ired[warp * 2] = wc;
+          ired[warp * 2 + 1] = nc < kWarpCand ? nc : kWarpCand;
+          fin[warp * 4 + 0] = static_cast<double>(t.x);
+          fin[warp * 4 + 1] = static_cast<double>(t.y);
+          fin[warp * 4 + 2] = ws;
+        }
+      }
+      const int ovf = team_sync_or(nc > kWarpCand);  // S3: the sample slot is no longer read on the fast path
+      int cnt_hi = 0, ncand = 0;
+#pragma unroll
+      for (int w = 0; w < kSweepWarps; ++w) {
+        cnt_hi += ired[w * 2];
+        ncand += ired[w * 2 + 1];
+      }
+      fast = !ovf && cnt_hi < a.kc && a.kc <= cnt_hi + ncand;
+      if (fast) {
+        if (tid == 0) {
+          if (!kTail && a.bulk && b_next < a.B) issue_bulk(b_next);
+          ctl->mode = kModeFinish;
+          ctl->cnt_hi = cnt_hi;
+          ctl->status = status;
+          mbar_arrive(&bars->full[par]);   // hand halfspace b to the finisher warp
+        }
+        next_issued = !kTail && a.bulk;
+        if (kTail) {
+          // parity mode: the sweep team needs T and the total count to emit the tail indices
+          mbar_wait(&bars->empty[par], use & 1);
+          T_thr = ctl->T;
+          c_gt = 0;
+        }
+      }
+    }
+
+    int c_tot = 0;
+    if (!fast) {
+      if (!nonfinite) {
         // -------------------------------------------------------------- general path: sweeps over all samples
         status |= kStatusGeneral;
         unsigned long long kmin = ~0ull, kmax = 0ull;
-        for (int i = tid; i < N; i += kThreads) {
+        for (int i = tid; i < N; i += kSweepThreads) {
           const V2 v = sm[i];
           const unsigned long long k = key_of(loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y)));
           kmin = k < kmin ? k : kmin;
@@ -788,28 +931,28 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           kmax = o2 > kmax ? o2 : kmax;
         }
         unsigned long long* kred = reinterpret_cast<unsigned long long*>(red);
-        __syncthreads();  // red[] of this iteration was consumed by warp 0 above
+        team_sync();  // red[] was consumed by warp 0 above; hist/small of this parity are ours until the handoff
         if (lane == 0) {
           kred[warp * 2] = kmin;
           kred[warp * 2 + 1] = kmax;
         }
-        __syncthreads();
+        team_sync();
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
+        for (int w = 0; w < kSweepWarps; ++w) {
           kmin = kred[w * 2] < kmin ? kred[w * 2] : kmin;
           kmax = kred[w * 2 + 1] > kmax ? kred[w * 2 + 1] : kmax;
         }
         T_thr = select_rank(
             [&](auto&& f) {
-              for (int i = tid; i < N; i += kThreads) {
+              for (int i = tid; i < N; i += kSweepThreads) {
                 const V2 v = sm[i];
                 f(loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y)));
               }
             },
-            kmin, kmax, a.kc, hist, small, ctl);
+            [] { team_sync(); }, warp == 0, tid, kSweepThreads, kmin, kmax, a.kc, hist, small, ctl);
         c_gt = 0;
         s_gt = 0.0;
-        for (int i = tid; i < N; i += kThreads) {
+        for (int i = tid; i < N; i += kSweepThreads) {
           const V2 v = sm[i];
           const double L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
           if (L > T_thr) {
@@ -817,31 +960,27 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
             s_gt += L;
           }
         }
+      } else {
+        c_gt = 0;
+        s_gt = 0.0;
       }
-    }
-
-    // ------------------------------------------------------------------ block totals of (c_gt, s_gt) unless warp 0 has them
-    int c_tot = c_gt;
-    double s_tot = s_gt;
-    if (!finished_by_warp0) {
+      // team totals of (c_gt, s_gt)
       const int wc = __reduce_add_sync(kFull, c_gt);
       const double ws = warp_sum_any(s_gt);
-      __syncthreads();  // protects ired / fin reuse
+      team_sync();
       if (lane == 0) {
-        ired[3 * kWarps + warp] = wc;
-        fin[warp * 8 + 4] = ws;
+        iscr[warp] = wc;
+        red[warp] = ws;
       }
-      __syncthreads();
-      c_tot = 0;
-      s_tot = 0.0;
+      team_sync();
+      double s_tot = 0.0;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) {
-        c_tot += ired[3 * kWarps + w];
-        s_tot += fin[w * 8 + 4];
+      for (int w = 0; w < kSweepWarps; ++w) {
+        c_tot += iscr[w];
+        s_tot += red[w];
       }
+      if (tid == 0) write_outputs(a, b, ctl, nonfinite, s_tot, c_tot, T_thr, status);
     } else if (kTail) {
-      __syncthreads();  // T and the total count were produced by warp 0
-      T_thr = ctl->T;
       c_tot = ctl->c_tot;
     }
 
@@ -849,14 +988,14 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     if (kTail && a.tail_idx_out != nullptr) {
       int* out = a.tail_idx_out + b * static_cast<long long>(a.kc);
       if (nonfinite) {
-        for (int i = tid; i < a.kc; i += kThreads) out[i] = -1;
+        for (int i = tid; i < a.kc; i += kSweepThreads) out[i] = -1;
       } else {
         const int need = a.kc - c_tot;
         int run_eq = 0, run_out = 0;
-        int* weq = ired;           // [kWarps]
-        int* wsel = ired + kWarps; // [kWarps]
-        __syncthreads();
-        for (int bb = 0; bb < N; bb += kThreads) {
+        int* weq = iscr + kSweepWarps;       // [kSweepWarps]
+        int* wsel = iscr + 2 * kSweepWarps;  // [kSweepWarps]
+        team_sync();
+        for (int bb = 0; bb < N; bb += kSweepThreads) {
           const int i = bb + tid;
           const bool valid = i < N;
           double L = 0.0;
@@ -867,10 +1006,10 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           const bool gt = valid && (L > T_thr), eq = valid && (L == T_thr);
           const unsigned meq = __ballot_sync(kFull, eq);
           if (lane == 0) weq[warp] = __popc(meq);
-          __syncthreads();
+          team_sync();
           int eq_before = run_eq, tile_eq = 0;
 #pragma unroll
-          for (int w = 0; w < kWarps; ++w) {
+          for (int w = 0; w < kSweepWarps; ++w) {
             if (w < warp) eq_before += weq[w];
             tile_eq += weq[w];
           }
@@ -878,74 +1017,31 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           const bool sel = gt || (eq && eq_rank < need);
           const unsigned msel = __ballot_sync(kFull, sel);
           if (lane == 0) wsel[warp] = __popc(msel);
-          __syncthreads();
+          team_sync();
           int out_before = run_out, tile_sel = 0;
 #pragma unroll
-          for (int w = 0; w < kWarps; ++w) {
+          for (int w = 0; w < kSweepWarps; ++w) {
             if (w < warp) out_before += wsel[w];
             tile_sel += wsel[w];
           }
           if (sel) out[out_before + __popc(msel & ((1u << lane) - 1u))] = i;
           run_eq += tile_eq;
           run_out += tile_sel;
-          __syncthreads();
+          team_sync();
         }
       }
     }
 
-    // ------------------------------------------------------------------ epilogue (one thread)
-    if (tid == 0) {
-      const double m0 = ctl->m0, m1 = ctl->m1;
-      const double hn = norm2_canon(h0, h1);
-      const double r = __dmul_rn(a.R, hn);
-      double cvar, g_cvar, g_star, g_dr, var_t;
-      if (nonfinite) {
-        cvar = __longlong_as_double(0x7ff8000000000000ll);
-        var_t = cvar;
-        g_cvar = 100.0;
-        g_star = 100.0;
-        g_dr = __dsub_rn(100.0, r);
-      } else {
-        const double S = __dadd_rn(s_tot, __dmul_rn(__dsub_rn(a.k_f, static_cast<double>(c_tot)), T_thr));
-        cvar = __ddiv_rn(S, a.k_f);
-        var_t = T_thr;
-        const double cr = __dadd_rn(cvar, r);
-        g_cvar = __dsub_rn(cr, a.delta);
-        g_star = __dsub_rn(__dadd_rn(cr, a.eoa), a.delta);
-        g_dr = __dsub_rn(g_star, r);
-      }
-      // mean halfspace: direction from the ORIGIN (core/halfspaces.py:88)
-      double hm0, hm1;
-      const double mn = norm2_canon(m0, m1);
-      if (mn < 1e-10) {
-        hm0 = 1.0;
-        hm1 = 0.0;
-      } else {
-        hm0 = __ddiv_rn(m0, mn);
-        hm1 = __ddiv_rn(m1, mn);
-      }
-      const double hmn = norm2_canon(hm0, hm1);
-      const double g_mean =
-          -__dsub_rn(__dadd_rn(__dmul_rn(hm0, m0), __dmul_rn(hm1, m1)), __dmul_rn(a.R, hmn));
-      a.h_out[2 * b] = h0;
-      a.h_out[2 * b + 1] = h1;
-      if (a.h_mean_out) {
-        a.h_mean_out[2 * b] = hm0;
-        a.h_mean_out[2 * b + 1] = hm1;
-      }
-      a.g_out[3 * b] = g_mean;
-      a.g_out[3 * b + 1] = g_cvar;
-      a.g_out[3 * b + 2] = g_dr;
-      if (a.cvar_out) a.cvar_out[b] = cvar;
-      if (a.var_out) a.var_out[b] = var_t;
-      if (a.gstar_out) a.gstar_out[b] = g_star;
-      if (a.status_out) a.status_out[b] = status;
-    }
-
-    // ------------------------------------------------------------------ release the slot / prefetch
+    // ------------------------------------------------------------------ release the slot / prefetch / keep the pipeline in step
     if (!next_issued) {
-      __syncthreads();
-      if (a.bulk && tid == 0 && b_next < a.B) issue_bulk(b_next);
+      team_sync();
+      if (tid == 0) {
+        if (a.bulk && b_next < a.B) issue_bulk(b_next);
+        if (!fast) {
+          ctl->mode = kModeSkip;   // result already written by the team: the finisher only recycles the buffers
+          mbar_arrive(&bars->full[par]);
+        }
+      }
     }
   }
 }
