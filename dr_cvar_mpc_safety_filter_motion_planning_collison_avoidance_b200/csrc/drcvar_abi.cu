@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -92,6 +93,10 @@ bool plan_window(long long n, long long kc, double* z_lo, double* z_hi) {
   return true;
 }
 
+#ifdef DRCVAR_PROFILE_PHASES
+long long* g_phase_cycles = nullptr;  // device buffer [4096][2][12], set by drcvar_debug_phase_buffer()
+#endif
+
 struct DeviceInfo {
   bool ready = false;
   int sms = 0;
@@ -170,13 +175,21 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   a.status_out = c.status_out;
   a.tail_idx_out = c.tail_idx_out;
 
+#ifdef DRCVAR_PROFILE_PHASES
+  a.phase_cycles = g_phase_cycles;
+#else
+  a.phase_cycles = nullptr;
+#endif
   const bool tail = c.tail_idx_out != nullptr;
   auto kern = tail ? halfspace_kernel<T, true> : halfspace_kernel<T, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
   if (per_sm < 1) return fail(DRCVAR_ERR_UNSUPPORTED, "kernel does not fit on an SM for N=%lld", c.N);
-  const long long grid = std::min<long long>(c.B, static_cast<long long>(per_sm) * di->sms);
+  long long grid = std::min<long long>(c.B, static_cast<long long>(per_sm) * di->sms);
+#ifdef DRCVAR_PROFILE_PHASES
+  if (const char* e = getenv("DRCVAR_DEBUG_GRID")) grid = std::min<long long>(grid, atoll(e));
+#endif
   kern<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -492,6 +505,11 @@ void drcvar_host_free(void* p) {
 }
 
 int64_t drcvar_launch_count(void) { return g_launches.load(); }
+
+#ifdef DRCVAR_PROFILE_PHASES
+// profiling builds only (not part of include/drcvar.h): device buffer receiving per-CTA phase cycle counts
+void drcvar_debug_phase_buffer(long long* dev_buf) { g_phase_cycles = dev_buf; }
+#endif
 
 int drcvar_last_host_call_stats(double* stage_ms, double* kernel_ms, int64_t* h2d_bytes, int64_t* d2h_bytes) {
   if (stage_ms) *stage_ms = g_host.last_stage_ms;

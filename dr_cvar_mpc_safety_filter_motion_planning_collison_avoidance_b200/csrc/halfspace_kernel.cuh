@@ -27,6 +27,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Optional phase timing (profiling builds only: -DDRCVAR_PROFILE_PHASES; see profiles/README.md)
+#ifdef DRCVAR_PROFILE_PHASES
+#define PH_DECL long long ph_t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long ph_last = clock64();
+#define PH_MARK(k) { const long long ph_now = clock64(); ph_t[k] += ph_now - ph_last; ph_last = ph_now; }
+#else
+#define PH_DECL
+#define PH_MARK(k)
+#endif
+
 namespace drcvar {
 
 constexpr int kSweepWarps = 8;
@@ -69,6 +78,7 @@ struct KernelArgs {
   double* gstar_out;
   int* status_out;
   int* tail_idx_out;
+  long long* phase_cycles;   // profiling builds: [grid][2][12] accumulated cycles (sweep warp 1, finisher)
 };
 
 struct Ctl {                        // one per parity buffer
@@ -129,7 +139,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
@@ -396,6 +406,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   // ============================================================================================ finisher warp
   if (warp == kSweepWarps) {
     int iter = 0;
+    PH_DECL
     for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
       const int par = iter & 1, use = iter >> 1;
       Ctl* ctl = ctl_base + par;
@@ -405,10 +416,19 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       const int* ired = ired_base + par * 2 * kSweepWarps;
       double* small = small_base + par * kResolveMax;
       mbar_wait(&bars->full[par], use & 1);
+      PH_MARK(0)
       if (ctl->mode == kModeFinish) {
         const int cnt_hi = ctl->cnt_hi;
         const unsigned long long klo = ctl->key_lo;
         const int hshift = ctl->hist_shift;
+        // histogram of the window candidates (256 monotone buckets between key(t_lo) and key(t_hi))
+        for (int w = 0; w < kSweepWarps; ++w) {
+          const int nc = ired[w * 2 + 1];
+          const double* wc = cand + w * kWarpCand;
+          for (int j = lane; j < nc; j += 32)
+            atomicAdd(&hist[static_cast<unsigned>((key_of(wc[j]) - klo) >> hshift)], 1u);
+        }
+        __syncwarp();
         int bstar, r, cnt_in;
         scan_hist_warp(hist, a.kc - cnt_hi, lane, bstar, r, cnt_in);
         // pass over all candidates: above bucket b* -> counted/summed; bucket b* -> gathered for exact ranking
@@ -508,7 +528,12 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       if (lane == 0) ctl->small_n = 0;
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->empty[par]);
+      PH_MARK(1)
     }
+#ifdef DRCVAR_PROFILE_PHASES
+    if (lane == 0 && a.phase_cycles)
+      for (int k = 0; k < 12; ++k) a.phase_cycles[(blockIdx.x * 2 + 1) * 12 + k] = ph_t[k];
+#endif
     return;
   }
 
@@ -528,6 +553,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   int iter = 0;
   const int tiles = (N + kTile - 1) / kTile;
   const int full_tiles = N / kTile;
+  PH_DECL
 
   for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
     const int par = iter & 1, use = iter >> 1;
@@ -557,6 +583,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     }
     // parity buffers must have been handed back by the finisher (two iterations ago)
     if (use > 0) mbar_wait(&bars->empty[par], (use - 1) & 1);
+    PH_MARK(0)
 
     // ------------------------------------------------------------------ sweep A: canonical lane sums (+ heuristics)
     double sx[kQ], sy[kQ];                          // this thread's kQ slots of the 512-wide fp64 tree (slot = tid + 256 q)
@@ -577,15 +604,25 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         qxy = fmaf(dx0, dy0, fmaf(dx1, dy1, qxy));
         qyy = fmaf(dy0, dy0, fmaf(dy1, dy1, qyy));
       };
-#pragma unroll 2
-      for (int m = 0; m < full_tiles; ++m) {
+      auto body = [&](const float4 v, int q) {
+        acc[q][0] = __fadd2_rn(acc[q][0], make_float2(v.x, v.y));
+        acc[q][1] = __fadd2_rn(acc[q][1], make_float2(v.z, v.w));
+        amax = absmax3(absmax3(amax, v.x, v.y), v.z, v.w);
+      };
+      if (mom_warp) {
+        for (int m = 0; m < full_tiles; ++m) {
 #pragma unroll
-        for (int q = 0; q < kQ; ++q) {
-          const float4 v = sm4[m * kSlots + q * kSweepThreads + tid];   // samples 1024 m + 2 slot, +1
-          acc[q][0] = __fadd2_rn(acc[q][0], make_float2(v.x, v.y));
-          acc[q][1] = __fadd2_rn(acc[q][1], make_float2(v.z, v.w));
-          amax = absmax3(absmax3(amax, v.x, v.y), v.z, v.w);
-          if (mom_warp) moments(v);
+          for (int q = 0; q < kQ; ++q) {
+            const float4 v = sm4[m * kSlots + q * kSweepThreads + tid];   // samples 1024 m + 2 slot, +1
+            body(v, q);
+            moments(v);
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int m = 0; m < full_tiles; ++m) {
+#pragma unroll
+          for (int q = 0; q < kQ; ++q) body(sm4[m * kSlots + q * kSweepThreads + tid], q);
         }
       }
       if (full_tiles < tiles) {  // ragged last tile: element-wise
@@ -666,7 +703,9 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       }
       if (lane == 0) red[2 * kGroups + 16 + warp] = static_cast<double>(__uint_as_float(mxb));
     }
+    PH_MARK(1)
     team_sync();  // S1
+    PH_MARK(2)
 
     // ------------------------------------------------------------------ direction + window (warp 0)
     if (warp == 0) {
@@ -747,6 +786,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       }
     }
     team_sync();  // S2
+    PH_MARK(3)
     const double h0 = ctl->h0, h1 = ctl->h1;
     const bool nonfinite = ctl->nonfinite != 0;
     const bool window = ctl->window_ok != 0;
@@ -760,133 +800,137 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
 
     if (!nonfinite && window) {
       // ---------------------------------------------------------------- sweep B: classify, build the exact-needed mask
-      unsigned mask[kMaskWords] = {0u, 0u, 0u, 0u};   // bit (kQ kPerLoad m + kPerLoad q + e) of the concatenation
-      int c32 = 0;                                    // "surely above" by the fp32 bound
+      // rows: 16-byte loads in visit order, row r = smem vector index r*256 + tid.  Mask bit P = kPerLoad r + e.
+      unsigned mask[kMaskWords] = {0u, 0u, 0u, 0u};
+      int c32 = 0;                                    // "surely above" (fp32 bound, or exactly in the band)
       unsigned long long ab64 = 0ull;                 // packed (sum x, sum y) of their raw fp32 coordinates
-      constexpr int kBitsPerTile = kQ * kPerLoad;     // 4 (fp32) / 2 (fp64)
-      constexpr int kTilesPerWord = 32 / kBitsPerTile;
+      constexpr int kRowsPerWord = 32 / kPerLoad;     // 16 (fp32) / 32 (fp64)
+      const int full_rows = full_tiles * kQ;
       if constexpr (kF32) {
         const float4* sm4 = reinterpret_cast<const float4*>(smem_raw);
         const float h0f = ctl->h0f, h1f = ctl->h1f, thr_keep = ctl->thr_keep, thr_above = ctl->thr_above;
 #pragma unroll
         for (int wd = 0; wd < kMaskWords; ++wd) {
-          const int m_lo = wd * kTilesPerWord;
-          const int m_hi = full_tiles < m_lo + kTilesPerWord ? full_tiles : m_lo + kTilesPerWord;
-          unsigned bit = 1u;
-#pragma unroll 2
-          for (int m = m_lo; m < m_hi; ++m) {
-#pragma unroll
-            for (int q = 0; q < kQ; ++q) {
-              const float4 v = sm4[m * kSlots + q * kSweepThreads + tid];
-              const float p0 = fmaf(h1f, v.y, h0f * v.x), p1 = fmaf(h1f, v.w, h0f * v.z);
-              classify_f32(p0, thr_above, thr_keep, pack2(v.x, v.y), ab64, c32, mask[wd], bit << (2 * q));
-              classify_f32(p1, thr_above, thr_keep, pack2(v.z, v.w), ab64, c32, mask[wd], bit << (2 * q + 1));
-            }
-            bit <<= kBitsPerTile;
+          const int r_lo = wd * kRowsPerWord;
+          const int r_hi = full_rows < r_lo + kRowsPerWord ? full_rows : r_lo + kRowsPerWord;
+          unsigned bit0 = 1u, bit1 = 2u;
+#pragma unroll 4
+          for (int r = r_lo; r < r_hi; ++r) {
+            const float4 v = sm4[r * kSweepThreads + tid];
+            const float p0 = fmaf(h1f, v.y, h0f * v.x), p1 = fmaf(h1f, v.w, h0f * v.z);
+            classify_f32(p0, thr_above, thr_keep, pack2(v.x, v.y), ab64, c32, mask[wd], bit0);
+            classify_f32(p1, thr_above, thr_keep, pack2(v.z, v.w), ab64, c32, mask[wd], bit1);
+            bit0 <<= 2;
+            bit1 <<= 2;
           }
         }
-        if (full_tiles < tiles) {  // ragged last tile
-          const int wd = full_tiles / kTilesPerWord;
-          const unsigned bit0 = 1u << ((full_tiles % kTilesPerWord) * kBitsPerTile);
-          unsigned mk = 0;
+        if (full_tiles < tiles) {  // ragged last tile, element-wise
 #pragma unroll
           for (int q = 0; q < kQ; ++q) {
-            const int i0 = full_tiles * kTile + 2 * (q * kSweepThreads + tid);
-            if (i0 < N) {
-              const float2 v = sm[i0];
-              classify_f32(fmaf(h1f, v.y, h0f * v.x), thr_above, thr_keep, pack2(v.x, v.y), ab64, c32, mk, bit0 << (2 * q));
-            }
-            if (i0 + 1 < N) {
-              const float2 v = sm[i0 + 1];
-              classify_f32(fmaf(h1f, v.y, h0f * v.x), thr_above, thr_keep, pack2(v.x, v.y), ab64, c32, mk, bit0 << (2 * q + 1));
-            }
-          }
+            const int rr = full_rows + q;
 #pragma unroll
-          for (int w2 = 0; w2 < kMaskWords; ++w2)
-            if (w2 == wd) mask[w2] |= mk;
-        }
-      } else {
-#pragma unroll
-        for (int wd = 0; wd < kMaskWords; ++wd) {
-          const int m_lo = wd * kTilesPerWord;
-          const int m_hi = tiles < m_lo + kTilesPerWord ? tiles : m_lo + kTilesPerWord;
-          unsigned bit = 1u;
-          for (int m = m_lo; m < m_hi; ++m) {
-#pragma unroll
-            for (int q = 0; q < kQ; ++q) {
-              const int i = m * kSlots + q * kSweepThreads + tid;
+            for (int e = 0; e < 2; ++e) {
+              const int i = rr * (2 * kSweepThreads) + 2 * tid + e;
               if (i < N) {
-                const V2 v = sm[i];
-                const double L = loss_of(h0, h1, v.x, v.y);
-                if (L > t_hi) {
-                  ++c_gt;
-                  s_gt += L;
-                } else if (L >= t_lo) {
-                  mask[wd] |= bit << q;
-                }
+                const float2 v = sm[i];
+                const int P = 2 * rr + e;
+                unsigned mk = 0;
+                classify_f32(fmaf(h1f, v.y, h0f * v.x), thr_above, thr_keep, pack2(v.x, v.y), ab64, c32, mk, 1u << (P & 31));
+#pragma unroll
+                for (int w2 = 0; w2 < kMaskWords; ++w2)
+                  if (w2 == (P >> 5)) mask[w2] |= mk;
               }
             }
-            bit <<= kBitsPerTile;
+          }
+        }
+      } else {
+        const int rows_all = tiles * kQ;
+#pragma unroll
+        for (int wd = 0; wd < kMaskWords; ++wd) {
+          const int r_lo = wd * kRowsPerWord;
+          const int r_hi = rows_all < r_lo + kRowsPerWord ? rows_all : r_lo + kRowsPerWord;
+          unsigned bit = 1u;
+          for (int r = r_lo; r < r_hi; ++r, bit <<= 1) {
+            const int i = r * kSweepThreads + tid;
+            if (i < N) {
+              const V2 v = sm[i];
+              const double L = loss_of(h0, h1, v.x, v.y);
+              if (L > t_hi) {
+                ++c_gt;
+                s_gt += L;
+              } else if (L >= t_lo) {
+                mask[wd] |= bit;
+              }
+            }
           }
         }
       }
 
+      PH_MARK(4)
       // -------------------------------------------------------------- phase 2: exact loss of the masked samples
-      // warp-lockstep over each lane's k-th masked sample; window losses -> candidates + histogram
+      // warp-lockstep over each lane's k-th masked sample; window losses -> this warp's candidate list
       int nc = 0;  // candidates of this warp (warp-uniform)
-      const unsigned long long klo = ctl->key_lo;
-      const int hshift = ctl->hist_shift;
+      for (;;) {
+        int P = -1;
 #pragma unroll
-      for (int wd = 0; wd < kMaskWords; ++wd) {
-        unsigned mm = mask[wd];
-        while (__any_sync(kFull, mm != 0)) {
-          const bool active = mm != 0;
-          double L = 0.0;
-          if (active) {
-            const int bp = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const int m = wd * kTilesPerWord + bp / kBitsPerTile;
-            const int within = bp % kBitsPerTile;
-            const int slot = (within / kPerLoad) * kSweepThreads + tid;
-            const int i = m * kTile + slot * kPerLoad + (within % kPerLoad);
-            const V2 v = sm[i];
-            L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
-          }
-          const bool up = active && (L > t_hi);
-          const bool cd = active && !up && (L >= t_lo);
-          if (kF32 && up) {  // inside the fp32 uncertainty band but exactly above the window
-            ++c_gt;
-            s_gt += L;
-          }
-          const unsigned bal = __ballot_sync(kFull, cd);
-          if (bal) {
-            const int pos = nc + __popc(bal & ((1u << lane) - 1u));
-            if (cd && pos < kWarpCand) {
-              wcand[pos] = L;
-              atomicAdd(&hist[static_cast<unsigned>((key_of(L) - klo) >> hshift)], 1u);
-            }
-            nc += __popc(bal);
+        for (int wd = 0; wd < kMaskWords; ++wd) {
+          if (P < 0 && mask[wd] != 0u) {
+            P = 32 * wd + (__ffs(mask[wd]) - 1);
+            mask[wd] &= mask[wd] - 1u;
           }
         }
+        if (!__any_sync(kFull, P >= 0)) break;
+        const bool active = P >= 0;
+        double L = 0.0;
+        V2 v = first;
+        if (active) {
+          const unsigned uP = static_cast<unsigned>(P);
+          const unsigned i = kF32 ? ((uP >> 1) * (2u * kSweepThreads) + 2u * tid + (uP & 1u)) : (uP * kSweepThreads + tid);
+          v = sm[i];
+          L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
+        }
+        const bool up = active && (L > t_hi);
+        const bool cd = active && !up && (L >= t_lo);
+        if constexpr (kF32) {
+          if (up) {  // inside the fp32 uncertainty band but exactly above the window: joins the "above" set
+            ++c32;
+            ab64 = pack2(__fadd_rn(unpack2(ab64).x, v.x), __fadd_rn(unpack2(ab64).y, v.y));
+          }
+        }
+        const unsigned bal = __ballot_sync(kFull, cd);
+        if (bal) {
+          const int pos = nc + __popc(bal & ((1u << lane) - 1u));
+          if (cd && pos < kWarpCand) wcand[pos] = L;
+          nc += __popc(bal);
+        }
       }
+      PH_MARK(5)
       // per-warp partials
       {
         const int wc = __reduce_add_sync(kFull, c_gt + c32);
-        const double ws = warp_sum_any(s_gt);
-        // packed fp32 warp sum of the raw coordinate sums, widened at the end
-        float2 t = unpack2(ab64);
+        double px = 0.0, py = 0.0, pe = 0.0;
+        if constexpr (kF32) {
+          // packed fp32 warp sum of the raw coordinate sums, widened at the end
+          float2 t = unpack2(ab64);
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1)
-          t = __fadd2_rn(t, make_float2(__shfl_xor_sync(kFull, t.x, m), __shfl_xor_sync(kFull, t.y, m)));
+          for (int m = 16; m >= 1; m >>= 1)
+            t = __fadd2_rn(t, make_float2(__shfl_xor_sync(kFull, t.x, m), __shfl_xor_sync(kFull, t.y, m)));
+          px = static_cast<double>(t.x);
+          py = static_cast<double>(t.y);
+        } else {
+          pe = warp_sum_any(s_gt);
+        }
         if (lane == 0) {
           ired[warp * 2] = wc;
           ired[warp * 2 + 1] = nc < kWarpCand ? nc : kWarpCand;
-          fin[warp * 4 + 0] = static_cast<double>(t.x);
-          fin[warp * 4 + 1] = static_cast<double>(t.y);
-          fin[warp * 4 + 2] = ws;
+          fin[warp * 4 + 0] = px;
+          fin[warp * 4 + 1] = py;
+          fin[warp * 4 + 2] = pe;
         }
       }
+      PH_MARK(6)
       const int ovf = team_sync_or(nc > kWarpCand);  // S3: the sample slot is no longer read on the fast path
+      PH_MARK(7)
       int cnt_hi = 0, ncand = 0;
 #pragma unroll
       for (int w = 0; w < kSweepWarps; ++w) {
@@ -1032,6 +1076,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       }
     }
 
+    PH_MARK(8)
     // ------------------------------------------------------------------ release the slot / prefetch / keep the pipeline in step
     if (!next_issued) {
       team_sync();
@@ -1044,6 +1089,10 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       }
     }
   }
+#ifdef DRCVAR_PROFILE_PHASES
+  if (tid == 32 && a.phase_cycles)
+    for (int k = 0; k < 12; ++k) a.phase_cycles[(blockIdx.x * 2 + 0) * 12 + k] = ph_t[k];
+#endif
 }
 
 }  // namespace drcvar

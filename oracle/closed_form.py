@@ -25,13 +25,14 @@ What is restated (reference file:line, relative to /root/reference):
 
 CANONICAL ARITHMETIC (the reference's BLAS matvec / np.mean are not bit-reproducible, so the
 oracle DEFINES the arithmetic the CUDA path must reproduce bit-for-bit where order matters):
-  * sums for the sample mean (per coordinate):
-      fp64 inputs: 512 lanes, lane l accumulates samples i = l (mod 512) in increasing i, in fp64;
-      fp32 inputs: 1024 lanes, lane l accumulates samples i = l (mod 1024) in increasing i IN FP32
-                   (like numpy's own float32 mean), the 1024 lane sums are widened to fp64 and adjacent
-                   lanes (2j, 2j+1) are added, giving 512 values;
-      then each group of 32 consecutive values is combined by an xor-butterfly (1,2,4,8,16) and the 16
-      group totals w0..w15 by an adjacent-pair tree  ((w0+w1)+(w2+w3))+... ; mean = sum / N in fp64.
+  * sample mean (per coordinate), v = the coordinate of the N samples:
+      fp64 inputs: 512 slots, slot l accumulates samples i = l (mod 512) in increasing i, in fp64;
+      fp32 inputs: d_i = fl32(v_i - v_0) (shift by the FIRST sample), 1024 lanes, lane l accumulates
+                   d_i for i = l (mod 1024) in increasing i IN FP32; the 1024 lane sums are widened to
+                   fp64 and adjacent lanes (2j, 2j+1) are added, giving 512 slots;
+      then u[j] = s[j] + s[j+256] (j < 256); each group of 32 consecutive u is combined by an
+      xor-butterfly (1,2,4,8,16); the 8 group totals by an adjacent-pair tree ((w0+w1)+(w2+w3))+((w4+w5)+(w6+w7));
+      mean = S / N in fp64 (fp32 inputs: mean = fl64(v_0) + S / N).
   * projection  p_i = rn(rn(h0*x_i) + rn(h1*y_i))  (no FMA);  loss  L_i = -p_i.
   * tail: k_f = alpha*N (snapped to the nearest integer when within 1e-9 relative),
     kc = ceil(k_f); T = kc-th largest loss; index set = {L_i > T} U lowest-index ties, |set| = kc
@@ -53,18 +54,21 @@ SENTINEL = 100.0  # core/risk_metrics.py:177,265,303,338
 _XOR_IDX = {x: (np.arange(32) ^ x) for x in (1, 2, 4, 8, 16)}
 
 
-def canonical_sum(v) -> float:
-    """Deterministic lane-structured sum (see module docstring); the lane layout depends on v's dtype."""
-    v = np.ascontiguousarray(v).ravel()
-    if v.dtype == np.float32:
-        lanes, acc_t = 2 * LANES, np.float32
-    else:
-        v = v.astype(np.float64, copy=False)
-        lanes, acc_t = LANES, np.float64
+def _tree512(s) -> float:
+    """512 fp64 slots -> one fp64 total: pair (j, j+256), xor-butterfly in groups of 32, adjacent tree of 8."""
+    u = s[:256] + s[256:]
+    w = u.reshape(8, 32)
+    for x in (1, 2, 4, 8, 16):
+        w = w + w[:, _XOR_IDX[x]]
+    w = w[:, 0]
+    while w.shape[0] > 1:
+        w = w[0::2] + w[1::2]
+    return float(w[0])
+
+
+def _lane_sums(v, lanes, acc_t):
     n = v.shape[0]
     rows = (n + lanes - 1) // lanes
-    if rows == 0:
-        return 0.0
     pad = rows * lanes - n
     if pad:
         v = np.concatenate([v, np.zeros(pad, dtype=v.dtype)])
@@ -72,23 +76,35 @@ def canonical_sum(v) -> float:
     s = np.zeros(lanes, dtype=acc_t)
     for r in range(rows):  # sequential per lane, increasing sample index, in the accumulation dtype
         s = s + a[r]
-    s = s.astype(np.float64)
-    if lanes == 2 * LANES:
-        s = s[0::2] + s[1::2]      # adjacent lanes, in fp64
-    w = s.reshape(LANES // 32, 32)
-    for x in (1, 2, 4, 8, 16):
-        w = w + w[:, _XOR_IDX[x]]
-    w = w[:, 0]
-    while w.shape[0] > 1:          # adjacent-pair tree over the 16 group totals
-        w = w[0::2] + w[1::2]
-    return float(w[0])
+    return s
+
+
+def canonical_sum(v) -> float:
+    """Deterministic slot-structured fp64 sum (fp64 contract of the module docstring)."""
+    v = np.ascontiguousarray(v, dtype=np.float64).ravel()
+    if v.shape[0] == 0:
+        return 0.0
+    return _tree512(_lane_sums(v, LANES, np.float64))
+
+
+def canonical_mean_1d(v) -> float:
+    """Canonical mean of one coordinate; the arithmetic depends on the INPUT dtype (see module docstring)."""
+    v = np.ascontiguousarray(v).ravel()
+    n = v.shape[0]
+    if v.dtype == np.float32:
+        d = (v - v[0]).astype(np.float32)                      # fl32(v_i - v_0)
+        s = _lane_sums(d, 2 * LANES, np.float32).astype(np.float64)
+        s = s[0::2] + s[1::2]                                  # adjacent fp32 lanes, added in fp64
+        return float(np.float64(v[0]) + np.float64(_tree512(s)) / np.float64(n))
+    return float(np.float64(canonical_sum(v)) / np.float64(n))
 
 
 def canonical_mean(samples) -> np.ndarray:
     """Mean obstacle position; stands in for np.mean(samples, axis=0) at core/halfspaces.py:85,130,174."""
     s = np.asarray(samples)
-    n = s.shape[0]
-    return np.array([canonical_sum(s[:, 0]) / float(n), canonical_sum(s[:, 1]) / float(n)], dtype=np.float64)
+    if s.dtype != np.float32:
+        s = s.astype(np.float64, copy=False)
+    return np.array([canonical_mean_1d(s[:, 0]), canonical_mean_1d(s[:, 1])], dtype=np.float64)
 
 
 def norm2(v0: float, v1: float) -> float:

@@ -150,6 +150,9 @@ def test_canonical_sum_properties():
     for n in (1, 31, 32, 511, 512, 513, 10000):
         v = rng.normal(size=n)
         assert abs(cf.canonical_sum(v) - float(np.sum(v))) <= 1e-12 * max(1.0, np.abs(v).sum())
+        v32 = (5.0 + 0.1 * v).astype(np.float32)
+        assert abs(cf.canonical_mean_1d(v32) - float(np.mean(v32.astype(np.float64)))) <= 1e-7
+        assert abs(cf.canonical_mean_1d(v) - float(np.mean(v))) <= 1e-13
     # exactly representable data: any order gives the same bits
     v = rng.randint(-1000, 1000, size=5000).astype(np.float64)
     assert cf.canonical_sum(v) == float(v.sum())
