@@ -7,27 +7,31 @@
 //
 // sweep team, per halfspace:
 //   stage   N samples -> shared memory with cp.async.bulk (TMA bulk copy, mbarrier completion) or a strided loader
-//   sweep A canonical lane sums of x,y (fp32 inputs: packed fp32 lane partials, fp64 cross-lane tree;
-//           fp64 inputs: fp64 throughout) + heuristic second moments + max |coordinate|          -> mean m
+//   sweep A canonical lane sums of the coordinates (fp32 inputs: shifted by the first sample, packed fp32 lane
+//           partials, fp64 cross-lane tree; fp64 inputs: fp64 throughout) + second moments              -> mean m
 //   h       = unit(m - ego)                                                            core/geometry.py:35-53
 //   sweep B classify every sample against a statistical window [t_lo, t_hi] around the expected kc-th largest
-//           loss.  fp32 inputs: a rigorous fp32 bound decides "surely above" (count + raw coordinate sums; the
+//           loss.  fp32 inputs: a rigorous fp32 bound decides "surely above" (count + shifted coordinate sums; the
 //           loss sum follows from linearity), "surely below" (ignored) or "needs the exact fp64 loss" (a bit in a
 //           per-thread mask).  fp64 inputs: exact canonical loss for every sample.
-//   phase 2 masked samples get the canonical fp64 loss L_i = -(h.xi_i) (no FMA); window losses go to warp-private
-//           candidate lists and a 256-bucket histogram over the window; the sample slot is released and the
-//           next halfspace's bulk copy is issued
+//   phase 2 masked samples are compacted per warp and get the canonical fp64 loss L_i = -(h.xi_i) (no FMA); window
+//           losses go to warp-private candidate lists and a 256-bucket histogram; the sample slot is released
+//           and the next halfspace's bulk copy is issued
 // finisher warp, per halfspace:
 //   select  exact kc-th largest loss T: histogram scan -> bucket -> all-pairs rank inside the bucket
-//   finish  CVaR = (sum_{L>T} L + (k_f - #{L>T}) T) / k_f  and the three offsets        core/risk_metrics.py:84-338
+//   finish  CVaR = (sum_{L>T} L + (k_f - #{L>T}) T) / k_f  and the CVaR / DR-CVaR offsets  core/risk_metrics.py:84-338
 // The window and the fp32 bound only decide HOW FAST the exact threshold is found; a miss is detected and the
 // general multi-sweep radix select (sweep team, all samples) runs instead.  Arithmetic contract: DESIGN.md.
+//
+// Pipe budget notes (measured on B200, profiles/ubench): FFMA/FADD/FMUL/IADD issue at 4 warp-inst/clk/SM; FSETP, SEL,
+// LOP3, SHF, FMNMX, FADD2, IMAD, DADD/DMUL at 2; SHFL ~1; POPC/FLO/REDUX/F2F ~0.5; LDS.128 moves 128 B/clk/SM.  The hot
+// loops are written to keep the half-rate "ALU" ops to the two FSETPs per sample.
 #pragma once
 
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-// Optional phase timing (profiling builds only: -DDRCVAR_PROFILE_PHASES; see profiles/README.md)
+// Optional phase timing (profiling builds only: -DDRCVAR_PROFILE_PHASES; see profiles/phase_cycles.py)
 #ifdef DRCVAR_PROFILE_PHASES
 #define PH_DECL long long ph_t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long ph_last = clock64();
 #define PH_MARK(k) { const long long ph_now = clock64(); ph_t[k] += ph_now - ph_last; ph_last = ph_now; }
@@ -41,10 +45,9 @@ namespace drcvar {
 constexpr int kSweepWarps = 8;
 constexpr int kSweepThreads = kSweepWarps * 32;      // 256
 constexpr int kThreads = kSweepThreads + 32;         // + finisher warp
-constexpr int kSlots = 512;                          // canonical cross-lane tree width
-constexpr int kQ = kSlots / kSweepThreads;           // tree slots per sweep thread (2)
-constexpr int kGroups = kSlots / 32;                 // 16 butterfly groups
+constexpr int kSlots = 512;                          // canonical cross-lane tree width (2 slots per sweep thread)
 constexpr int kWarpCand = 128;                       // candidate losses per sweep warp (window path)
+constexpr int kWarpList = 192;                       // masked sample indices per sweep warp
 constexpr int kHistBuckets = 256;
 constexpr int kResolveMax = 32;                      // a bucket this small is ranked by one warp
 constexpr int kMaskWords = 4;                        // per-thread "needs exact loss" mask: 128 bits
@@ -78,13 +81,14 @@ struct KernelArgs {
   double* gstar_out;
   int* status_out;
   int* tail_idx_out;
-  long long* phase_cycles;   // profiling builds: [grid][2][12] accumulated cycles (sweep warp 1, finisher)
+  long long* phase_cycles;   // profiling builds: [grid][2][12] accumulated cycles (sweep warp 2, finisher)
 };
 
 struct Ctl {                        // one per parity buffer
   unsigned long long key_lo;       // key(t_lo): histogram origin
   double T;
   double h0, h1, t_lo, t_hi, m0, m1;
+  double f0, f1;                   // first sample (fp32 path: shift origin)
   float h0f, h1f, thr_above, thr_keep;
   int hist_shift;
   int bstar, rprime, cnt_in, small_n;
@@ -106,8 +110,8 @@ template <> struct Vec2<double> { using type = double2; };
 __host__ __device__ inline size_t slot_bytes_for(long long n, size_t elem_bytes) {
   return (static_cast<size_t>(n) * 2 * elem_bytes + 127) & ~static_cast<size_t>(127);
 }
-constexpr int kRedDoubles = kGroups * 2 + 2 * 8 + kSweepWarps;   // group totals, moments of 2 warps, amax per warp
-constexpr int kFinDoubles = kSweepWarps * 4;                     // per parity: {sum x, sum y, exact sum, -}
+constexpr int kRedDoubles = kSweepWarps * 8;                     // per warp: {tx, ty, qxx, qyy, qxy, bound, mdx, mdy}
+constexpr int kFinDoubles = kSweepWarps * 4;                     // per parity, per warp: {sum dx, sum dy, exact sum, n}
 __host__ __device__ inline size_t fixed_smem_bytes() {
   return sizeof(double) * 2 * kWarpCand * kSweepWarps   // cand   [2][warps][kWarpCand]
          + sizeof(unsigned) * 2 * kHistBuckets          // hist   [2][256]
@@ -116,6 +120,7 @@ __host__ __device__ inline size_t fixed_smem_bytes() {
          + sizeof(double) * 2 * kResolveMax             // small  [2]
          + sizeof(int) * 2 * 2 * kSweepWarps            // ired   [2][warps][2]
          + sizeof(int) * 4 * kSweepWarps                // iscr   (team scratch)
+         + sizeof(unsigned short) * kWarpList * kSweepWarps  // list
          + 2 * sizeof(Ctl) + sizeof(Bars);
 }
 
@@ -139,7 +144,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
@@ -171,28 +176,20 @@ __device__ __forceinline__ int team_sync_or(int pred) {
       : "memory");
   return r;
 }
-// fp32 classification of one sample (p = h.xi in fp32):  up = p < thr_above;  keep = !up && p <= thr_keep.
-// up: packed add of (x, y) into acc and count; keep: set `bit` in mask.  5 instructions.
-__device__ __forceinline__ unsigned long long pack2(float x, float y) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
-  return r;
-}
-__device__ __forceinline__ float2 unpack2(unsigned long long v) {
-  float2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-  return r;
-}
-__device__ __forceinline__ void classify_f32(float p, float thr_above, float thr_keep, unsigned long long xy,
-                                             unsigned long long& acc, int& cnt, unsigned& mask, unsigned bit) {
+// fp32 classification of one sample (p = h.(xi - first) in fp32):  up = p < thr_above;  keep = !up && p <= thr_keep.
+//   up:   accumulate the shifted coordinates and a float count (full-rate FADDs, fma pipe)
+//   keep: add `bit` into the mask (bits are distinct, so add == or; full-rate IADD)
+__device__ __forceinline__ void classify_f32(float p, float thr_above, float thr_keep, float dx, float dy, float& ax,
+                                             float& ay, float& cnt, unsigned& mask, unsigned bit) {
   asm("{\n\t.reg .pred u, k;\n\t"
-      "setp.lt.f32 u, %3, %4;\n\t"
-      "setp.le.and.f32 k, %3, %5, !u;\n\t"
-      "@u add.rn.f32x2 %0, %0, %6;\n\t"
-      "@u add.s32 %1, %1, 1;\n\t"
-      "@k or.b32 %2, %2, %7;\n\t}"
-      : "+l"(acc), "+r"(cnt), "+r"(mask)
-      : "f"(p), "f"(thr_above), "f"(thr_keep), "l"(xy), "r"(bit));
+      "setp.lt.f32 u, %4, %5;\n\t"
+      "setp.le.and.f32 k, %4, %6, !u;\n\t"
+      "@u add.f32 %0, %0, %7;\n\t"
+      "@u add.f32 %1, %1, %8;\n\t"
+      "@u add.f32 %2, %2, 0f3F800000;\n\t"
+      "@k add.u32 %3, %3, %9;\n\t}"
+      : "+f"(ax), "+f"(ay), "+f"(cnt), "+r"(mask)
+      : "f"(p), "f"(thr_above), "f"(thr_keep), "f"(dx), "f"(dy), "r"(bit));
 }
 
 // ---------------------------------------------------------------------------------------------- small helpers
@@ -227,7 +224,6 @@ __device__ __forceinline__ double warp_sum_canon(double v) {  // xor 1,2,4,8,16 
   for (int m = 1; m <= 16; m <<= 1) v = __dadd_rn(v, shfl_xor_d(v, m));
   return v;
 }
-__device__ __forceinline__ float absmax3(float m, float a, float b) { return fmaxf(m, fmaxf(fabsf(a), fabsf(b))); }
 
 // Histogram scan by ONE warp: finds the bucket (from the top) that holds rank r (1-based).
 __device__ __forceinline__ void scan_hist_warp(const unsigned* hist, int r, int lane, int& bstar, int& rprime, int& cnt_in) {
@@ -320,10 +316,30 @@ __device__ double select_rank(ForEach&& for_each, Sync&& SYNC, bool leader, int 
   }
 }
 
-// Offsets of one halfspace from (h, mean, CVaR ingredients); one thread.            core/risk_metrics.py, core/halfspaces.py
-__device__ __forceinline__ void write_outputs(const KernelArgs& a, long long b, const Ctl* ctl, bool nonfinite, double s_tot,
-                                              int c_tot, double T_thr, int status) {
-  const double h0 = ctl->h0, h1 = ctl->h1, m0 = ctl->m0, m1 = ctl->m1;
+// Mean halfspace of one (scenario, obstacle, step): direction from the ORIGIN, core/halfspaces.py:70-106.  One thread.
+__device__ __forceinline__ void write_mean_outputs(const KernelArgs& a, long long b, double m0, double m1) {
+  double hm0, hm1;
+  const double mn = norm2_canon(m0, m1);
+  if (mn < 1e-10) {
+    hm0 = 1.0;
+    hm1 = 0.0;
+  } else {
+    hm0 = __ddiv_rn(m0, mn);
+    hm1 = __ddiv_rn(m1, mn);
+  }
+  const double hmn = norm2_canon(hm0, hm1);
+  const double g_mean = -__dsub_rn(__dadd_rn(__dmul_rn(hm0, m0), __dmul_rn(hm1, m1)), __dmul_rn(a.R, hmn));
+  if (a.h_mean_out) {
+    a.h_mean_out[2 * b] = hm0;
+    a.h_mean_out[2 * b + 1] = hm1;
+  }
+  a.g_out[3 * b] = g_mean;
+}
+
+// CVaR / DR-CVaR offsets of one halfspace from (h, CVaR ingredients); one thread.      core/risk_metrics.py:84-338
+__device__ __forceinline__ void write_risk_outputs(const KernelArgs& a, long long b, const Ctl* ctl, bool nonfinite,
+                                                   double s_tot, int c_tot, double T_thr, int status) {
+  const double h0 = ctl->h0, h1 = ctl->h1;
   const double hn = norm2_canon(h0, h1);
   const double r = __dmul_rn(a.R, hn);
   double cvar, g_cvar, g_star, g_dr, var_t;
@@ -342,25 +358,8 @@ __device__ __forceinline__ void write_outputs(const KernelArgs& a, long long b, 
     g_star = __dsub_rn(__dadd_rn(cr, a.eoa), a.delta);
     g_dr = __dsub_rn(g_star, r);
   }
-  // mean halfspace: direction from the ORIGIN (core/halfspaces.py:88)
-  double hm0, hm1;
-  const double mn = norm2_canon(m0, m1);
-  if (mn < 1e-10) {
-    hm0 = 1.0;
-    hm1 = 0.0;
-  } else {
-    hm0 = __ddiv_rn(m0, mn);
-    hm1 = __ddiv_rn(m1, mn);
-  }
-  const double hmn = norm2_canon(hm0, hm1);
-  const double g_mean = -__dsub_rn(__dadd_rn(__dmul_rn(hm0, m0), __dmul_rn(hm1, m1)), __dmul_rn(a.R, hmn));
   a.h_out[2 * b] = h0;
   a.h_out[2 * b + 1] = h1;
-  if (a.h_mean_out) {
-    a.h_mean_out[2 * b] = hm0;
-    a.h_mean_out[2 * b + 1] = hm1;
-  }
-  a.g_out[3 * b] = g_mean;
   a.g_out[3 * b + 1] = g_cvar;
   a.g_out[3 * b + 2] = g_dr;
   if (a.cvar_out) a.cvar_out[b] = cvar;
@@ -375,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   using V2 = typename Vec2<T>::type;
   constexpr bool kF32 = sizeof(T) == 4;
   constexpr int kPerLoad = kF32 ? 2 : 1;          // samples per 16-byte shared load
-  constexpr int kTile = kSlots * kPerLoad;        // samples per canonical tile (1024 fp32 / 512 fp64)
+  constexpr int kRowSamples = kSweepThreads * kPerLoad;   // samples per row of 16-byte loads (512 / 256)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
@@ -388,7 +387,8 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   double* small_base = fin_base + 2 * kFinDoubles;
   int* ired_base = reinterpret_cast<int*>(small_base + 2 * kResolveMax);
   int* iscr = ired_base + 2 * 2 * kSweepWarps;
-  Ctl* ctl_base = reinterpret_cast<Ctl*>(iscr + 4 * kSweepWarps);
+  unsigned short* list_base = reinterpret_cast<unsigned short*>(iscr + 4 * kSweepWarps);
+  Ctl* ctl_base = reinterpret_cast<Ctl*>(list_base + kWarpList * kSweepWarps);
   Bars* bars = reinterpret_cast<Bars*>(ctl_base + 2);
 
   if (tid == 0) {
@@ -421,14 +421,6 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         const int cnt_hi = ctl->cnt_hi;
         const unsigned long long klo = ctl->key_lo;
         const int hshift = ctl->hist_shift;
-        // histogram of the window candidates (256 monotone buckets between key(t_lo) and key(t_hi))
-        for (int w = 0; w < kSweepWarps; ++w) {
-          const int nc = ired[w * 2 + 1];
-          const double* wc = cand + w * kWarpCand;
-          for (int j = lane; j < nc; j += 32)
-            atomicAdd(&hist[static_cast<unsigned>((key_of(wc[j]) - klo) >> hshift)], 1u);
-        }
-        __syncwarp();
         int bstar, r, cnt_in;
         scan_hist_warp(hist, a.kc - cnt_hi, lane, bstar, r, cnt_in);
         // pass over all candidates: above bucket b* -> counted/summed; bucket b* -> gathered for exact ranking
@@ -491,7 +483,6 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
             }
           };
           T_thr = select_rank(each, [] { __syncwarp(); }, true, lane, 32, lo2, hi2, r, hist, small, ctl);
-          // members of bucket b* above T
           each([&](double L) {
             const int bk = static_cast<int>((key_of(L) - klo) >> hshift);
             if (bk == bstar && L > T_thr) {
@@ -505,18 +496,20 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         const int c3t = __reduce_add_sync(kFull, c3);
         const double s3t = warp_sum_any(s3);
         if (lane == 0) {
-          double s_x = 0.0, s_y = 0.0, s_e = 0.0;
+          double s_x = 0.0, s_y = 0.0, s_e = 0.0, n_lin = 0.0;
 #pragma unroll
           for (int w = 0; w < kSweepWarps; ++w) {
             s_x += fin[w * 4 + 0];
             s_y += fin[w * 4 + 1];
             s_e += fin[w * 4 + 2];
+            n_lin += fin[w * 4 + 3];
           }
-          // loss sum of the "surely above" set by linearity: sum_i -(h.xi_i) = -(h0 sum x + h1 sum y)
-          const double s_lin = -(ctl->h0 * s_x + ctl->h1 * s_y);
+          // loss sum of the "surely above" set by linearity (fp32 inputs), xi_i = f + d_i:
+          //   sum_i -(h.xi_i) = -(h0 (n f0 + sum dx) + h1 (n f1 + sum dy))
+          const double s_lin = -(ctl->h0 * (n_lin * ctl->f0 + s_x) + ctl->h1 * (n_lin * ctl->f1 + s_y));
           const double s_tot = ((s_e + s_lin) + s3t) + s4;
           const int c_tot = cnt_hi + c3t + c4;
-          write_outputs(a, b, ctl, false, s_tot, c_tot, T_thr, ctl->status);
+          write_risk_outputs(a, b, ctl, false, s_tot, c_tot, T_thr, ctl->status);
           if (kTail) {
             ctl->T = T_thr;
             ctl->c_tot = c_tot;
@@ -551,8 +544,9 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   if (a.bulk && tid == 0 && static_cast<long long>(blockIdx.x) < a.B) issue_bulk(blockIdx.x);
   uint32_t phase = 0;
   int iter = 0;
-  const int tiles = (N + kTile - 1) / kTile;
-  const int full_tiles = N / kTile;
+  const int full_rows = N / kRowSamples;                 // rows of 16-byte loads fully inside the data
+  const int rows_all = (N + kRowSamples - 1) / kRowSamples;
+  unsigned short* wlist = list_base + warp * kWarpList;
   PH_DECL
 
   for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
@@ -585,204 +579,220 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     if (use > 0) mbar_wait(&bars->empty[par], (use - 1) & 1);
     PH_MARK(0)
 
-    // ------------------------------------------------------------------ sweep A: canonical lane sums (+ heuristics)
-    double sx[kQ], sy[kQ];                          // this thread's kQ slots of the 512-wide fp64 tree (slot = tid + 256 q)
-    T qdx = 0, qdy = 0, qxx = 0, qxy = 0, qyy = 0;  // second moments (warps 0-1 only), shifted by the first sample
-    float amax = 0.f;                               // max |coordinate| (bounds the fp32 classification error)
+    // ------------------------------------------------------------------ sweep A: canonical lane sums + second moments
+    // Row r = the 16-byte vector r*256 + tid.  fp32: samples 2(r*256+tid)+{0,1} = lanes 2 slot + {0,1} of tile r/2,
+    // slot = (r&1)*256 + tid.  fp64: sample r*256 + tid = slot (r&1)*256 + tid of tile r/2.
     const V2 first = sm[0];
-    const bool mom_warp = warp < 2;
+    double u_x, u_y;                 // this thread's value in the 256-wide tree: slot tid + slot tid+256
+    double q_xx, q_yy, q_xy;         // second moments of (xi - first): all samples (fp32) / every 4th row (fp64)
+    double q_dx = 0.0, q_dy = 0.0;   // fp64 inputs only: first moments of the same subset
+    float bound2 = 0.f;              // fp32 inputs: per-thread sum of |xi - first|^2 >= max |xi - first|^2
     if constexpr (kF32) {
       const float4* sm4 = reinterpret_cast<const float4*>(smem_raw);
-      float2 acc[kQ][2];
+      const float2 nf = make_float2(-first.x, -first.y);
+      float2 acc[2][2];
 #pragma unroll
-      for (int q = 0; q < kQ; ++q) acc[q][0] = acc[q][1] = make_float2(0.f, 0.f);
-      auto moments = [&](const float4 v) {
-        const float dx0 = v.x - first.x, dy0 = v.y - first.y, dx1 = v.z - first.x, dy1 = v.w - first.y;
-        qdx += dx0 + dx1;
-        qdy += dy0 + dy1;
-        qxx = fmaf(dx0, dx0, fmaf(dx1, dx1, qxx));
-        qxy = fmaf(dx0, dy0, fmaf(dx1, dy1, qxy));
-        qyy = fmaf(dy0, dy0, fmaf(dy1, dy1, qyy));
-      };
+      for (int q = 0; q < 2; ++q) acc[q][0] = acc[q][1] = make_float2(0.f, 0.f);
+      float2 sq = make_float2(0.f, 0.f);
+      float sxy = 0.f;
       auto body = [&](const float4 v, int q) {
-        acc[q][0] = __fadd2_rn(acc[q][0], make_float2(v.x, v.y));
-        acc[q][1] = __fadd2_rn(acc[q][1], make_float2(v.z, v.w));
-        amax = absmax3(absmax3(amax, v.x, v.y), v.z, v.w);
+        const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nf), d1 = __fadd2_rn(make_float2(v.z, v.w), nf);
+        acc[q][0] = __fadd2_rn(acc[q][0], d0);
+        acc[q][1] = __fadd2_rn(acc[q][1], d1);
+        sq = __ffma2_rn(d0, d0, sq);
+        sq = __ffma2_rn(d1, d1, sq);
+        sxy = fmaf(d0.x, d0.y, sxy);
+        sxy = fmaf(d1.x, d1.y, sxy);
       };
-      if (mom_warp) {
-        for (int m = 0; m < full_tiles; ++m) {
-#pragma unroll
-          for (int q = 0; q < kQ; ++q) {
-            const float4 v = sm4[m * kSlots + q * kSweepThreads + tid];   // samples 1024 m + 2 slot, +1
-            body(v, q);
-            moments(v);
-          }
-        }
-      } else {
-#pragma unroll 4
-        for (int m = 0; m < full_tiles; ++m) {
-#pragma unroll
-          for (int q = 0; q < kQ; ++q) body(sm4[m * kSlots + q * kSweepThreads + tid], q);
-        }
-      }
-      if (full_tiles < tiles) {  // ragged last tile: element-wise
-#pragma unroll
-        for (int q = 0; q < kQ; ++q) {
-          const int i0 = full_tiles * kTile + 2 * (q * kSweepThreads + tid);
-          if (i0 < N) {
-            const float2 v = sm[i0];
-            acc[q][0] = __fadd2_rn(acc[q][0], v);
-            amax = absmax3(amax, v.x, v.y);
-          }
-          if (i0 + 1 < N) {
-            const float2 v = sm[i0 + 1];
-            acc[q][1] = __fadd2_rn(acc[q][1], v);
-            amax = absmax3(amax, v.x, v.y);
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < kQ; ++q) {  // adjacent fp32 lanes (2 slot, 2 slot + 1), widened, added in fp64
-        sx[q] = __dadd_rn(static_cast<double>(acc[q][0].x), static_cast<double>(acc[q][1].x));
-        sy[q] = __dadd_rn(static_cast<double>(acc[q][0].y), static_cast<double>(acc[q][1].y));
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < kQ; ++q) sx[q] = sy[q] = 0.0;
-      auto moments = [&](const V2 v) {
-        const T dx = v.x - first.x, dy = v.y - first.y;
-        qdx += dx;
-        qdy += dy;
-        qxx = fma(dx, dx, qxx);
-        qxy = fma(dx, dy, qxy);
-        qyy = fma(dy, dy, qyy);
-      };
+      int r = 0;
 #pragma unroll 2
-      for (int m = 0; m < full_tiles; ++m) {
-#pragma unroll
-        for (int q = 0; q < kQ; ++q) {
-          const V2 v = sm[m * kSlots + q * kSweepThreads + tid];
-          sx[q] = __dadd_rn(sx[q], v.x);
-          sy[q] = __dadd_rn(sy[q], v.y);
-          if (mom_warp) moments(v);
-        }
+      for (; r + 1 < full_rows; r += 2) {
+        const float4 va = sm4[r * kSweepThreads + tid], vb = sm4[(r + 1) * kSweepThreads + tid];
+        body(va, 0);
+        body(vb, 1);
       }
-      if (full_tiles < tiles) {
+      // remaining rows (at most 3: an odd full row and the ragged rows), element-wise with bounds checks
+      for (; r < rows_all; ++r) {
+        const int q = r & 1;
 #pragma unroll
-        for (int q = 0; q < kQ; ++q) {
-          const int i = full_tiles * kTile + q * kSweepThreads + tid;
+        for (int e = 0; e < 2; ++e) {
+          const int i = r * kRowSamples + 2 * tid + e;
           if (i < N) {
-            const V2 v = sm[i];
-            sx[q] = __dadd_rn(sx[q], v.x);
-            sy[q] = __dadd_rn(sy[q], v.y);
+            const float2 v = sm[i];
+            const float2 d = __fadd2_rn(v, nf);
+            if (q == 0) acc[0][e] = __fadd2_rn(acc[0][e], d); else acc[1][e] = __fadd2_rn(acc[1][e], d);
+            sq = __ffma2_rn(d, d, sq);
+            sxy = fmaf(d.x, d.y, sxy);
           }
         }
       }
+      // adjacent fp32 lanes (2 slot, 2 slot + 1) widened and added in fp64, then slot tid + slot tid+256
+      const double s0x = __dadd_rn(static_cast<double>(acc[0][0].x), static_cast<double>(acc[0][1].x));
+      const double s0y = __dadd_rn(static_cast<double>(acc[0][0].y), static_cast<double>(acc[0][1].y));
+      const double s1x = __dadd_rn(static_cast<double>(acc[1][0].x), static_cast<double>(acc[1][1].x));
+      const double s1y = __dadd_rn(static_cast<double>(acc[1][0].y), static_cast<double>(acc[1][1].y));
+      u_x = __dadd_rn(s0x, s1x);
+      u_y = __dadd_rn(s0y, s1y);
+      q_xx = sq.x;
+      q_yy = sq.y;
+      q_xy = sxy;
+      bound2 = sq.x + sq.y;
+    } else {
+      double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+      q_xx = q_yy = q_xy = 0.0;
+      for (int r = 0; r < rows_all; ++r) {
+        const int i = r * kRowSamples + tid;
+        if (i < N) {
+          const V2 v = sm[i];
+          if ((r & 1) == 0) {
+            s00 = __dadd_rn(s00, v.x);
+            s01 = __dadd_rn(s01, v.y);
+          } else {
+            s10 = __dadd_rn(s10, v.x);
+            s11 = __dadd_rn(s11, v.y);
+          }
+          if ((r & 3) == 0) {
+            const double dx = v.x - first.x, dy = v.y - first.y;
+            q_dx += dx;
+            q_dy += dy;
+            q_xx = fma(dx, dx, q_xx);
+            q_yy = fma(dy, dy, q_yy);
+            q_xy = fma(dx, dy, q_xy);
+          }
+        }
+      }
+      u_x = __dadd_rn(s00, s10);
+      u_y = __dadd_rn(s01, s11);
     }
     {
-      // canonical: xor-butterfly inside each group of 32 slots; the 16 group totals are tree-added by warp 0
-#pragma unroll
-      for (int q = 0; q < kQ; ++q) {
-        const double tx = warp_sum_canon(sx[q]);
-        const double ty = warp_sum_canon(sy[q]);
-        if (lane == 0) {
-          const int g = q * kSweepWarps + warp;   // slots [32 g, 32 g + 32)
-          red[2 * g] = tx;
-          red[2 * g + 1] = ty;
-        }
+      // canonical: xor-butterfly inside each group of 32; the 8 group totals are tree-added by warps 0 and 1
+      const double tx = warp_sum_canon(u_x);
+      const double ty = warp_sum_canon(u_y);
+      const float mxx = warp_sum_any(static_cast<float>(q_xx)), myy = warp_sum_any(static_cast<float>(q_yy));
+      const float mxy = warp_sum_any(static_cast<float>(q_xy));
+      const unsigned bnd = __reduce_max_sync(kFull, __float_as_uint(bound2));
+      float mdx = 0.f, mdy = 0.f;
+      if constexpr (!kF32) {
+        mdx = warp_sum_any(static_cast<float>(q_dx));
+        mdy = warp_sum_any(static_cast<float>(q_dy));
       }
-      const unsigned mxb = __reduce_max_sync(kFull, __float_as_uint(amax));
-      if (mom_warp) {
-        const float mdx = warp_sum_any(static_cast<float>(qdx)), mdy = warp_sum_any(static_cast<float>(qdy));
-        const float mxx = warp_sum_any(static_cast<float>(qxx)), mxy = warp_sum_any(static_cast<float>(qxy));
-        const float myy = warp_sum_any(static_cast<float>(qyy));
-        if (lane == 0) {
-          double* w = red + 2 * kGroups + warp * 8;
-          w[0] = mdx; w[1] = mdy; w[2] = mxx; w[3] = mxy; w[4] = myy;
-        }
+      if (lane == 0) {
+        double* w = red + warp * 8;
+        w[0] = tx; w[1] = ty; w[2] = mxx; w[3] = myy; w[4] = mxy;
+        w[5] = static_cast<double>(__uint_as_float(bnd));
+        w[6] = mdx; w[7] = mdy;
       }
-      if (lane == 0) red[2 * kGroups + 16 + warp] = static_cast<double>(__uint_as_float(mxb));
     }
     PH_MARK(1)
     team_sync();  // S1
     PH_MARK(2)
 
-    // ------------------------------------------------------------------ direction + window (warp 0)
-    if (warp == 0) {
+    // ------------------------------------------------------------------ direction + window (warp 0); mean halfspace (warp 1)
+    if (warp < 2) {
       double w[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        double t[kGroups];
+        double t[kSweepWarps];
 #pragma unroll
-        for (int g = 0; g < kGroups; ++g) t[g] = red[2 * g + j];
+        for (int g = 0; g < kSweepWarps; ++g) t[g] = red[g * 8 + j];
 #pragma unroll
-        for (int n = kGroups; n > 1; n >>= 1)
+        for (int n = kSweepWarps; n > 1; n >>= 1)
 #pragma unroll
           for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);  // adjacent-pair tree
         w[j] = t[0];
       }
-      double q[5];
-#pragma unroll
-      for (int j = 0; j < 5; ++j) q[j] = red[2 * kGroups + j] + red[2 * kGroups + 8 + j];
-      float mx = 0.f;
-#pragma unroll
-      for (int ww = 0; ww < kSweepWarps; ++ww) mx = fmaxf(mx, static_cast<float>(red[2 * kGroups + 16 + ww]));
-      const double m0 = __ddiv_rn(w[0], static_cast<double>(N));
-      const double m1 = __ddiv_rn(w[1], static_cast<double>(N));
-      int nonfinite = !(isfinite(m0) && isfinite(m1));
-      int degenerate = 0;
-      double h0, h1;
-      if (a.h_in != nullptr) {
-        h0 = a.h_in[2 * b];
-        h1 = a.h_in[2 * b + 1];
-      } else {
-        const double e0 = a.ego ? a.ego[2 * b] : 0.0, e1 = a.ego ? a.ego[2 * b + 1] : 0.0;
-        const double d0 = __dsub_rn(m0, e0), d1 = __dsub_rn(m1, e1);
-        const double nrm = norm2_canon(d0, d1);
-        if (nrm < 1e-10) {
-          h0 = 1.0;
-          h1 = 0.0;
-          degenerate = 1;
-        } else {
-          h0 = __ddiv_rn(d0, nrm);
-          h1 = __ddiv_rn(d1, nrm);
-        }
+      double m0 = __ddiv_rn(w[0], static_cast<double>(N));
+      double m1 = __ddiv_rn(w[1], static_cast<double>(N));
+      if constexpr (kF32) {  // fp32 inputs: the lane sums were taken relative to the first sample
+        m0 = __dadd_rn(static_cast<double>(first.x), m0);
+        m1 = __dadd_rn(static_cast<double>(first.y), m1);
       }
-      nonfinite |= !(isfinite(h0) && isfinite(h1));
-      // heuristic window around the expected kc-th largest loss (affects speed only, never the result).
-      // moments came from warps 0-1: slots {tid, tid + 256} for tid < 64, full tiles only.
-      const int n_sub_i = full_tiles * 64 * kQ * kPerLoad;
-      const double n_sub = static_cast<double>(n_sub_i > 0 ? n_sub_i : 1);
-      const double ex = q[0] / n_sub, ey = q[1] / n_sub;
-      const double cxx = q[2] / n_sub - ex * ex, cxy = q[3] / n_sub - ex * ey, cyy = q[4] / n_sub - ey * ey;
-      const double var_l = h0 * h0 * cxx + 2.0 * h0 * h1 * cxy + h1 * h1 * cyy;
-      const double mu_l = -(h0 * m0 + h1 * m1);
-      const double sigma = static_cast<double>(sqrtf(static_cast<float>(var_l)));
-      int window_ok = a.use_window && (n_sub_i >= 256) && (var_l > 0.0) && isfinite(sigma) && !nonfinite &&
-                      (tiles * kQ * kPerLoad <= 32 * kMaskWords);
-      const double t_lo = __dadd_rn(mu_l + a.z_lo * sigma, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
-      const double t_hi = __dadd_rn(mu_l + a.z_hi * sigma, 0.0);
-      // fp32 classification of p32 = fma(h1f, y, h0f*x)  (p = h.xi = -L):
-      //   |p32 - p| <= 4 * 2^-24 * (|h0| + |h1|) * max|coord|; we allow 2^-19 (32x) plus the rounding of the thresholds.
-      //   p32 <  thr_above  =>  L > t_hi  for sure;    p32 > thr_keep  =>  L < t_lo  for sure.
-      const float h0f = static_cast<float>(h0), h1f = static_cast<float>(h1);
-      const float bound = (fabsf(h0f) + fabsf(h1f)) * mx * 1.9073486e-06f + 1.1754944e-38f;
-      const float thr_keep = static_cast<float>(-t_lo) + (bound + fabsf(static_cast<float>(t_lo)) * 2.3841858e-07f);
-      const float thr_above = static_cast<float>(-t_hi) - (bound + fabsf(static_cast<float>(t_hi)) * 2.3841858e-07f);
-      const unsigned long long klo = key_of(t_lo), khi = key_of(t_hi);
-      const unsigned long long span = khi - klo;
-      const int bits = span ? 64 - __clzll(static_cast<long long>(span)) : 0;
-      window_ok = window_ok && isfinite(thr_keep) && isfinite(thr_above) && (khi >= klo) && (thr_above <= thr_keep);
-      if (lane == 0) {
-        ctl->h0 = h0; ctl->h1 = h1; ctl->m0 = m0; ctl->m1 = m1;
-        ctl->t_lo = t_lo;
-        ctl->t_hi = t_hi;
-        ctl->h0f = h0f; ctl->h1f = h1f; ctl->thr_keep = thr_keep; ctl->thr_above = thr_above;
-        ctl->key_lo = klo;
-        ctl->hist_shift = bits > 8 ? bits - 8 : 0;
-        ctl->window_ok = window_ok;
-        ctl->nonfinite = nonfinite;
-        ctl->degenerate = degenerate;
+      if (warp == 1) {
+        if (lane == 0) write_mean_outputs(a, b, m0, m1);
+      } else {
+        double q[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          q[j] = 0.0;
+#pragma unroll
+          for (int g = 0; g < kSweepWarps; ++g) q[j] += red[g * 8 + (j < 3 ? 2 + j : 3 + j)];  // qxx,qyy,qxy,mdx,mdy
+        }
+        float b2 = 0.f;
+#pragma unroll
+        for (int g = 0; g < kSweepWarps; ++g) b2 = fmaxf(b2, static_cast<float>(red[g * 8 + 5]));
+        int nonfinite = !(isfinite(m0) && isfinite(m1));
+        int degenerate = 0;
+        double h0, h1;
+        if (a.h_in != nullptr) {
+          h0 = a.h_in[2 * b];
+          h1 = a.h_in[2 * b + 1];
+        } else {
+          const double e0 = a.ego ? a.ego[2 * b] : 0.0, e1 = a.ego ? a.ego[2 * b + 1] : 0.0;
+          const double d0 = __dsub_rn(m0, e0), d1 = __dsub_rn(m1, e1);
+          const double nrm = norm2_canon(d0, d1);
+          if (nrm < 1e-10) {
+            h0 = 1.0;
+            h1 = 0.0;
+            degenerate = 1;
+          } else {
+            h0 = __ddiv_rn(d0, nrm);
+            h1 = __ddiv_rn(d1, nrm);
+          }
+        }
+        nonfinite |= !(isfinite(h0) && isfinite(h1));
+        // heuristic window around the expected kc-th largest loss (affects speed only, never the result)
+        const double f0 = static_cast<double>(first.x), f1 = static_cast<double>(first.y);
+        int n_sub_i;
+        double ex, ey;
+        if (kF32) {
+          n_sub_i = N;
+          ex = m0 - f0;
+          ey = m1 - f1;
+        } else {
+          const int r4 = (rows_all + 3) / 4;                       // rows 0, 4, 8, ...
+          const int last = (r4 - 1) * 4 * kRowSamples;             // first sample of the last such row
+          n_sub_i = (r4 - 1) * kSweepThreads + (N - last < kSweepThreads ? N - last : kSweepThreads);
+          ex = q[3] / n_sub_i;
+          ey = q[4] / n_sub_i;
+        }
+        const double n_sub = static_cast<double>(n_sub_i > 0 ? n_sub_i : 1);
+        const double cxx = q[0] / n_sub - ex * ex, cyy = q[1] / n_sub - ey * ey, cxy = q[2] / n_sub - ex * ey;
+        const double var_l = h0 * h0 * cxx + 2.0 * h0 * h1 * cxy + h1 * h1 * cyy;
+        const double mu_l = -(h0 * m0 + h1 * m1);
+        const double sigma = static_cast<double>(sqrtf(static_cast<float>(var_l)));
+        int window_ok = a.use_window && (n_sub_i >= 256) && (var_l > 0.0) && isfinite(sigma) && !nonfinite &&
+                        (rows_all * kPerLoad <= 32 * kMaskWords);
+        const double t_lo = __dadd_rn(mu_l + a.z_lo * sigma, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
+        const double t_hi = __dadd_rn(mu_l + a.z_hi * sigma, 0.0);
+        // fp32 classification of p32 = fma(h1f, dy, h0f*dx), d = fl32(xi - first)  (p = h.xi = h.first + h.d = -L):
+        //   |p32 - h.d| <= 5 * 2^-24 * (|h0| + |h1|) * max|d|; we allow 2^-19 (32x) plus the rounding of the thresholds.
+        //   p32 <  thr_above  =>  L > t_hi  for sure;    p32 > thr_keep  =>  L < t_lo  for sure.
+        const float h0f = static_cast<float>(h0), h1f = static_cast<float>(h1);
+        const float dmax = sqrtf(b2) * 1.0001f;
+        const double c = h0 * f0 + h1 * f1;
+        const double a_lo = -t_lo - c, a_hi = -t_hi - c;
+        // + fp64 roundings of c and of the canonical loss itself (both <= 2^-51 of these magnitudes)
+        const double eps64 = (fabs(h0 * f0) + fabs(h1 * f1) + (fabs(h0) + fabs(h1)) * static_cast<double>(dmax)) * 1e-15;
+        const float bound = (fabsf(h0f) + fabsf(h1f)) * dmax * 1.9073486e-06f + 1.1754944e-38f +
+                            static_cast<float>(eps64) * 1.0001f;
+        const float thr_keep = static_cast<float>(a_lo) + (bound + fabsf(static_cast<float>(a_lo)) * 2.3841858e-07f);
+        const float thr_above = static_cast<float>(a_hi) - (bound + fabsf(static_cast<float>(a_hi)) * 2.3841858e-07f);
+        const unsigned long long klo = key_of(t_lo), khi = key_of(t_hi);
+        const unsigned long long span = khi - klo;
+        const int bits = span ? 64 - __clzll(static_cast<long long>(span)) : 0;
+        window_ok = window_ok && isfinite(thr_keep) && isfinite(thr_above) && (khi >= klo) && (thr_above <= thr_keep);
+        if (lane == 0) {
+          ctl->h0 = h0; ctl->h1 = h1; ctl->m0 = m0; ctl->m1 = m1;
+          ctl->f0 = f0; ctl->f1 = f1;
+          ctl->t_lo = t_lo;
+          ctl->t_hi = t_hi;
+          ctl->h0f = h0f; ctl->h1f = h1f; ctl->thr_keep = thr_keep; ctl->thr_above = thr_above;
+          ctl->key_lo = klo;
+          ctl->hist_shift = bits > 8 ? bits - 8 : 0;
+          ctl->window_ok = window_ok;
+          ctl->nonfinite = nonfinite;
+          ctl->degenerate = degenerate;
+        }
       }
     }
     team_sync();  // S2
@@ -800,58 +810,53 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
 
     if (!nonfinite && window) {
       // ---------------------------------------------------------------- sweep B: classify, build the exact-needed mask
-      // rows: 16-byte loads in visit order, row r = smem vector index r*256 + tid.  Mask bit P = kPerLoad r + e.
+      // Mask bit P = kPerLoad r + e  <->  sample r*kRowSamples + kPerLoad tid + e.
       unsigned mask[kMaskWords] = {0u, 0u, 0u, 0u};
-      int c32 = 0;                                    // "surely above" (fp32 bound, or exactly in the band)
-      unsigned long long ab64 = 0ull;                 // packed (sum x, sum y) of their raw fp32 coordinates
+      float ax = 0.f, ay = 0.f, cf = 0.f;            // "surely above": shifted coordinate sums and count
       constexpr int kRowsPerWord = 32 / kPerLoad;     // 16 (fp32) / 32 (fp64)
-      const int full_rows = full_tiles * kQ;
       if constexpr (kF32) {
         const float4* sm4 = reinterpret_cast<const float4*>(smem_raw);
         const float h0f = ctl->h0f, h1f = ctl->h1f, thr_keep = ctl->thr_keep, thr_above = ctl->thr_above;
+        const float2 nf = make_float2(-first.x, -first.y);
 #pragma unroll
         for (int wd = 0; wd < kMaskWords; ++wd) {
           const int r_lo = wd * kRowsPerWord;
           const int r_hi = full_rows < r_lo + kRowsPerWord ? full_rows : r_lo + kRowsPerWord;
-          unsigned bit0 = 1u, bit1 = 2u;
+          unsigned bit = 1u;
 #pragma unroll 4
           for (int r = r_lo; r < r_hi; ++r) {
             const float4 v = sm4[r * kSweepThreads + tid];
-            const float p0 = fmaf(h1f, v.y, h0f * v.x), p1 = fmaf(h1f, v.w, h0f * v.z);
-            classify_f32(p0, thr_above, thr_keep, pack2(v.x, v.y), ab64, c32, mask[wd], bit0);
-            classify_f32(p1, thr_above, thr_keep, pack2(v.z, v.w), ab64, c32, mask[wd], bit1);
-            bit0 <<= 2;
-            bit1 <<= 2;
+            const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nf), d1 = __fadd2_rn(make_float2(v.z, v.w), nf);
+            const float p0 = fmaf(h1f, d0.y, h0f * d0.x), p1 = fmaf(h1f, d1.y, h0f * d1.x);
+            classify_f32(p0, thr_above, thr_keep, d0.x, d0.y, ax, ay, cf, mask[wd], bit);
+            classify_f32(p1, thr_above, thr_keep, d1.x, d1.y, ax, ay, cf, mask[wd], bit + bit);
+            bit <<= 2;
           }
         }
-        if (full_tiles < tiles) {  // ragged last tile, element-wise
+        for (int r = full_rows; r < rows_all; ++r) {  // ragged rows, element-wise
 #pragma unroll
-          for (int q = 0; q < kQ; ++q) {
-            const int rr = full_rows + q;
+          for (int e = 0; e < 2; ++e) {
+            const int i = r * kRowSamples + 2 * tid + e;
+            if (i < N) {
+              const float2 v = sm[i];
+              const float2 d = __fadd2_rn(v, nf);
+              const int P = 2 * r + e;
+              unsigned mk = 0;
+              classify_f32(fmaf(h1f, d.y, h0f * d.x), thr_above, thr_keep, d.x, d.y, ax, ay, cf, mk, 1u << (P & 31));
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int i = rr * (2 * kSweepThreads) + 2 * tid + e;
-              if (i < N) {
-                const float2 v = sm[i];
-                const int P = 2 * rr + e;
-                unsigned mk = 0;
-                classify_f32(fmaf(h1f, v.y, h0f * v.x), thr_above, thr_keep, pack2(v.x, v.y), ab64, c32, mk, 1u << (P & 31));
-#pragma unroll
-                for (int w2 = 0; w2 < kMaskWords; ++w2)
-                  if (w2 == (P >> 5)) mask[w2] |= mk;
-              }
+              for (int w2 = 0; w2 < kMaskWords; ++w2)
+                if (w2 == (P >> 5)) mask[w2] |= mk;
             }
           }
         }
       } else {
-        const int rows_all = tiles * kQ;
 #pragma unroll
         for (int wd = 0; wd < kMaskWords; ++wd) {
           const int r_lo = wd * kRowsPerWord;
           const int r_hi = rows_all < r_lo + kRowsPerWord ? rows_all : r_lo + kRowsPerWord;
           unsigned bit = 1u;
           for (int r = r_lo; r < r_hi; ++r, bit <<= 1) {
-            const int i = r * kSweepThreads + tid;
+            const int i = r * kRowSamples + tid;
             if (i < N) {
               const V2 v = sm[i];
               const double L = loss_of(h0, h1, v.x, v.y);
@@ -865,58 +870,82 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           }
         }
       }
-
       PH_MARK(4)
-      // -------------------------------------------------------------- phase 2: exact loss of the masked samples
-      // warp-lockstep over each lane's k-th masked sample; window losses -> this warp's candidate list
-      int nc = 0;  // candidates of this warp (warp-uniform)
-      for (;;) {
-        int P = -1;
+
+      // -------------------------------------------------------------- phase 2a: compact the masked samples per warp
+      int mine_n = 0;
+#pragma unroll
+      for (int wd = 0; wd < kMaskWords; ++wd)
+        if (wd * 32 < rows_all * kPerLoad) mine_n += __popc(mask[wd]);
+      int incl = mine_n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const int n_list = __shfl_sync(kFull, incl, 31);
+      bool overflow = n_list > kWarpList;
+      if (!overflow) {
+        int pos = incl - mine_n;
 #pragma unroll
         for (int wd = 0; wd < kMaskWords; ++wd) {
-          if (P < 0 && mask[wd] != 0u) {
-            P = 32 * wd + (__ffs(mask[wd]) - 1);
-            mask[wd] &= mask[wd] - 1u;
+          if (wd * 32 < rows_all * kPerLoad) {
+            unsigned mm = mask[wd];
+            while (mm) {
+              const unsigned bp = 31u - static_cast<unsigned>(__clz(static_cast<int>(mm)));   // highest set bit (one FLO)
+              mm ^= 1u << bp;
+              const unsigned P = 32u * wd + bp;
+              const unsigned i = kF32 ? ((P >> 1) * kRowSamples + 2u * tid + (P & 1u)) : (P * kRowSamples + tid);
+              wlist[pos++] = static_cast<unsigned short>(i);
+            }
           }
         }
-        if (!__any_sync(kFull, P >= 0)) break;
-        const bool active = P >= 0;
-        double L = 0.0;
-        V2 v = first;
-        if (active) {
-          const unsigned uP = static_cast<unsigned>(P);
-          const unsigned i = kF32 ? ((uP >> 1) * (2u * kSweepThreads) + 2u * tid + (uP & 1u)) : (uP * kSweepThreads + tid);
-          v = sm[i];
-          L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
-        }
-        const bool up = active && (L > t_hi);
-        const bool cd = active && !up && (L >= t_lo);
-        if constexpr (kF32) {
-          if (up) {  // inside the fp32 uncertainty band but exactly above the window: joins the "above" set
-            ++c32;
-            ab64 = pack2(__fadd_rn(unpack2(ab64).x, v.x), __fadd_rn(unpack2(ab64).y, v.y));
+      }
+      __syncwarp();
+      // -------------------------------------------------------------- phase 2b: exact loss of the listed samples, dense
+      int nc = 0;  // candidates of this warp (warp-uniform)
+      const unsigned long long klo = ctl->key_lo;
+      const int hshift = ctl->hist_shift;
+      if (!overflow) {
+        for (int k0 = 0; k0 < n_list; k0 += 32) {
+          const int k = k0 + lane;
+          const bool active = k < n_list;
+          double L = 0.0;
+          V2 v = first;
+          if (active) {
+            v = sm[wlist[k]];
+            L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
+          }
+          const bool up = active && (L > t_hi);
+          const bool cd = active && !up && (L >= t_lo);
+          if constexpr (kF32) {
+            if (up) {  // inside the fp32 uncertainty band but exactly above the window: joins the "above" set
+              cf += 1.0f;
+              ax += static_cast<float>(v.x) - static_cast<float>(first.x);
+              ay += static_cast<float>(v.y) - static_cast<float>(first.y);
+            }
+          }
+          const unsigned bal = __ballot_sync(kFull, cd);
+          if (bal) {
+            const int pos = nc + __popc(bal & ((1u << lane) - 1u));
+            if (cd && pos < kWarpCand) {
+              wcand[pos] = L;
+              atomicAdd(&hist[static_cast<unsigned>((key_of(L) - klo) >> hshift)], 1u);
+            }
+            nc += __popc(bal);
           }
         }
-        const unsigned bal = __ballot_sync(kFull, cd);
-        if (bal) {
-          const int pos = nc + __popc(bal & ((1u << lane) - 1u));
-          if (cd && pos < kWarpCand) wcand[pos] = L;
-          nc += __popc(bal);
-        }
+        overflow = nc > kWarpCand;
       }
       PH_MARK(5)
       // per-warp partials
       {
-        const int wc = __reduce_add_sync(kFull, c_gt + c32);
-        double px = 0.0, py = 0.0, pe = 0.0;
+        const int wc = __reduce_add_sync(kFull, c_gt + static_cast<int>(cf));
+        double px = 0.0, py = 0.0, pe = 0.0, pn = 0.0;
         if constexpr (kF32) {
-          // packed fp32 warp sum of the raw coordinate sums, widened at the end
-          float2 t = unpack2(ab64);
-#pragma unroll
-          for (int m = 16; m >= 1; m >>= 1)
-            t = __fadd2_rn(t, make_float2(__shfl_xor_sync(kFull, t.x, m), __shfl_xor_sync(kFull, t.y, m)));
-          px = static_cast<double>(t.x);
-          py = static_cast<double>(t.y);
+          px = static_cast<double>(warp_sum_any(ax));
+          py = static_cast<double>(warp_sum_any(ay));
+          pn = static_cast<double>(wc);
         } else {
           pe = warp_sum_any(s_gt);
         }
@@ -926,10 +955,11 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           fin[warp * 4 + 0] = px;
           fin[warp * 4 + 1] = py;
           fin[warp * 4 + 2] = pe;
+          fin[warp * 4 + 3] = pn;
         }
       }
       PH_MARK(6)
-      const int ovf = team_sync_or(nc > kWarpCand);  // S3: the sample slot is no longer read on the fast path
+      const int ovf = team_sync_or(overflow);  // S3: the sample slot is no longer read on the fast path
       PH_MARK(7)
       int cnt_hi = 0, ncand = 0;
 #pragma unroll
@@ -975,7 +1005,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           kmax = o2 > kmax ? o2 : kmax;
         }
         unsigned long long* kred = reinterpret_cast<unsigned long long*>(red);
-        team_sync();  // red[] was consumed by warp 0 above; hist/small of this parity are ours until the handoff
+        team_sync();  // red[] was consumed by warps 0-1 above; hist/small of this parity are ours until the handoff
         if (lane == 0) {
           kred[warp * 2] = kmin;
           kred[warp * 2 + 1] = kmax;
@@ -1023,7 +1053,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         c_tot += iscr[w];
         s_tot += red[w];
       }
-      if (tid == 0) write_outputs(a, b, ctl, nonfinite, s_tot, c_tot, T_thr, status);
+      if (tid == 0) write_risk_outputs(a, b, ctl, nonfinite, s_tot, c_tot, T_thr, status);
     } else if (kTail) {
       c_tot = ctl->c_tot;
     }
@@ -1090,7 +1120,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     }
   }
 #ifdef DRCVAR_PROFILE_PHASES
-  if (tid == 32 && a.phase_cycles)
+  if (tid == 64 && a.phase_cycles)
     for (int k = 0; k < 12; ++k) a.phase_cycles[(blockIdx.x * 2 + 0) * 12 + k] = ph_t[k];
 #endif
 }
