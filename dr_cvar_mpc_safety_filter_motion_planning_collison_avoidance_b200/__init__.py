@@ -6,6 +6,7 @@ safety filter (mean / CVaR / Wasserstein DR-CVaR offsets), behind the reference'
   dropin/                     drop-in core/risk_metrics.py, core/halfspaces.py, core/geometry.py, ...
   sharding                    scenario sharding across the GPUs of one box (no collective on the hot path)
 """
-from .engine import HalfspaceBatch, compute_halfspaces, launch_count, max_samples, tail_count  # noqa: F401
+from .engine import (HalfspaceBatch, compute_halfspaces, compute_trajectory, launch_count, max_samples,  # noqa: F401
+                     tail_count)
 
-__all__ = ["HalfspaceBatch", "compute_halfspaces", "launch_count", "max_samples", "tail_count"]
+__all__ = ["HalfspaceBatch", "compute_halfspaces", "compute_trajectory", "launch_count", "max_samples", "tail_count"]

@@ -1,0 +1,92 @@
+"""
+Drop-in for the reference's simulation/environment.py (SafetyFilteringEnvironment, reference :6-139) with the
+(step, obstacle) double loop of compute_safe_halfspaces_for_trajectory replaced by ONE batched launch on the
+strided [N, T+1, 2] sample arrays.  Constructor, attributes and return structure are unchanged:
+{'mean'|'cvar'|'dr_cvar': [n_steps][n_obstacles] SafeHalfspace}.
+"""
+import time
+
+import numpy as np
+
+from core.halfspaces import MeanSafeHalfspace, CVaRSafeHalfspace, DRCVaRSafeHalfspace, compute_safe_halfspaces  # noqa: F401
+
+from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import engine as _engine
+
+
+def _double_integrator(dt, dim=2):
+    """A, B, C of the planar double integrator (same matrices as the reference's core/dynamics.py:7-33)."""
+    eye, zero = np.eye(dim), np.zeros((dim, dim))
+    A = np.block([[eye, dt * eye], [zero, eye]])
+    B = np.block([[0.5 * dt ** 2 * eye], [dt * eye]])
+    C = np.block([eye, zero])
+    return A, B, C
+
+
+class SafetyFilteringEnvironment:
+    def __init__(self, ROBOT_RADIUS, OBSTACLE_RADIUS, HORIZON, DT, ALPHA, DELTA, EPSILON):
+        self.ROBOT_RADIUS = ROBOT_RADIUS
+        self.OBSTACLE_RADIUS = OBSTACLE_RADIUS
+        self.HORIZON = HORIZON
+        self.DT = DT
+        self.ALPHA = ALPHA
+        self.DELTA = DELTA
+        self.EPSILON = EPSILON
+        self.A, self.B, self.C = _double_integrator(DT)
+        self.n_states = self.A.shape[0]
+        self.n_inputs = self.B.shape[1]
+        self.n_outputs = self.C.shape[0]
+        self.state_bounds = None
+        self.input_bounds = None
+
+    def set_bounds(self, state_bounds=None, input_bounds=None):
+        self.state_bounds = state_bounds
+        self.input_bounds = input_bounds
+
+    def compute_safe_halfspaces_for_trajectory(self, obstacle_sample_trajectories, ego_ref_trajectory):
+        """Safe halfspaces for each step t < min(len(ego_ref_trajectory), HORIZON) and each obstacle."""
+        n_steps = min(len(ego_ref_trajectory), self.HORIZON)
+        out = {'mean': [[] for _ in range(n_steps)], 'cvar': [[] for _ in range(n_steps)],
+               'dr_cvar': [[] for _ in range(n_steps)]}
+        if n_steps == 0 or len(obstacle_sample_trajectories) == 0:
+            return out
+        ego_steps = np.stack([self.C @ np.asarray(ego_ref_trajectory[t]) for t in range(n_steps)])
+        trajs = [np.asarray(tr, dtype=np.float64) for tr in obstacle_sample_trajectories]
+        uniform = all(tr.shape == trajs[0].shape for tr in trajs) and trajs[0].shape[1] >= n_steps
+        t0 = time.time()
+        if uniform:
+            h, hm, g, _ = _engine.compute_trajectory(trajs, ego_steps, alpha=self.ALPHA, delta=self.DELTA,
+                                                     epsilon=self.EPSILON, robot_radius=self.ROBOT_RADIUS,
+                                                     obstacle_radius=self.OBSTACLE_RADIUS)
+        else:  # ragged sample counts: one launch per step
+            rows = [compute_safe_halfspaces([tr[:, t, :] for tr in trajs], ego_steps[t], self.ROBOT_RADIUS,
+                                            self.OBSTACLE_RADIUS, self.ALPHA, self.DELTA, self.EPSILON)
+                    for t in range(n_steps)]
+            for t in range(n_steps):
+                for k in out:
+                    out[k][t] = rows[t][k]
+            return out
+        info = {'setup_time': 0.0, 'solve_time': time.time() - t0}
+        zero = {'setup_time': 0, 'solve_time': 0, 'solve_call_time': 0}
+        for t in range(n_steps):
+            for i in range(len(trajs)):
+                m = MeanSafeHalfspace(np.array(hm[t, i]), float(g[t, i, 0]))
+                m.info = dict(zero)
+                c = CVaRSafeHalfspace(np.array(h[t, i]), float(g[t, i, 1]))
+                c.info = dict(info)
+                d = DRCVaRSafeHalfspace(np.array(h[t, i]), float(g[t, i, 2]))
+                d.info = dict(info)
+                out['mean'][t].append(m)
+                out['cvar'][t].append(c)
+                out['dr_cvar'][t].append(d)
+        return out
+
+    def compute_distance_to_collision(self, ego_trajectory, obstacle_trajectories):
+        """Minimum clearance (centre distance minus both radii) over the obstacles, per time step."""
+        n_steps = min(len(ego_trajectory), len(obstacle_trajectories[0]))
+        distances = np.inf * np.ones(n_steps)
+        for t in range(n_steps):
+            ego = self.C @ np.asarray(ego_trajectory[t])
+            for traj in obstacle_trajectories:
+                d = np.linalg.norm(ego - traj[t]) - self.ROBOT_RADIUS - self.OBSTACLE_RADIUS
+                distances[t] = min(distances[t], d)
+        return distances

@@ -164,3 +164,36 @@ def launch_count() -> int:
 
 def max_samples(dtype, device: int = -1) -> int:
     return int(_lib.check(_lib.load().drcvar_max_samples(int(np.dtype(dtype).itemsize), int(device))))
+
+
+def compute_trajectory(obstacle_sample_trajectories, ego_steps, *, alpha, delta, epsilon, robot_radius,
+                       obstacle_radius, flags=0):
+    """
+    One launch for every (step, obstacle) of a reference trajectory — the batched form of
+    SafetyFilteringEnvironment.compute_safe_halfspaces_for_trajectory (simulation/environment.py:60-106):
+    halfspace (t, i) uses samples traj[i][:, t, :] and ego ego_steps[t].
+
+    obstacle_sample_trajectories: list of n_obs float64 arrays [N, T1, 2] (C-contiguous, same N and T1)
+    ego_steps: [n_steps, 2] float64, n_steps <= T1
+    Returns (h [n_steps, n_obs, 2], h_mean [n_steps, n_obs, 2], g [n_steps, n_obs, 3], status [n_steps, n_obs]).
+    """
+    lib = _lib.load()
+    trajs = [np.ascontiguousarray(t, dtype=np.float64) for t in obstacle_sample_trajectories]
+    n_obs = len(trajs)
+    if n_obs == 0:
+        raise ValueError("at least one obstacle is required")
+    N, T1, two = trajs[0].shape
+    if two != 2 or any(t.shape != (N, T1, 2) for t in trajs):
+        raise ValueError("every obstacle trajectory must be [N, T1, 2] with the same N and T1")
+    ego = np.ascontiguousarray(ego_steps, dtype=np.float64)
+    n_steps = ego.shape[0]
+    ptrs = (C.c_void_p * n_obs)(*[t.ctypes.data for t in trajs])
+    h = np.empty((n_steps, n_obs, 2))
+    hm = np.empty((n_steps, n_obs, 2))
+    g = np.empty((n_steps, n_obs, 3))
+    st = np.zeros((n_steps, n_obs), dtype=np.int32)
+    rc = lib.drcvar_trajectory_f64(ptrs, n_obs, N, T1, n_steps, ego.ctypes.data, float(alpha), float(delta),
+                                   float(epsilon), float(robot_radius), float(obstacle_radius), int(flags),
+                                   h.ctypes.data, hm.ctypes.data, g.ctypes.data, st.ctypes.data)
+    _lib.check(rc)
+    return h, hm, g, st

@@ -1,0 +1,192 @@
+"""
+Drop-in boundary tests.
+
+CPU part: the drop-in modules expose exactly the names and call signatures of the reference's
+core/risk_metrics.py, core/halfspaces.py, core/geometry.py, simulation/environment.py and utils/timing.py
+(checked against a frozen table, and against the reference itself when /root/reference is present).
+GPU part (-m gpu): the reference's call patterns (timing sweep, main.py single scenario) through the drop-in
+modules reproduce the golden vectors the reference's own modules produced.
+"""
+import importlib
+import inspect
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200", "dropin")
+_TOP = ("core", "utils", "simulation", "config", "evaluation")
+
+EXPECTED = {
+    "core.risk_metrics": {
+        "save_timing_info": "(key, setup_time, solve_time)",
+        "expected_value": "(samples)",
+        "var_metric": "(samples, alpha)",
+        "cvar_metric": "(samples, alpha)",
+        "dr_cvar_halfspace": "(samples, h, alpha, delta, epsilon, robot_radius, obstacle_radius)",
+        "cvar_halfspace": "(samples, h, alpha, delta, robot_radius, obstacle_radius)",
+        "DRCVaROptimizer.__init__": "(self, alpha, epsilon, delta, max_samples)",
+        "DRCVaROptimizer.solve": "(self, h, samples, combined_radius)",
+        "CVaROptimizer.__init__": "(self, alpha, delta, max_samples)",
+        "CVaROptimizer.solve": "(self, h, samples, combined_radius)",
+    },
+    "core.halfspaces": {
+        "SafeHalfspace.__init__": "(self, h, g_tilde)",
+        "SafeHalfspace.is_point_safe": "(self, point)",
+        "SafeHalfspace.distance_to_boundary": "(self, point)",
+        "SafeHalfspace.get_constraint_params": "(self)",
+        "MeanSafeHalfspace.create": "(samples, robot_radius, obstacle_radius)",
+        "CVaRSafeHalfspace.create": "(samples, ego_ref_pos, alpha, delta, robot_radius, obstacle_radius)",
+        "DRCVaRSafeHalfspace.create": "(samples, ego_ref_pos, alpha, delta, epsilon, robot_radius, obstacle_radius)",
+        "compute_safe_halfspaces": "(obstacle_samples, ego_ref_pos, robot_radius, obstacle_radius, alpha, delta, epsilon)",
+    },
+    "core.geometry": {"compute_separating_vector": "(ego_pos, obstacle_pos)"},
+    "simulation.environment": {
+        "SafetyFilteringEnvironment.__init__": "(self, ROBOT_RADIUS, OBSTACLE_RADIUS, HORIZON, DT, ALPHA, DELTA, EPSILON)",
+        "SafetyFilteringEnvironment.set_bounds": "(self, state_bounds=None, input_bounds=None)",
+        "SafetyFilteringEnvironment.compute_safe_halfspaces_for_trajectory": "(self, obstacle_sample_trajectories, ego_ref_trajectory)",
+        "SafetyFilteringEnvironment.compute_distance_to_collision": "(self, ego_trajectory, obstacle_trajectories)",
+    },
+    "utils.timing": {
+        "Timer.__init__": "(self, name=None)", "Timer.start": "(self)", "Timer.stop": "(self)", "timeit": "(func)",
+        "TimingStats.add": "(self, name, time_value)", "TimingStats.get_stats": "(self, name)",
+        "TimingStats.print_stats": "(self)",
+    },
+}
+
+
+def _purge():
+    for k in list(sys.modules):
+        if k.split(".")[0] in _TOP:
+            del sys.modules[k]
+
+
+@pytest.fixture()
+def dropin(tmp_path, monkeypatch):
+    """The drop-in modules imported fresh, cwd in a scratch dir (they write tmp/timing_info_*.json like the reference)."""
+    _purge()
+    monkeypatch.syspath_prepend(DROPIN)
+    monkeypatch.chdir(tmp_path)
+    mods = {name: importlib.import_module(name) for name in EXPECTED}
+    yield mods
+    _purge()
+
+
+def _sig(mod, dotted):
+    obj = mod
+    for part in dotted.split("."):
+        obj = inspect.getattr_static(obj, part) if inspect.isclass(obj) else getattr(obj, part)
+        if isinstance(obj, staticmethod):
+            obj = obj.__func__
+    return str(inspect.signature(obj))
+
+
+def test_signatures_match_frozen_table(dropin):
+    for modname, table in EXPECTED.items():
+        for dotted, sig in table.items():
+            assert _sig(dropin[modname], dotted) == sig, (modname, dotted)
+    rm = dropin["core.risk_metrics"]
+    assert rm.drcvar_optimizer is None and rm.cvar_optimizer is None          # module-global singletons exist
+    o = rm.DRCVaROptimizer(0.2, 0.15, 0.1, 20)
+    assert (o.alpha, o.epsilon, o.delta, o.n_samples) == (0.2, 0.15, 0.1, 20)
+
+
+def test_frozen_table_matches_the_reference_itself():
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference tree not present")
+    _purge()
+    with ref_harness.reference_modules() as ref:
+        mods = {"core.risk_metrics": ref.risk_metrics, "core.halfspaces": ref.halfspaces, "core.geometry": ref.geometry,
+                "simulation.environment": ref.environment, "utils.timing": importlib.import_module("utils.timing")}
+        for modname, table in EXPECTED.items():
+            for dotted, sig in table.items():
+                assert _sig(mods[modname], dotted) == sig, (modname, dotted)
+
+
+def test_dead_helpers_keep_reference_semantics(dropin):
+    rm = dropin["core.risk_metrics"]
+    x = np.arange(20.0)
+    assert rm.var_metric(x, 0.2) == 15.0 and rm.cvar_metric(x, 0.2) == 17.0      # top floor(aN)+1 samples
+    assert np.allclose(rm.expected_value(np.ones((4, 2))), [1.0, 1.0])
+    g = dropin["core.geometry"]
+    assert np.array_equal(g.compute_separating_vector(np.zeros(2), np.zeros(2)), [1.0, 0.0])
+    assert np.allclose(g.compute_separating_vector(np.array([1.0, 1.0]), np.array([4.0, 5.0])), [0.6, 0.8])
+
+
+def test_timer_and_stats(dropin, capsys):
+    t = dropin["utils.timing"]
+    with t.Timer("X") as tm:
+        pass
+    assert "X: " in capsys.readouterr().out and tm.elapsed >= 0
+    s = t.TimingStats()
+    s.add("a", 1.0); s.add("a", 3.0)
+    assert s.get_stats("a")["mean"] == 2.0 and s.get_stats("b") is None
+
+
+# ------------------------------------------------------------------------------------------------ GPU part
+@pytest.mark.gpu
+def test_timing_sweep_call_pattern(dropin, golden_dir, capsys):
+    z = np.load(os.path.join(golden_dir, "timing_sweep.npz"))
+    alpha, delta, eps, rr, ro = (float(v) for v in z["params"])
+    H = dropin["core.halfspaces"]
+    for n in z["sizes"]:
+        s, ref = z[f"samples_{n}"], z[f"out_{n}"]
+        ego = np.array([0.0, 0.0])
+        dr = H.DRCVaRSafeHalfspace.create(s, ego, alpha, delta, eps, rr, ro)          # evaluation/timing_analysis.py:74
+        cv = H.CVaRSafeHalfspace.create(s, ego, alpha, delta, rr, ro)                 # evaluation/timing_analysis.py:101
+        mn = H.MeanSafeHalfspace.create(s, rr, ro)
+        assert np.abs(dr.h - ref[0:2]).max() < 1e-12 and abs(dr.g_tilde - ref[2]) < 1e-9
+        assert np.abs(cv.h - ref[3:5]).max() < 1e-12 and abs(cv.g_tilde - ref[5]) < 1e-9
+        assert np.abs(mn.h - ref[6:8]).max() < 1e-12 and abs(mn.g_tilde - ref[8]) < 1e-9
+        assert set(dr.info) >= {"setup_time", "solve_time"} and set(mn.info) == {"setup_time", "solve_time", "solve_call_time"}
+        for key in ("drcvar", "cvar"):                                                # side channel read by the sweep (:84,:111)
+            with open(f"tmp/timing_info_{key}.json") as f:
+                assert set(json.load(f)) == {"setup_time", "solve_time"}
+        h, g = dr.get_constraint_params()
+        assert isinstance(g, float) and h.shape == (2,) and bool(dr.is_point_safe(np.array([-5.0, 0.0])))
+    out = capsys.readouterr().out
+    assert "DR-CVaR Optimization:" in out and "create:" in out and "DEBUG - Saved drcvar timing" in out
+
+
+@pytest.mark.gpu
+def test_explicit_h_entry_points(dropin, golden_dir):
+    z = np.load(os.path.join(golden_dir, "explicit_h.npz"))
+    rm = dropin["core.risk_metrics"]
+    for c in range(int(z["n_cases"])):
+        alpha, delta, eps, rr, ro, h0, h1 = (float(v) for v in z[f"in_{c}"])
+        g_star, g_tilde, g_cvar = z[f"out_{c}"]
+        a, b = rm.dr_cvar_halfspace(z[f"samples_{c}"], np.array([h0, h1]), alpha, delta, eps, rr, ro)
+        assert abs(a - g_star) < 1e-9 and abs(b - g_tilde) < 1e-9
+        assert abs(rm.cvar_halfspace(z[f"samples_{c}"], np.array([h0, h1]), alpha, delta, rr, ro) - g_cvar) < 1e-9
+    bad = np.full((8, 2), np.nan)
+    assert rm.cvar_halfspace(bad, np.array([1.0, 0.0]), 0.25, 0.1, 0.3, 0.3) == 100.0       # failure sentinel
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["head_on_seed42.npz", "multi_obstacle_seed42.npz"])
+def test_trajectory_driver_matches_reference(dropin, golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    alpha, delta, eps, rr, ro, horizon = (float(v) for v in z["params"])
+    env_mod = dropin["simulation.environment"]
+    env = env_mod.SafetyFilteringEnvironment(rr, ro, int(horizon), 0.2, alpha, delta, eps)
+    traj = [z["sample_trajectories"][i] for i in range(z["sample_trajectories"].shape[0])]
+    hs = env.compute_safe_halfspaces_for_trajectory(traj, z["x_ref"])                     # main.py:95
+    n_steps, n_obs = z["g_mean"].shape
+    assert len(hs["mean"]) == n_steps and all(len(r) == n_obs for r in hs["dr_cvar"])
+    for metric in ("mean", "cvar", "dr_cvar"):
+        for t in range(n_steps):
+            for i in range(n_obs):
+                h, g = hs[metric][t][i].get_constraint_params()
+                assert np.abs(h - z[f"h_{metric}"][t, i]).max() < 1e-12
+                assert abs(g - z[f"g_{metric}"][t, i]) < 1e-9
+    # the per-step API gives the same objects (core/halfspaces.py:196 called from environment.py:95)
+    H = dropin["core.halfspaces"]
+    t = 5
+    row = H.compute_safe_halfspaces([tr[:, t, :] for tr in traj], z["x_ref"][t][:2], rr, ro, alpha, delta, eps)
+    for i in range(n_obs):
+        assert row["dr_cvar"][i].g_tilde == hs["dr_cvar"][t][i].g_tilde
+        assert np.array_equal(row["cvar"][i].h, hs["cvar"][t][i].h)
