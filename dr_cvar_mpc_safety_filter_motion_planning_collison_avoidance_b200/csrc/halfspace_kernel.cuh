@@ -1,15 +1,17 @@
 // halfspace_kernel.cuh — sm_100a device code of the risk-bounded safe-halfspace path.
 //
 // One CTA per (scenario, obstacle, step) halfspace, persistent over the batch; two CTAs per SM.
-// A CTA is a team of 8 "sweep" warps plus 1 "finisher" warp, pipelined over consecutive halfspaces through two
-// parity buffers and shared-memory mbarriers (full / empty), so the select + epilogue of halfspace j overlaps the
-// load and sweeps of halfspace j+1.
+// A CTA is a team of 8 "sweep" warps plus a "finisher" warp and a "director" warp, pipelined over consecutive
+// halfspaces through two parity buffers and shared-memory mbarriers, so the select + epilogue of halfspace j and
+// the slow IEEE div/sqrt chain of the canonical direction overlap the load and sweeps around them.
 //
 // sweep team, per halfspace:
 //   stage   N samples -> shared memory with cp.async.bulk (TMA bulk copy, mbarrier completion) or a strided loader
 //   sweep A canonical lane sums of the coordinates (fp32 inputs: shifted by the first sample, packed fp32 lane
 //           partials, fp64 cross-lane tree; fp64 inputs: fp64 throughout) + second moments              -> mean m
-//   h       = unit(m - ego)                                                            core/geometry.py:35-53
+//   h       warp 0: fp64-accurate (1e-15) direction WITHOUT div/sqrt, only to place the window and the fp32 thresholds
+//           director warp (concurrently): the canonical h = unit(m - ego) with IEEE div/sqrt  core/geometry.py:35-53
+//           and the mean halfspace                                                            core/halfspaces.py:70-106
 //   sweep B classify every sample against a statistical window [t_lo, t_hi] around the expected kc-th largest
 //           loss.  fp32 inputs: a rigorous fp32 bound decides "surely above" (count + shifted coordinate sums; the
 //           loss sum follows from linearity), "surely below" (ignored) or "needs the exact fp64 loss" (a bit in a
@@ -44,7 +46,9 @@ namespace drcvar {
 
 constexpr int kSweepWarps = 8;
 constexpr int kSweepThreads = kSweepWarps * 32;      // 256
-constexpr int kThreads = kSweepThreads + 32;         // + finisher warp
+constexpr int kThreads = kSweepThreads + 64;         // + finisher warp + director warp
+constexpr int kFinisherWarp = kSweepWarps;
+constexpr int kDirectorWarp = kSweepWarps + 1;
 constexpr int kSlots = 512;                          // canonical cross-lane tree width (2 slots per sweep thread)
 constexpr int kWarpCand = 128;                       // candidate losses per sweep warp (window path)
 constexpr int kWarpList = 192;                       // masked sample indices per sweep warp
@@ -100,6 +104,8 @@ struct Bars {
   unsigned long long data;         // bulk copy landed
   unsigned long long full[2];      // sweep team -> finisher
   unsigned long long empty[2];     // finisher -> sweep team
+  unsigned long long adone[2];     // sweep team -> director: lane sums of sweep A are in red[par]
+  unsigned long long hdone[2];     // director -> sweep team: canonical h / mean / flags are in ctl[par]
 };
 
 template <typename T> struct Vec2;
@@ -115,7 +121,7 @@ constexpr int kFinDoubles = kSweepWarps * 4;                     // per parity, 
 __host__ __device__ inline size_t fixed_smem_bytes() {
   return sizeof(double) * 2 * kWarpCand * kSweepWarps   // cand   [2][warps][kWarpCand]
          + sizeof(unsigned) * 2 * kHistBuckets          // hist   [2][256]
-         + sizeof(double) * kRedDoubles                 // red
+         + sizeof(double) * 2 * kRedDoubles             // red    [2]
          + sizeof(double) * 2 * kFinDoubles             // fin    [2]
          + sizeof(double) * 2 * kResolveMax             // small  [2]
          + sizeof(int) * 2 * 2 * kSweepWarps            // ired   [2][warps][2]
@@ -382,8 +388,8 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   V2* sm = reinterpret_cast<V2*>(smem_raw);
   double* cand_base = reinterpret_cast<double*>(smem_raw + slot_bytes);
   unsigned* hist_base = reinterpret_cast<unsigned*>(cand_base + 2 * kWarpCand * kSweepWarps);
-  double* red = reinterpret_cast<double*>(hist_base + 2 * kHistBuckets);
-  double* fin_base = red + kRedDoubles;
+  double* red_base = reinterpret_cast<double*>(hist_base + 2 * kHistBuckets);
+  double* fin_base = red_base + 2 * kRedDoubles;
   double* small_base = fin_base + 2 * kFinDoubles;
   int* ired_base = reinterpret_cast<int*>(small_base + 2 * kResolveMax);
   int* iscr = ired_base + 2 * 2 * kSweepWarps;
@@ -397,6 +403,10 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     mbar_init(&bars->full[1], 1);
     mbar_init(&bars->empty[0], 1);
     mbar_init(&bars->empty[1], 1);
+    mbar_init(&bars->adone[0], 1);
+    mbar_init(&bars->adone[1], 1);
+    mbar_init(&bars->hdone[0], 1);
+    mbar_init(&bars->hdone[1], 1);
     mbar_fence_init();
   }
   for (int i = tid; i < 2 * kHistBuckets; i += kThreads) hist_base[i] = 0;
@@ -404,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   __syncthreads();
 
   // ============================================================================================ finisher warp
-  if (warp == kSweepWarps) {
+  if (warp == kFinisherWarp) {
     int iter = 0;
     PH_DECL
     for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
@@ -530,6 +540,67 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     return;
   }
 
+  // ============================================================================================ director warp
+  // Canonical direction (IEEE div / sqrt chain, ~2k cycles of latency) and the mean halfspace, off the team's path.
+  if (warp == kDirectorWarp) {
+    int iter = 0;
+    for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
+      const int par = iter & 1, use = iter >> 1;
+      Ctl* ctl = ctl_base + par;
+      const double* red = red_base + par * kRedDoubles;
+      mbar_wait(&bars->adone[par], use & 1);
+      double w[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double t[kSweepWarps];
+#pragma unroll
+        for (int g = 0; g < kSweepWarps; ++g) t[g] = red[g * 8 + j];
+#pragma unroll
+        for (int n = kSweepWarps; n > 1; n >>= 1)
+#pragma unroll
+          for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);  // adjacent-pair tree
+        w[j] = t[0];
+      }
+      double m0 = __ddiv_rn(w[0], static_cast<double>(N));
+      double m1 = __ddiv_rn(w[1], static_cast<double>(N));
+      if constexpr (kF32) {  // fp32 inputs: the lane sums were taken relative to the first sample
+        m0 = __dadd_rn(red[6], m0);
+        m1 = __dadd_rn(red[7], m1);
+      }
+      int nonfinite = !(isfinite(m0) && isfinite(m1));
+      int degenerate = 0;
+      double h0, h1;
+      if (a.h_in != nullptr) {
+        h0 = a.h_in[2 * b];
+        h1 = a.h_in[2 * b + 1];
+      } else {
+        const double e0 = a.ego ? a.ego[2 * b] : 0.0, e1 = a.ego ? a.ego[2 * b + 1] : 0.0;
+        const double d0 = __dsub_rn(m0, e0), d1 = __dsub_rn(m1, e1);
+        const double nrm = norm2_canon(d0, d1);
+        if (nrm < 1e-10) {
+          h0 = 1.0;
+          h1 = 0.0;
+          degenerate = 1;
+        } else {
+          h0 = __ddiv_rn(d0, nrm);
+          h1 = __ddiv_rn(d1, nrm);
+        }
+      }
+      nonfinite |= !(isfinite(h0) && isfinite(h1));
+      if (lane == 0) {
+        ctl->h0 = h0; ctl->h1 = h1; ctl->m0 = m0; ctl->m1 = m1;
+        ctl->nonfinite = nonfinite;
+        ctl->degenerate = degenerate;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars->hdone[par]);
+        write_mean_outputs(a, b, m0, m1);
+      }
+    }
+    return;
+  }
+
   // ============================================================================================ sweep team
   const uint32_t copy_bytes = static_cast<uint32_t>(static_cast<size_t>(N) * sizeof(V2));
   auto issue_bulk = [&](long long b) {
@@ -547,6 +618,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   const int full_rows = N / kRowSamples;                 // rows of 16-byte loads fully inside the data
   const int rows_all = (N + kRowSamples - 1) / kRowSamples;
   unsigned short* wlist = list_base + warp * kWarpList;
+  const double inv_n = 1.0 / static_cast<double>(N);
   PH_DECL
 
   for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
@@ -557,6 +629,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     double* fin = fin_base + par * kFinDoubles;
     int* ired = ired_base + par * 2 * kSweepWarps;
     double* small = small_base + par * kResolveMax;
+    double* red = red_base + par * kRedDoubles;
     bool next_issued = false;
     const long long b_next = b + gridDim.x;
 
@@ -680,15 +753,17 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         double* w = red + warp * 8;
         w[0] = tx; w[1] = ty; w[2] = mxx; w[3] = myy; w[4] = mxy;
         w[5] = static_cast<double>(__uint_as_float(bnd));
-        w[6] = mdx; w[7] = mdy;
+        w[6] = kF32 ? static_cast<double>(first.x) : static_cast<double>(mdx);   // fp32: shift origin for the director
+        w[7] = kF32 ? static_cast<double>(first.y) : static_cast<double>(mdy);
       }
     }
     PH_MARK(1)
     team_sync();  // S1
     PH_MARK(2)
 
-    // ------------------------------------------------------------------ direction + window (warp 0); mean halfspace (warp 1)
-    if (warp < 2) {
+    // ------------------------------------------------------------------ window placement (warp 0); canonical h: director warp
+    if (tid == 0) mbar_arrive(&bars->adone[par]);   // red[par] is complete (S1): the director starts the canonical chain
+    if (warp == 0) {
       double w[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -698,117 +773,128 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
 #pragma unroll
         for (int n = kSweepWarps; n > 1; n >>= 1)
 #pragma unroll
-          for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);  // adjacent-pair tree
+          for (int g = 0; g < n / 2; ++g) t[g] = t[2 * g] + t[2 * g + 1];
         w[j] = t[0];
       }
-      double m0 = __ddiv_rn(w[0], static_cast<double>(N));
-      double m1 = __ddiv_rn(w[1], static_cast<double>(N));
-      if constexpr (kF32) {  // fp32 inputs: the lane sums were taken relative to the first sample
-        m0 = __dadd_rn(static_cast<double>(first.x), m0);
-        m1 = __dadd_rn(static_cast<double>(first.y), m1);
+      const double f0 = static_cast<double>(first.x), f1 = static_cast<double>(first.y);
+      // fp64-accurate but NOT canonical mean / direction (reciprocal multiply, rsqrt + Newton): |h_a - h| <= rel below
+      double m0 = w[0] * inv_n, m1 = w[1] * inv_n;
+      if (kF32) {
+        m0 += f0;
+        m1 += f1;
       }
-      if (warp == 1) {
-        if (lane == 0) write_mean_outputs(a, b, m0, m1);
+      double q[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        q[j] = 0.0;
+#pragma unroll
+        for (int g = 0; g < kSweepWarps; ++g) q[j] += red[g * 8 + (j < 3 ? 2 + j : 3 + j)];  // qxx,qyy,qxy,mdx,mdy
+      }
+      float b2 = 0.f;
+#pragma unroll
+      for (int g = 0; g < kSweepWarps; ++g) b2 = fmaxf(b2, static_cast<float>(red[g * 8 + 5]));
+      bool usable = isfinite(m0) && isfinite(m1);
+      double h0, h1, rel = 0.0;
+      if (a.h_in != nullptr) {
+        h0 = a.h_in[2 * b];
+        h1 = a.h_in[2 * b + 1];
       } else {
-        double q[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          q[j] = 0.0;
-#pragma unroll
-          for (int g = 0; g < kSweepWarps; ++g) q[j] += red[g * 8 + (j < 3 ? 2 + j : 3 + j)];  // qxx,qyy,qxy,mdx,mdy
-        }
-        float b2 = 0.f;
-#pragma unroll
-        for (int g = 0; g < kSweepWarps; ++g) b2 = fmaxf(b2, static_cast<float>(red[g * 8 + 5]));
-        int nonfinite = !(isfinite(m0) && isfinite(m1));
-        int degenerate = 0;
-        double h0, h1;
-        if (a.h_in != nullptr) {
-          h0 = a.h_in[2 * b];
-          h1 = a.h_in[2 * b + 1];
+        const double e0 = a.ego ? a.ego[2 * b] : 0.0, e1 = a.ego ? a.ego[2 * b + 1] : 0.0;
+        const double d0 = m0 - e0, d1 = m1 - e1;
+        const double n2 = d0 * d0 + d1 * d1;
+        if (n2 > 0.999e-20 && n2 < 1.001e-20) usable = false;   // too close to the degenerate-direction switch
+        if (n2 < 1e-20) {
+          h0 = 1.0;
+          h1 = 0.0;
         } else {
-          const double e0 = a.ego ? a.ego[2 * b] : 0.0, e1 = a.ego ? a.ego[2 * b + 1] : 0.0;
-          const double d0 = __dsub_rn(m0, e0), d1 = __dsub_rn(m1, e1);
-          const double nrm = norm2_canon(d0, d1);
-          if (nrm < 1e-10) {
-            h0 = 1.0;
-            h1 = 0.0;
-            degenerate = 1;
-          } else {
-            h0 = __ddiv_rn(d0, nrm);
-            h1 = __ddiv_rn(d1, nrm);
-          }
+          double rn = static_cast<double>(rsqrtf(static_cast<float>(n2)));
+          rn = rn * (1.5 - 0.5 * n2 * rn * rn);
+          rn = rn * (1.5 - 0.5 * n2 * rn * rn);
+          h0 = d0 * rn;
+          h1 = d1 * rn;
+          rel = 4e-15 * (1.0 + (fabs(m0) + fabs(m1) + fabs(e0) + fabs(e1)) * rn);
+          usable = usable && isfinite(rn) && rn > 0.0;
         }
-        nonfinite |= !(isfinite(h0) && isfinite(h1));
-        // heuristic window around the expected kc-th largest loss (affects speed only, never the result)
-        const double f0 = static_cast<double>(first.x), f1 = static_cast<double>(first.y);
-        int n_sub_i;
-        double ex, ey;
-        if (kF32) {
-          n_sub_i = N;
-          ex = m0 - f0;
-          ey = m1 - f1;
-        } else {
-          const int r4 = (rows_all + 3) / 4;                       // rows 0, 4, 8, ...
-          const int last = (r4 - 1) * 4 * kRowSamples;             // first sample of the last such row
-          n_sub_i = (r4 - 1) * kSweepThreads + (N - last < kSweepThreads ? N - last : kSweepThreads);
-          ex = q[3] / n_sub_i;
-          ey = q[4] / n_sub_i;
-        }
-        const double n_sub = static_cast<double>(n_sub_i > 0 ? n_sub_i : 1);
-        const double cxx = q[0] / n_sub - ex * ex, cyy = q[1] / n_sub - ey * ey, cxy = q[2] / n_sub - ex * ey;
-        const double var_l = h0 * h0 * cxx + 2.0 * h0 * h1 * cxy + h1 * h1 * cyy;
-        const double mu_l = -(h0 * m0 + h1 * m1);
-        const double sigma = static_cast<double>(sqrtf(static_cast<float>(var_l)));
-        int window_ok = a.use_window && (n_sub_i >= 256) && (var_l > 0.0) && isfinite(sigma) && !nonfinite &&
-                        (rows_all * kPerLoad <= 32 * kMaskWords);
-        const double t_lo = __dadd_rn(mu_l + a.z_lo * sigma, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
-        const double t_hi = __dadd_rn(mu_l + a.z_hi * sigma, 0.0);
-        // fp32 classification of p32 = fma(h1f, dy, h0f*dx), d = fl32(xi - first)  (p = h.xi = h.first + h.d = -L):
-        //   |p32 - h.d| <= 5 * 2^-24 * (|h0| + |h1|) * max|d|; we allow 2^-19 (32x) plus the rounding of the thresholds.
-        //   p32 <  thr_above  =>  L > t_hi  for sure;    p32 > thr_keep  =>  L < t_lo  for sure.
-        const float h0f = static_cast<float>(h0), h1f = static_cast<float>(h1);
-        const float dmax = sqrtf(b2) * 1.0001f;
-        const double c = h0 * f0 + h1 * f1;
-        const double a_lo = -t_lo - c, a_hi = -t_hi - c;
-        // + fp64 roundings of c and of the canonical loss itself (both <= 2^-51 of these magnitudes)
-        const double eps64 = (fabs(h0 * f0) + fabs(h1 * f1) + (fabs(h0) + fabs(h1)) * static_cast<double>(dmax)) * 1e-15;
-        const float bound = (fabsf(h0f) + fabsf(h1f)) * dmax * 1.9073486e-06f + 1.1754944e-38f +
-                            static_cast<float>(eps64) * 1.0001f;
-        const float thr_keep = static_cast<float>(a_lo) + (bound + fabsf(static_cast<float>(a_lo)) * 2.3841858e-07f);
-        const float thr_above = static_cast<float>(a_hi) - (bound + fabsf(static_cast<float>(a_hi)) * 2.3841858e-07f);
-        const unsigned long long klo = key_of(t_lo), khi = key_of(t_hi);
-        const unsigned long long span = khi - klo;
-        const int bits = span ? 64 - __clzll(static_cast<long long>(span)) : 0;
-        window_ok = window_ok && isfinite(thr_keep) && isfinite(thr_above) && (khi >= klo) && (thr_above <= thr_keep);
-        if (lane == 0) {
-          ctl->h0 = h0; ctl->h1 = h1; ctl->m0 = m0; ctl->m1 = m1;
-          ctl->f0 = f0; ctl->f1 = f1;
-          ctl->t_lo = t_lo;
-          ctl->t_hi = t_hi;
-          ctl->h0f = h0f; ctl->h1f = h1f; ctl->thr_keep = thr_keep; ctl->thr_above = thr_above;
-          ctl->key_lo = klo;
-          ctl->hist_shift = bits > 8 ? bits - 8 : 0;
-          ctl->window_ok = window_ok;
-          ctl->nonfinite = nonfinite;
-          ctl->degenerate = degenerate;
-        }
+      }
+      usable = usable && isfinite(h0) && isfinite(h1) && rel < 1e-7;
+      // heuristic window around the expected kc-th largest loss (affects speed only, never the result)
+      int n_sub_i;
+      double ex, ey;
+      if (kF32) {
+        n_sub_i = N;
+        ex = m0 - f0;
+        ey = m1 - f1;
+      } else {
+        const int r4 = (rows_all + 3) / 4;                       // rows 0, 4, 8, ...
+        const int last = (r4 - 1) * 4 * kRowSamples;             // first sample of the last such row
+        n_sub_i = (r4 - 1) * kSweepThreads + (N - last < kSweepThreads ? N - last : kSweepThreads);
+        ex = q[3] / n_sub_i;
+        ey = q[4] / n_sub_i;
+      }
+      const double n_sub = static_cast<double>(n_sub_i > 0 ? n_sub_i : 1);
+      const double cxx = q[0] / n_sub - ex * ex, cyy = q[1] / n_sub - ey * ey, cxy = q[2] / n_sub - ex * ey;
+      const double var_l = h0 * h0 * cxx + 2.0 * h0 * h1 * cxy + h1 * h1 * cyy;
+      const double mu_l = -(h0 * m0 + h1 * m1);
+      const double sigma = static_cast<double>(sqrtf(static_cast<float>(var_l)));
+      int window_ok = a.use_window && usable && (n_sub_i >= 256) && (var_l > 0.0) && isfinite(sigma) &&
+                      (rows_all * kPerLoad <= 32 * kMaskWords);
+      const double t_lo = __dadd_rn(mu_l + a.z_lo * sigma, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
+      const double t_hi = __dadd_rn(mu_l + a.z_hi * sigma, 0.0);
+      // fp32 classification of p32 = fma(h1f, dy, h0f*dx), d = fl32(xi - first)  (p = h.xi = h.first + h.d = -L):
+      //   |p32 - h_a.d| <= 5 * 2^-24 * (|h0| + |h1|) * max|d|; we allow 2^-19 (32x) plus the rounding of the thresholds,
+      //   plus |h_a - h| (|first| + max|d|) for the canonical h the director is computing meanwhile.
+      //   p32 <  thr_above  =>  L > t_hi  for sure;    p32 > thr_keep  =>  L < t_lo  for sure.
+      const float h0f = static_cast<float>(h0), h1f = static_cast<float>(h1);
+      const float dmax = sqrtf(b2) * 1.0001f;
+      const double c = h0 * f0 + h1 * f1;
+      const double a_lo = -t_lo - c, a_hi = -t_hi - c;
+      const double eps64 = (fabs(h0 * f0) + fabs(h1 * f1) + (fabs(h0) + fabs(h1)) * static_cast<double>(dmax)) * 1e-15 +
+                           rel * 1.5 * (fabs(f0) + fabs(f1) + 2.0 * static_cast<double>(dmax));
+      const float bound = (fabsf(h0f) + fabsf(h1f)) * dmax * 1.9073486e-06f + 1.1754944e-38f +
+                          static_cast<float>(eps64) * 1.0001f;
+      const float thr_keep = static_cast<float>(a_lo) + (bound + fabsf(static_cast<float>(a_lo)) * 2.3841858e-07f);
+      const float thr_above = static_cast<float>(a_hi) - (bound + fabsf(static_cast<float>(a_hi)) * 2.3841858e-07f);
+      const unsigned long long klo = key_of(t_lo), khi = key_of(t_hi);
+      const unsigned long long span = khi - klo;
+      const int bits = span ? 64 - __clzll(static_cast<long long>(span)) : 0;
+      window_ok = window_ok && isfinite(thr_keep) && isfinite(thr_above) && (khi >= klo) && (thr_above <= thr_keep);
+      if (lane == 0) {
+        ctl->f0 = f0; ctl->f1 = f1;
+        ctl->t_lo = t_lo;
+        ctl->t_hi = t_hi;
+        ctl->h0f = h0f; ctl->h1f = h1f; ctl->thr_keep = thr_keep; ctl->thr_above = thr_above;
+        ctl->key_lo = klo;
+        ctl->hist_shift = bits > 8 ? bits - 8 : 0;
+        ctl->window_ok = window_ok;
       }
     }
     team_sync();  // S2
     PH_MARK(3)
-    const double h0 = ctl->h0, h1 = ctl->h1;
-    const bool nonfinite = ctl->nonfinite != 0;
     const bool window = ctl->window_ok != 0;
     const double t_lo = ctl->t_lo, t_hi = ctl->t_hi;
-    int status = (nonfinite ? kStatusNonfinite : 0) | (ctl->degenerate ? kStatusDegenerate : 0);
+    // canonical direction and flags arrive from the director warp; fp32 inputs only need them for phase 2b
+    double h0 = 0.0, h1 = 0.0;
+    bool nonfinite = false;
+    int status = 0;
+    bool have_h = false;
+    auto need_h = [&]() {
+      if (!have_h) {
+        mbar_wait(&bars->hdone[par], use & 1);
+        h0 = ctl->h0;
+        h1 = ctl->h1;
+        nonfinite = ctl->nonfinite != 0;
+        status = (nonfinite ? kStatusNonfinite : 0) | (ctl->degenerate ? kStatusDegenerate : 0);
+        have_h = true;
+      }
+    };
+    if (!kF32 || !window) need_h();
 
     double T_thr = 0.0;
     int c_gt = 0;        // exact-classified losses above the threshold (this thread)
     double s_gt = 0.0;   // their sum
     bool fast = false;
 
-    if (!nonfinite && window) {
+    if (window && !nonfinite) {
       // ---------------------------------------------------------------- sweep B: classify, build the exact-needed mask
       // Mask bit P = kPerLoad r + e  <->  sample r*kRowSamples + kPerLoad tid + e.
       unsigned mask[kMaskWords] = {0u, 0u, 0u, 0u};
@@ -902,6 +988,8 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         }
       }
       __syncwarp();
+      need_h();
+      if (nonfinite) overflow = true;   // (cannot happen when the window was placed; keeps the flow uniform)
       // -------------------------------------------------------------- phase 2b: exact loss of the listed samples, dense
       int nc = 0;  // candidates of this warp (warp-uniform)
       const unsigned long long klo = ctl->key_lo;
@@ -988,6 +1076,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
 
     int c_tot = 0;
     if (!fast) {
+      need_h();
       if (!nonfinite) {
         // -------------------------------------------------------------- general path: sweeps over all samples
         status |= kStatusGeneral;

@@ -45,7 +45,7 @@ names_f = ["wait full", "select + epilogue", "-"]
 print(f"B={B} N={N} {dt}: {ms:.3f} ms, {B/ms/1e3:.2f} M halfspaces/s, {B*N*2*s.element_size()/ms/1e6:.0f} GB/s; {per:.1f} halfspaces per CTA")
 tot = c[:, 0, :].sum(axis=1).mean() / per
 print(f"sweep warp 1: {tot:.0f} cycles per halfspace per CTA")
-for k in range(9):
+for k in range(12):
     print(f"  {names_s[k]:32s} {c[:, 0, k].mean() / per:8.0f}")
 print("finisher warp:")
 for k in range(2):
