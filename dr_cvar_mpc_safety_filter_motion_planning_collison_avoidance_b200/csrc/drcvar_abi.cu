@@ -85,7 +85,7 @@ bool plan_window(long long n, long long kc, double* z_lo, double* z_hi) {
   const double z = inv_norm_cdf(1.0 - p);
   const double phi = std::exp(-0.5 * z * z) / std::sqrt(2.0 * M_PI);
   const double sq = std::sqrt(p * (1.0 - p) / static_cast<double>(n)) / phi;  // std of the sample quantile
-  const double w = 6.0 * sq + 0.03 + 0.02 * std::fabs(z);
+  const double w = 6.0 * sq + 0.012 + 0.012 * std::fabs(z);  // quantile noise + moment-estimate error (all samples)
   const double expect = static_cast<double>(n) * 2.0 * w * phi;
   if (expect > 0.6 * drcvar::kWarpCand * drcvar::kSweepWarps) return false;  // per-warp lists: ~6 sigma headroom
   *z_lo = z - w;

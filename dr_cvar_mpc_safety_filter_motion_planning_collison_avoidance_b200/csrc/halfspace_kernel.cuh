@@ -161,6 +161,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// helper warps (finisher, director): potentially-blocking wait with a suspend-time hint so that the idle warp does not
+// burn issue slots of the sweep team while it spins
+__device__ __forceinline__ void mbar_wait_idle(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+  }
+}
 // TMA bulk copy global -> shared::cta, completion counted in bytes on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -425,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       const double* fin = fin_base + par * kFinDoubles;
       const int* ired = ired_base + par * 2 * kSweepWarps;
       double* small = small_base + par * kResolveMax;
-      mbar_wait(&bars->full[par], use & 1);
+      mbar_wait_idle(&bars->full[par], use & 1);
       PH_MARK(0)
       if (ctl->mode == kModeFinish) {
         const int cnt_hi = ctl->cnt_hi;
@@ -548,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       const int par = iter & 1, use = iter >> 1;
       Ctl* ctl = ctl_base + par;
       const double* red = red_base + par * kRedDoubles;
-      mbar_wait(&bars->adone[par], use & 1);
+      mbar_wait_idle(&bars->adone[par], use & 1);
       double w[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -619,6 +633,13 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   const int rows_all = (N + kRowSamples - 1) / kRowSamples;
   unsigned short* wlist = list_base + warp * kWarpList;
   const double inv_n = 1.0 / static_cast<double>(N);
+  double inv_sub = inv_n;   // 1 / (#samples in the second moments): all samples (fp32) / every 4th row (fp64)
+  if (!kF32) {
+    const int r4 = (rows_all + 3) / 4;
+    const int last = (r4 - 1) * 4 * kRowSamples;
+    const int n_sub0 = (r4 - 1) * kSweepThreads + (N - last < kSweepThreads ? N - last : kSweepThreads);
+    inv_sub = 1.0 / static_cast<double>(n_sub0 > 0 ? n_sub0 : 1);
+  }
   PH_DECL
 
   for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
@@ -828,11 +849,10 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         const int r4 = (rows_all + 3) / 4;                       // rows 0, 4, 8, ...
         const int last = (r4 - 1) * 4 * kRowSamples;             // first sample of the last such row
         n_sub_i = (r4 - 1) * kSweepThreads + (N - last < kSweepThreads ? N - last : kSweepThreads);
-        ex = q[3] / n_sub_i;
-        ey = q[4] / n_sub_i;
+        ex = q[3] * inv_sub;
+        ey = q[4] * inv_sub;
       }
-      const double n_sub = static_cast<double>(n_sub_i > 0 ? n_sub_i : 1);
-      const double cxx = q[0] / n_sub - ex * ex, cyy = q[1] / n_sub - ey * ey, cxy = q[2] / n_sub - ex * ey;
+      const double cxx = q[0] * inv_sub - ex * ex, cyy = q[1] * inv_sub - ey * ey, cxy = q[2] * inv_sub - ex * ey;
       const double var_l = h0 * h0 * cxx + 2.0 * h0 * h1 * cxy + h1 * h1 * cyy;
       const double mu_l = -(h0 * m0 + h1 * m1);
       const double sigma = static_cast<double>(sqrtf(static_cast<float>(var_l)));
