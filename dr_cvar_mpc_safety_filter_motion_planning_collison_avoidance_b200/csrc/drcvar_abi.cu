@@ -139,7 +139,7 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   double k_f;
   long long kc;
   if (!tail_count(c.alpha, c.N, &k_f, &kc)) return fail(DRCVAR_ERR_INVALID, "alpha must be in (0,1] and N >= 1");
-  const size_t smem = slot_bytes_for(c.N, sizeof(T)) + fixed_smem_bytes();
+  const size_t smem = slot_bytes_for(c.N, sizeof(T)) + fixed_smem_bytes(sizeof(T));
   if (smem > static_cast<size_t>(di->max_smem_optin))
     return fail(DRCVAR_ERR_UNSUPPORTED, "N=%lld needs %zu B of shared memory per CTA (limit %d)", c.N, smem,
                 di->max_smem_optin);
@@ -440,7 +440,7 @@ int64_t drcvar_max_samples(int elem_bytes, int device) {
   DeviceInfo* di = nullptr;
   int rc = device_info(dev, &di);
   if (rc) return rc;
-  const size_t avail = static_cast<size_t>(di->max_smem_optin) - drcvar::fixed_smem_bytes();
+  const size_t avail = static_cast<size_t>(di->max_smem_optin) - drcvar::fixed_smem_bytes(static_cast<size_t>(elem_bytes));
   return static_cast<int64_t>((avail & ~static_cast<size_t>(127)) / (2 * static_cast<size_t>(elem_bytes)));
 }
 

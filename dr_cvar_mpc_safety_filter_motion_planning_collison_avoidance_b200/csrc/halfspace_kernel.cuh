@@ -51,7 +51,7 @@ constexpr int kFinisherWarp = kSweepWarps;
 constexpr int kDirectorWarp = kSweepWarps + 1;
 constexpr int kSlots = 512;                          // canonical cross-lane tree width (2 slots per sweep thread)
 constexpr int kWarpCand = 128;                       // candidate losses per sweep warp (window path)
-constexpr int kWarpList = 192;                       // masked sample indices per sweep warp
+constexpr int kWarpList = 160;                       // masked samples (raw copies) per sweep warp
 constexpr int kHistBuckets = 256;
 constexpr int kResolveMax = 32;                      // a bucket this small is ranked by one warp
 constexpr int kMaskWords = 4;                        // per-thread "needs exact loss" mask: 128 bits
@@ -106,6 +106,7 @@ struct Bars {
   unsigned long long empty[2];     // finisher -> sweep team
   unsigned long long adone[2];     // sweep team -> director: lane sums of sweep A are in red[par]
   unsigned long long hdone[2];     // director -> sweep team: canonical h / mean / flags are in ctl[par]
+  unsigned long long slotfree;     // 8 sweep warps -> director: nobody reads the sample slot any more
 };
 
 template <typename T> struct Vec2;
@@ -118,7 +119,7 @@ __host__ __device__ inline size_t slot_bytes_for(long long n, size_t elem_bytes)
 }
 constexpr int kRedDoubles = kSweepWarps * 8;                     // per warp: {tx, ty, qxx, qyy, qxy, bound, mdx, mdy}
 constexpr int kFinDoubles = kSweepWarps * 4;                     // per parity, per warp: {sum dx, sum dy, exact sum, n}
-__host__ __device__ inline size_t fixed_smem_bytes() {
+__host__ __device__ inline size_t fixed_smem_bytes(size_t elem_bytes) {
   return sizeof(double) * 2 * kWarpCand * kSweepWarps   // cand   [2][warps][kWarpCand]
          + sizeof(unsigned) * 2 * kHistBuckets          // hist   [2][256]
          + sizeof(double) * 2 * kRedDoubles             // red    [2]
@@ -126,7 +127,7 @@ __host__ __device__ inline size_t fixed_smem_bytes() {
          + sizeof(double) * 2 * kResolveMax             // small  [2]
          + sizeof(int) * 2 * 2 * kSweepWarps            // ired   [2][warps][2]
          + sizeof(int) * 4 * kSweepWarps                // iscr   (team scratch)
-         + sizeof(unsigned short) * kWarpList * kSweepWarps  // list
+         + 2 * elem_bytes * kWarpList * kSweepWarps     // raw copies of the masked samples [warps][kWarpList]
          + 2 * sizeof(Ctl) + sizeof(Bars);
 }
 
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   double* small_base = fin_base + 2 * kFinDoubles;
   int* ired_base = reinterpret_cast<int*>(small_base + 2 * kResolveMax);
   int* iscr = ired_base + 2 * 2 * kSweepWarps;
-  unsigned short* list_base = reinterpret_cast<unsigned short*>(iscr + 4 * kSweepWarps);
+  V2* list_base = reinterpret_cast<V2*>(iscr + 4 * kSweepWarps);
   Ctl* ctl_base = reinterpret_cast<Ctl*>(list_base + kWarpList * kSweepWarps);
   Bars* bars = reinterpret_cast<Bars*>(ctl_base + 2);
 
@@ -421,11 +422,23 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     mbar_init(&bars->adone[1], 1);
     mbar_init(&bars->hdone[0], 1);
     mbar_init(&bars->hdone[1], 1);
+    mbar_init(&bars->slotfree, kSweepWarps);
     mbar_fence_init();
   }
   for (int i = tid; i < 2 * kHistBuckets; i += kThreads) hist_base[i] = 0;
   if (tid < 2) ctl_base[tid].small_n = 0;
   __syncthreads();
+
+  const uint32_t copy_bytes = static_cast<uint32_t>(static_cast<size_t>(N) * sizeof(V2));
+  auto issue_bulk = [&](long long b) {
+    const unsigned char* src =
+        reinterpret_cast<const unsigned char*>(a.samples) + static_cast<size_t>(b) * a.stride_b * sizeof(T);
+    mbar_expect_tx(&bars->data, copy_bytes);
+    for (uint32_t off = 0; off < copy_bytes; off += kBulkChunk) {
+      const uint32_t n = copy_bytes - off < kBulkChunk ? copy_bytes - off : kBulkChunk;
+      bulk_g2s(smem_raw + off, src + off, n, &bars->data);
+    }
+  };
 
   // ============================================================================================ finisher warp
   if (warp == kFinisherWarp) {
@@ -607,31 +620,25 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         ctl->degenerate = degenerate;
       }
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&bars->hdone[par]);
-        write_mean_outputs(a, b, m0, m1);
+      if (lane == 0) mbar_arrive(&bars->hdone[par]);
+      if (a.bulk) {
+        // TMA producer: as soon as all 8 sweep warps are done with the sample slot, fetch the next halfspace
+        mbar_wait_idle(&bars->slotfree, iter & 1);
+        const long long b_next = b + gridDim.x;
+        if (lane == 0 && b_next < a.B) issue_bulk(b_next);
       }
+      if (lane == 0) write_mean_outputs(a, b, m0, m1);
     }
     return;
   }
 
   // ============================================================================================ sweep team
-  const uint32_t copy_bytes = static_cast<uint32_t>(static_cast<size_t>(N) * sizeof(V2));
-  auto issue_bulk = [&](long long b) {
-    const unsigned char* src =
-        reinterpret_cast<const unsigned char*>(a.samples) + static_cast<size_t>(b) * a.stride_b * sizeof(T);
-    mbar_expect_tx(&bars->data, copy_bytes);
-    for (uint32_t off = 0; off < copy_bytes; off += kBulkChunk) {
-      const uint32_t n = copy_bytes - off < kBulkChunk ? copy_bytes - off : kBulkChunk;
-      bulk_g2s(smem_raw + off, src + off, n, &bars->data);
-    }
-  };
   if (a.bulk && tid == 0 && static_cast<long long>(blockIdx.x) < a.B) issue_bulk(blockIdx.x);
   uint32_t phase = 0;
   int iter = 0;
   const int full_rows = N / kRowSamples;                 // rows of 16-byte loads fully inside the data
   const int rows_all = (N + kRowSamples - 1) / kRowSamples;
-  unsigned short* wlist = list_base + warp * kWarpList;
+  V2* wlist = list_base + warp * kWarpList;
   const double inv_n = 1.0 / static_cast<double>(N);
   double inv_sub = inv_n;   // 1 / (#samples in the second moments): all samples (fp32) / every 4th row (fp64)
   if (!kF32) {
@@ -651,7 +658,8 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     int* ired = ired_base + par * 2 * kSweepWarps;
     double* small = small_base + par * kResolveMax;
     double* red = red_base + par * kRedDoubles;
-    bool next_issued = false;
+    bool released = false;   // this warp has told the director that it no longer reads the sample slot
+    bool redo_bulk = false;
     const long long b_next = b + gridDim.x;
 
     // ------------------------------------------------------------------ stage
@@ -659,6 +667,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       mbar_wait(&bars->data, phase);
       phase ^= 1u;
     } else {
+      team_sync();   // every warp is done with the previous halfspace's samples
       const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
       for (int i = tid; i < N; i += kSweepThreads) {
         const T* p = base + static_cast<long long>(i) * a.stride_n;
@@ -1002,12 +1011,17 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
               mm ^= 1u << bp;
               const unsigned P = 32u * wd + bp;
               const unsigned i = kF32 ? ((P >> 1) * kRowSamples + 2u * tid + (P & 1u)) : (P * kRowSamples + tid);
-              wlist[pos++] = static_cast<unsigned short>(i);
+              wlist[pos++] = sm[i];
             }
           }
         }
       }
       __syncwarp();
+      if (!kTail) {
+        // the masked samples were copied out: the slot can be refilled while phase 2b and the select run
+        if (lane == 0) mbar_arrive(&bars->slotfree);
+        released = true;
+      }
       need_h();
       if (nonfinite) overflow = true;   // (cannot happen when the window was placed; keeps the flow uniform)
       // -------------------------------------------------------------- phase 2b: exact loss of the listed samples, dense
@@ -1021,7 +1035,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           double L = 0.0;
           V2 v = first;
           if (active) {
-            v = sm[wlist[k]];
+            v = wlist[k];
             L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
           }
           const bool up = active && (L > t_hi);
@@ -1078,13 +1092,11 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       fast = !ovf && cnt_hi < a.kc && a.kc <= cnt_hi + ncand;
       if (fast) {
         if (tid == 0) {
-          if (!kTail && a.bulk && b_next < a.B) issue_bulk(b_next);
           ctl->mode = kModeFinish;
           ctl->cnt_hi = cnt_hi;
           ctl->status = status;
           mbar_arrive(&bars->full[par]);   // hand halfspace b to the finisher warp
         }
-        next_issued = !kTail && a.bulk;
         if (kTail) {
           // parity mode: the sweep team needs T and the total count to emit the tail indices
           mbar_wait(&bars->empty[par], use & 1);
@@ -1097,6 +1109,31 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     int c_tot = 0;
     if (!fast) {
       need_h();
+      if (released && !nonfinite) {
+        // rare: the window was placed but missed, and the slot has already been handed back -> fetch halfspace b again
+        if (a.bulk) {
+          if (b_next < a.B) {   // the director's prefetch of b_next is landing in the slot: let it finish, then overwrite
+            mbar_wait(&bars->data, phase);
+            phase ^= 1u;
+          }
+          team_sync();
+          if (tid == 0) issue_bulk(b);
+          mbar_wait(&bars->data, phase);
+          phase ^= 1u;
+          redo_bulk = true;
+        } else {
+          team_sync();
+          const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
+          for (int i = tid; i < N; i += kSweepThreads) {
+            const T* p = base + static_cast<long long>(i) * a.stride_n;
+            V2 v;
+            v.x = p[0];
+            v.y = p[a.stride_c];
+            sm[i] = v;
+          }
+          team_sync();
+        }
+      }
       if (!nonfinite) {
         // -------------------------------------------------------------- general path: sweeps over all samples
         status |= kStatusGeneral;
@@ -1216,16 +1253,18 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     }
 
     PH_MARK(8)
-    // ------------------------------------------------------------------ release the slot / prefetch / keep the pipeline in step
-    if (!next_issued) {
+    // ------------------------------------------------------------------ release the slot / keep the pipeline in step
+    if (!fast) {
       team_sync();
       if (tid == 0) {
-        if (a.bulk && b_next < a.B) issue_bulk(b_next);
-        if (!fast) {
-          ctl->mode = kModeSkip;   // result already written by the team: the finisher only recycles the buffers
-          mbar_arrive(&bars->full[par]);
-        }
+        ctl->mode = kModeSkip;   // result already written by the team: the finisher only recycles the buffers
+        mbar_arrive(&bars->full[par]);
+        if (redo_bulk && b_next < a.B) issue_bulk(b_next);   // the re-fetch of b displaced the director's prefetch
       }
+    }
+    if (!released) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->slotfree);
     }
   }
 #ifdef DRCVAR_PROFILE_PHASES

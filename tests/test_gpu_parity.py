@@ -176,6 +176,18 @@ def test_window_miss_falls_back_exactly(eng):
     check_batch(res, s, ego, p)
     assert (res.status[3::4] & _lib.STATUS_GENERAL).all()
     assert np.array_equal(res.tail_idx[3], np.arange(600))
+    # the timed configuration (no tail output) hands the sample slot back early; a window miss must then re-fetch the
+    # halfspace (bulk and strided loaders) and still give the same answer, also in fp32 and with many halfspaces per CTA
+    for flags in (0, _lib.FLAG_NO_BULK):
+        r2 = eng.compute_halfspaces(s, ego, flags=flags, **p)
+        assert np.array_equal(r2.var, res.var) and rel_close(r2.g, res.g, 1e-12)
+    big = np.concatenate([s] * 60).astype(np.float32)          # 720 halfspaces > 2 per CTA of the persistent grid
+    ego_b = np.zeros((big.shape[0], 2))
+    r3 = eng.compute_halfspaces(big, ego_b, **p)
+    r4 = eng.compute_halfspaces(big, ego_b, flags=_lib.FLAG_GENERAL_ONLY, **p)
+    assert np.array_equal(r3.var, r4.var) and np.abs(r3.g - r4.g).max() < 1e-6
+    assert np.array_equal(r3.var[:12], r3.var[-12:])
+    assert (r3.status & _lib.STATUS_GENERAL).any()
 
 
 def test_degenerate_direction_and_nonfinite(eng):
