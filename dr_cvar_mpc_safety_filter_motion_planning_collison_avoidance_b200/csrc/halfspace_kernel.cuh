@@ -658,6 +658,16 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     int* ired = ired_base + par * 2 * kSweepWarps;
     double* small = small_base + par * kResolveMax;
     double* red = red_base + par * kRedDoubles;
+    double pre0 = 0.0, pre1 = 0.0;   // warp 0: ego (or the explicit normal) of halfspace b, fetched early
+    if (warp == 0) {
+      if (a.h_in != nullptr) {
+        pre0 = a.h_in[2 * b];
+        pre1 = a.h_in[2 * b + 1];
+      } else if (a.ego != nullptr) {
+        pre0 = a.ego[2 * b];
+        pre1 = a.ego[2 * b + 1];
+      }
+    }
     bool released = false;   // this warp has told the director that it no longer reads the sample slot
     bool redo_bulk = false;
     const long long b_next = b + gridDim.x;
@@ -826,10 +836,10 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       bool usable = isfinite(m0) && isfinite(m1);
       double h0, h1, rel = 0.0;
       if (a.h_in != nullptr) {
-        h0 = a.h_in[2 * b];
-        h1 = a.h_in[2 * b + 1];
+        h0 = pre0;
+        h1 = pre1;
       } else {
-        const double e0 = a.ego ? a.ego[2 * b] : 0.0, e1 = a.ego ? a.ego[2 * b + 1] : 0.0;
+        const double e0 = pre0, e1 = pre1;
         const double d0 = m0 - e0, d1 = m1 - e1;
         const double n2 = d0 * d0 + d1 * d1;
         if (n2 > 0.999e-20 && n2 < 1.001e-20) usable = false;   // too close to the degenerate-direction switch
