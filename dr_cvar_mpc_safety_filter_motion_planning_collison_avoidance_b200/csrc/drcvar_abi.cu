@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "halfspace_kernel.cuh"
+#include "streaming_kernel.cuh"
 
 namespace {
 
@@ -140,9 +141,8 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   long long kc;
   if (!tail_count(c.alpha, c.N, &k_f, &kc)) return fail(DRCVAR_ERR_INVALID, "alpha must be in (0,1] and N >= 1");
   const size_t smem = slot_bytes_for(c.N, sizeof(T)) + fixed_smem_bytes(sizeof(T));
-  if (smem > static_cast<size_t>(di->max_smem_optin))
-    return fail(DRCVAR_ERR_UNSUPPORTED, "N=%lld needs %zu B of shared memory per CTA (limit %d)", c.N, smem,
-                di->max_smem_optin);
+  // N beyond one CTA's shared memory (or on request): samples stay in global memory and are streamed several times
+  const bool streaming = (c.flags & DRCVAR_FLAG_FORCE_STREAMING) || smem > static_cast<size_t>(di->max_smem_optin);
   if (c.B == 0) return DRCVAR_OK;
 
   KernelArgs a{};
@@ -181,6 +181,16 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   a.phase_cycles = nullptr;
 #endif
   const bool tail = c.tail_idx_out != nullptr;
+  if (streaming) {
+    auto sk = tail ? streaming_kernel<T, true> : streaming_kernel<T, false>;
+    a.use_window = 0;
+    a.bulk = 0;
+    const long long sgrid = std::min<long long>(c.B, static_cast<long long>(di->sms) * 8);
+    sk<<<static_cast<unsigned>(sgrid), kStreamThreads, 0, stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return DRCVAR_OK;
+  }
   auto kern = tail ? halfspace_kernel<T, true> : halfspace_kernel<T, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;

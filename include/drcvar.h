@@ -45,7 +45,7 @@ extern "C" {
 #define DRCVAR_OK 0
 #define DRCVAR_ERR_INVALID (-1)     /* bad argument (alpha not in (0,1], N < 1, null pointer, bad stride) */
 #define DRCVAR_ERR_CUDA (-2)        /* a CUDA runtime call failed; see drcvar_last_error() */
-#define DRCVAR_ERR_UNSUPPORTED (-3) /* N too large for the on-chip kernels of this build */
+#define DRCVAR_ERR_UNSUPPORTED (-3) /* reserved (every N >= 1 is supported: large N uses the streaming kernel) */
 #define DRCVAR_ERR_NOMEM (-4)
 
 #define DRCVAR_HOST (-1)
@@ -54,7 +54,7 @@ extern "C" {
 #define DRCVAR_FLAG_SYNC 1u          /* device pointers: synchronise the stream before returning */
 #define DRCVAR_FLAG_GENERAL_ONLY 2u  /* disable the statistical candidate window (always use the general select) */
 #define DRCVAR_FLAG_NO_BULK 4u       /* disable cp.async.bulk staging (use the generic strided loader) */
-#define DRCVAR_FLAG_FORCE_CLUSTER 8u /* use the cluster/DSMEM kernel even when one CTA could hold N samples */
+#define DRCVAR_FLAG_FORCE_STREAMING 8u /* use the multi-pass streaming kernel even when one CTA could hold N samples */
 
 /* per-halfspace status bits written to status_out */
 #define DRCVAR_STATUS_NONFINITE 1   /* non-finite input: sentinel 100.0 emitted (core/risk_metrics.py:177,265,303,338) */
@@ -75,7 +75,8 @@ int drcvar_reduction_lanes(void);
  */
 int64_t drcvar_tail_count(double alpha, int64_t n_samples, double* k_f_out);
 
-/* Largest N the kernels of this build accept for a sample dtype of `elem_bytes` (4 or 8) on `device`. */
+/* Largest N the single-read shared-memory kernel holds for a sample dtype of `elem_bytes` (4 or 8) on `device`;
+ * larger N is served by the multi-pass streaming kernel (same results, several reads of the samples). */
 int64_t drcvar_max_samples(int elem_bytes, int device);
 
 /*

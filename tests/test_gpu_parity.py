@@ -230,10 +230,32 @@ def test_bad_arguments_raise(eng):
         eng.compute_halfspaces(s, None, **dict(PARAMS, alpha=0.0))
     with pytest.raises(_lib.DrcvarError):
         eng.compute_halfspaces(s, None, **dict(PARAMS, alpha=1.5))
-    big = np.zeros((1, eng.max_samples(np.float64) + 64, 2))
-    with pytest.raises(_lib.DrcvarError) as ei:
-        eng.compute_halfspaces(big, None, **PARAMS)
-    assert ei.value.code == _lib.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_large_n_streaming_kernel(eng, dtype):
+    """N beyond one CTA's shared memory (BASELINE config 5: N = 100 000) goes through the multi-pass streaming kernel."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    rng = np.random.RandomState(17)
+    p = dict(PARAMS, alpha=0.1, epsilon=0.01)
+    n = 100000
+    assert n > eng.max_samples(dtype)
+    s = (rng.uniform(-4, 4, size=(3, 1, 2)) + 0.1 * rng.standard_normal((3, n, 2))).astype(dtype)
+    ego = rng.uniform(-1, 1, size=(3, 2))
+    res = eng.compute_halfspaces(s, ego, want_tail=True, **p)
+    check_batch(res, s, ego, p)
+    assert res.tail_idx.shape == (3, 10000)
+    # forced on small N it must agree bit for bit with the shared-memory kernel's general path
+    for nn in (10000, 777, 20, 1):
+        ss = (rng.uniform(-4, 4, size=(16, 1, 2)) + 0.1 * rng.standard_normal((16, nn, 2))).astype(dtype)
+        ee = rng.uniform(-1, 1, size=(16, 2))
+        a = eng.compute_halfspaces(ss, ee, want_tail=True, flags=_lib.FLAG_FORCE_STREAMING, **p)
+        b = eng.compute_halfspaces(ss, ee, want_tail=True, flags=_lib.FLAG_GENERAL_ONLY, **p)
+        assert np.array_equal(a.tail_idx, b.tail_idx) and np.array_equal(a.var, b.var) and np.array_equal(a.h, b.h)
+        assert rel_close(a.g, b.g, 1e-12)
+        strided = np.repeat(ss[:, :, None, :], 3, axis=2)[:, :, 1, :]          # non-contiguous view
+        c = eng.compute_halfspaces(strided, ee, flags=_lib.FLAG_FORCE_STREAMING, **p)
+        assert np.array_equal(c.var, a.var)
 
 
 def test_run_to_run_determinism(eng):
