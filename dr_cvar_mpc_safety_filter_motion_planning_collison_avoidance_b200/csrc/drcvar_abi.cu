@@ -184,7 +184,8 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   if (streaming) {
     auto sk = tail ? streaming_kernel<T, true> : streaming_kernel<T, false>;
     a.use_window = 0;
-    a.bulk = 0;
+    a.bulk = contiguous && (reinterpret_cast<uintptr_t>(c.samples) % (2 * sizeof(T)) == 0) &&
+             ((static_cast<size_t>(c.stride_b) * sizeof(T)) % (2 * sizeof(T)) == 0 || c.B == 1);   // vector loads
     const long long sgrid = std::min<long long>(c.B, static_cast<long long>(di->sms) * 8);
     sk<<<static_cast<unsigned>(sgrid), kStreamThreads, 0, stream>>>(a);
     CUDA_TRY(cudaGetLastError());

@@ -33,7 +33,9 @@ __global__ void __launch_bounds__(kStreamThreads) streaming_kernel(const KernelA
 
   for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
     const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
+    const bool vec = a.bulk != 0;   // contiguous (x, y) pairs aligned to sizeof(V2): one vector load per sample
     auto load = [&](int i) {
+      if (vec) return reinterpret_cast<const V2*>(base)[i];
       const T* p = base + static_cast<long long>(i) * a.stride_n;
       V2 v;
       v.x = p[0];
