@@ -88,7 +88,7 @@ bool plan_window(long long n, long long kc, double* z_lo, double* z_hi) {
   const double sq = std::sqrt(p * (1.0 - p) / static_cast<double>(n)) / phi;  // std of the sample quantile
   const double w = 6.0 * sq + 0.012 + 0.012 * std::fabs(z);  // quantile noise + moment-estimate error (all samples)
   const double expect = static_cast<double>(n) * 2.0 * w * phi;
-  if (expect > 0.6 * drcvar::kWarpCand * drcvar::kSweepWarps) return false;  // per-warp lists: ~6 sigma headroom
+  if (expect > 0.6 * drcvar::kCandCap * drcvar::kSweepWarps) return false;  // per-warp lists: ~6 sigma headroom
   *z_lo = z - w;
   *z_hi = z + w;
   return true;

@@ -50,7 +50,8 @@ constexpr int kThreads = kSweepThreads + 64;         // + finisher warp + direct
 constexpr int kFinisherWarp = kSweepWarps;
 constexpr int kDirectorWarp = kSweepWarps + 1;
 constexpr int kSlots = 512;                          // canonical cross-lane tree width (2 slots per sweep thread)
-constexpr int kWarpCand = 128;                       // candidate losses per sweep warp (window path)
+constexpr int kWarpCand = 128;                       // doubles per sweep warp in the candidate buffer ...
+constexpr int kCandCap = 96;                         // ... of which candidate losses; the last 32 hold per-lane (sum dx, sum dy)
 constexpr int kWarpList = 160;                       // masked samples (raw copies) per sweep warp
 constexpr int kHistBuckets = 256;
 constexpr int kResolveMax = 32;                      // a bucket this small is ranked by one warp
@@ -158,12 +159,13 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_spin(unsigned long long* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
 // helper warps (finisher, director): potentially-blocking wait with a suspend-time hint so that the idle warp does not
 // burn issue slots of the sweep team while it spins
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity);
 __device__ __forceinline__ void mbar_wait_idle(unsigned long long* bar, uint32_t parity) {
   uint32_t ok = 0;
   while (!ok) {
@@ -176,6 +178,7 @@ __device__ __forceinline__ void mbar_wait_idle(unsigned long long* bar, uint32_t
         : "memory");
   }
 }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) { mbar_wait_idle(bar, parity); }
 // TMA bulk copy global -> shared::cta, completion counted in bytes on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -532,12 +535,20 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         }
         const int c3t = __reduce_add_sync(kFull, c3);
         const double s3t = warp_sum_any(s3);
-        if (lane == 0) {
-          double s_x = 0.0, s_y = 0.0, s_e = 0.0, n_lin = 0.0;
+        double lx = 0.0, ly = 0.0;   // "surely above" coordinate sums: lane partials of the 8 sweep warps, fixed order
+        if constexpr (kF32) {
 #pragma unroll
           for (int w = 0; w < kSweepWarps; ++w) {
-            s_x += fin[w * 4 + 0];
-            s_y += fin[w * 4 + 1];
+            const float2 p = reinterpret_cast<const float2*>(cand + w * kWarpCand + kCandCap)[lane];
+            lx += static_cast<double>(p.x);
+            ly += static_cast<double>(p.y);
+          }
+        }
+        const double s_x = warp_sum_any(lx), s_y = warp_sum_any(ly);
+        if (lane == 0) {
+          double s_e = 0.0, n_lin = 0.0;
+#pragma unroll
+          for (int w = 0; w < kSweepWarps; ++w) {
             s_e += fin[w * 4 + 2];
             n_lin += fin[w * 4 + 3];
           }
@@ -1060,34 +1071,30 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           const unsigned bal = __ballot_sync(kFull, cd);
           if (bal) {
             const int pos = nc + __popc(bal & ((1u << lane) - 1u));
-            if (cd && pos < kWarpCand) {
+            if (cd && pos < kCandCap) {
               wcand[pos] = L;
               atomicAdd(&hist[static_cast<unsigned>((key_of(L) - klo) >> hshift)], 1u);
             }
             nc += __popc(bal);
           }
         }
-        overflow = nc > kWarpCand;
+        overflow = nc > kCandCap;
       }
       PH_MARK(5)
-      // per-warp partials
+      // per-warp partials (fp32 inputs: the per-lane coordinate sums go to the finisher as they are)
       {
         const int wc = __reduce_add_sync(kFull, c_gt + static_cast<int>(cf));
-        double px = 0.0, py = 0.0, pe = 0.0, pn = 0.0;
+        double pe = 0.0;
         if constexpr (kF32) {
-          px = static_cast<double>(warp_sum_any(ax));
-          py = static_cast<double>(warp_sum_any(ay));
-          pn = static_cast<double>(wc);
+          reinterpret_cast<float2*>(wcand + kCandCap)[lane] = make_float2(ax, ay);
         } else {
           pe = warp_sum_any(s_gt);
         }
         if (lane == 0) {
           ired[warp * 2] = wc;
-          ired[warp * 2 + 1] = nc < kWarpCand ? nc : kWarpCand;
-          fin[warp * 4 + 0] = px;
-          fin[warp * 4 + 1] = py;
+          ired[warp * 2 + 1] = nc < kCandCap ? nc : kCandCap;
           fin[warp * 4 + 2] = pe;
-          fin[warp * 4 + 3] = pn;
+          fin[warp * 4 + 3] = kF32 ? static_cast<double>(wc) : 0.0;
         }
       }
       PH_MARK(6)
