@@ -735,20 +735,15 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         body(va, 0);
         body(vb, 1);
       }
-      // remaining rows (at most 3: an odd full row and the ragged rows), element-wise with bounds checks
+      // remaining rows (an odd full row and/or the ragged last row): same vector path; samples beyond N are replaced
+      // by the first sample, whose shifted value is +0 and adds nothing (the slot is followed by other shared arrays,
+      // so the 16-byte load itself stays inside the CTA's allocation)
       for (; r < rows_all; ++r) {
-        const int q = r & 1;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int i = r * kRowSamples + 2 * tid + e;
-          if (i < N) {
-            const float2 v = sm[i];
-            const float2 d = __fadd2_rn(v, nf);
-            if (q == 0) acc[0][e] = __fadd2_rn(acc[0][e], d); else acc[1][e] = __fadd2_rn(acc[1][e], d);
-            sq = __ffma2_rn(d, d, sq);
-            sxy = fmaf(d.x, d.y, sxy);
-          }
-        }
+        float4 v = sm4[r * kSweepThreads + tid];
+        const int i0 = r * kRowSamples + 2 * tid;
+        if (i0 >= N) { v.x = first.x; v.y = first.y; }
+        if (i0 + 1 >= N) { v.z = first.x; v.w = first.y; }
+        if (r & 1) body(v, 1); else body(v, 0);
       }
       // adjacent fp32 lanes (2 slot, 2 slot + 1) widened and added in fp64, then slot tid + slot tid+256
       const double s0x = __dadd_rn(static_cast<double>(acc[0][0].x), static_cast<double>(acc[0][1].x));
@@ -969,21 +964,21 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
             bit <<= 2;
           }
         }
-        for (int r = full_rows; r < rows_all; ++r) {  // ragged rows, element-wise
+        if (full_rows < rows_all) {  // ragged last row: same vector path, samples beyond N can neither be "above" nor kept
+          const int r = full_rows;
+          const float4 v = sm4[r * kSweepThreads + tid];
+          const int i0 = r * kRowSamples + 2 * tid;
+          const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nf), d1 = __fadd2_rn(make_float2(v.z, v.w), nf);
+          float p0 = fmaf(h1f, d0.y, h0f * d0.x), p1 = fmaf(h1f, d1.y, h0f * d1.x);
+          if (i0 >= N) p0 = __int_as_float(0x7f800000);
+          if (i0 + 1 >= N) p1 = __int_as_float(0x7f800000);
+          const unsigned bit0 = 1u << ((2 * r) & 31);
+          unsigned mk = 0;
+          classify_f32(p0, thr_above, thr_keep, d0.x, d0.y, ax, ay, cf, mk, bit0);
+          classify_f32(p1, thr_above, thr_keep, d1.x, d1.y, ax, ay, cf, mk, bit0 + bit0);
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int i = r * kRowSamples + 2 * tid + e;
-            if (i < N) {
-              const float2 v = sm[i];
-              const float2 d = __fadd2_rn(v, nf);
-              const int P = 2 * r + e;
-              unsigned mk = 0;
-              classify_f32(fmaf(h1f, d.y, h0f * d.x), thr_above, thr_keep, d.x, d.y, ax, ay, cf, mk, 1u << (P & 31));
-#pragma unroll
-              for (int w2 = 0; w2 < kMaskWords; ++w2)
-                if (w2 == (P >> 5)) mask[w2] |= mk;
-            }
-          }
+          for (int w2 = 0; w2 < kMaskWords; ++w2)
+            if (w2 == ((2 * r) >> 5)) mask[w2] |= mk;
         }
       } else {
 #pragma unroll
