@@ -797,10 +797,14 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       }
       if (lane == 0) {
         double* w = red + warp * 8;
-        w[0] = tx; w[1] = ty; w[2] = mxx; w[3] = myy; w[4] = mxy;
-        w[5] = static_cast<double>(__uint_as_float(bnd));
-        w[6] = kF32 ? static_cast<double>(first.x) : static_cast<double>(mdx);   // fp32: shift origin for the director
-        w[7] = kF32 ? static_cast<double>(first.y) : static_cast<double>(mdy);
+        float* wf = reinterpret_cast<float*>(w);
+        w[0] = tx; w[1] = ty;
+        wf[4] = mxx; wf[5] = myy; wf[6] = mxy; wf[7] = __uint_as_float(bnd);
+        wf[8] = mdx; wf[9] = mdy;
+        if (kF32) {   // shift origin for the director
+          w[6] = static_cast<double>(first.x);
+          w[7] = static_cast<double>(first.y);
+        }
       }
     }
     PH_MARK(1)
@@ -810,6 +814,9 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     // ------------------------------------------------------------------ window placement (warp 0); canonical h: director warp
     if (tid == 0) mbar_arrive(&bars->adone[par]);   // red[par] is complete (S1): the director starts the canonical chain
     if (warp == 0) {
+      // Everything here only PLACES the window (speed, never the result) except the fp32 thresholds, which carry
+      // rigorous error bounds against the canonical direction the director is computing meanwhile.  The direction used
+      // for the classification is h_a = (h0f, h1f), an fp32 approximation: |h_a - h| <= err_h per component.
       double w[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -822,87 +829,99 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           for (int g = 0; g < n / 2; ++g) t[g] = t[2 * g] + t[2 * g + 1];
         w[j] = t[0];
       }
+      const float* redf = reinterpret_cast<const float*>(red);   // warp g: floats 4..9 of its 16 = qxx,qyy,qxy,bound,mdx,mdy
+      float q[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      float b2 = 0.f;
+#pragma unroll
+      for (int g = 0; g < kSweepWarps; ++g) {
+        q[0] += redf[g * 16 + 4];
+        q[1] += redf[g * 16 + 5];
+        q[2] += redf[g * 16 + 6];
+        b2 = fmaxf(b2, redf[g * 16 + 7]);
+        if (!kF32) {
+          q[3] += redf[g * 16 + 8];
+          q[4] += redf[g * 16 + 9];
+        }
+      }
       const double f0 = static_cast<double>(first.x), f1 = static_cast<double>(first.y);
-      // fp64-accurate but NOT canonical mean / direction (reciprocal multiply, rsqrt + Newton): |h_a - h| <= rel below
-      double m0 = w[0] * inv_n, m1 = w[1] * inv_n;
+      double m0 = w[0] * inv_n, m1 = w[1] * inv_n;   // fp32 inputs: mean relative to the first sample
+      double mr0 = m0, mr1 = m1;
       if (kF32) {
         m0 += f0;
         m1 += f1;
-      }
-      double q[5];
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        q[j] = 0.0;
-#pragma unroll
-        for (int g = 0; g < kSweepWarps; ++g) q[j] += red[g * 8 + (j < 3 ? 2 + j : 3 + j)];  // qxx,qyy,qxy,mdx,mdy
-      }
-      float b2 = 0.f;
-#pragma unroll
-      for (int g = 0; g < kSweepWarps; ++g) b2 = fmaxf(b2, static_cast<float>(red[g * 8 + 5]));
-      bool usable = isfinite(m0) && isfinite(m1);
-      double h0, h1, rel = 0.0;
-      if (a.h_in != nullptr) {
-        h0 = pre0;
-        h1 = pre1;
       } else {
-        const double e0 = pre0, e1 = pre1;
-        const double d0 = m0 - e0, d1 = m1 - e1;
-        const double n2 = d0 * d0 + d1 * d1;
-        if (n2 > 0.999e-20 && n2 < 1.001e-20) usable = false;   // too close to the degenerate-direction switch
-        if (n2 < 1e-20) {
-          h0 = 1.0;
-          h1 = 0.0;
+        mr0 = m0 - f0;
+        mr1 = m1 - f1;
+      }
+      const float mr0f = static_cast<float>(mr0), mr1f = static_cast<float>(mr1);
+      bool usable = isfinite(m0) && isfinite(m1);
+      float h0f, h1f, err_h;
+      if (a.h_in != nullptr) {
+        h0f = static_cast<float>(pre0);
+        h1f = static_cast<float>(pre1);
+        err_h = fmaxf(fabsf(h0f), fabsf(h1f)) * 1.2e-7f + 1.5e-45f;
+      } else {
+        const double d0 = m0 - pre0, d1 = m1 - pre1;   // pre = ego
+        const float d0f = static_cast<float>(d0), d1f = static_cast<float>(d1);
+        const float n2 = fmaf(d0f, d0f, d1f * d1f);
+        if (n2 > 0.99e-20f && n2 < 1.01e-20f) usable = false;   // too close to the degenerate-direction switch
+        if (n2 < 1e-20f) {
+          h0f = 1.0f;
+          h1f = 0.0f;
+          err_h = 0.f;
         } else {
-          double rn = static_cast<double>(rsqrtf(static_cast<float>(n2)));
-          rn = rn * (1.5 - 0.5 * n2 * rn * rn);
-          rn = rn * (1.5 - 0.5 * n2 * rn * rn);
-          h0 = d0 * rn;
-          h1 = d1 * rn;
-          rel = 4e-15 * (1.0 + (fabs(m0) + fabs(m1) + fabs(e0) + fabs(e1)) * rn);
-          usable = usable && isfinite(rn) && rn > 0.0;
+          const float rn = rsqrtf(n2);
+          h0f = d0f * rn;
+          h1f = d1f * rn;
+          // fp32 chain: 2 conversions, fma, rsqrt (2 ulp), multiply  ->  < 5e-7; plus the fp64 cancellation in m - ego
+          const float mag = static_cast<float>(fabs(m0) + fabs(m1) + fabs(pre0) + fabs(pre1));
+          err_h = 1e-6f + 4e-15f * mag * rn;
+          usable = usable && isfinite(rn) && rn > 0.f && isfinite(mag);
         }
       }
-      usable = usable && isfinite(h0) && isfinite(h1) && rel < 1e-7;
-      // heuristic window around the expected kc-th largest loss (affects speed only, never the result)
+      usable = usable && isfinite(h0f) && isfinite(h1f) && err_h < 1e-3f;
+      // heuristic window around the expected kc-th largest loss
       int n_sub_i;
-      double ex, ey;
+      float ex, ey;
+      const float inv_sub_f = static_cast<float>(inv_sub);
       if (kF32) {
         n_sub_i = N;
-        ex = m0 - f0;
-        ey = m1 - f1;
+        ex = mr0f;
+        ey = mr1f;
       } else {
         const int r4 = (rows_all + 3) / 4;                       // rows 0, 4, 8, ...
         const int last = (r4 - 1) * 4 * kRowSamples;             // first sample of the last such row
         n_sub_i = (r4 - 1) * kSweepThreads + (N - last < kSweepThreads ? N - last : kSweepThreads);
-        ex = q[3] * inv_sub;
-        ey = q[4] * inv_sub;
+        ex = q[3] * inv_sub_f;
+        ey = q[4] * inv_sub_f;
       }
-      const double cxx = q[0] * inv_sub - ex * ex, cyy = q[1] * inv_sub - ey * ey, cxy = q[2] * inv_sub - ex * ey;
-      const double var_l = h0 * h0 * cxx + 2.0 * h0 * h1 * cxy + h1 * h1 * cyy;
-      const double mu_l = -(h0 * m0 + h1 * m1);
-      const double sigma = static_cast<double>(sqrtf(static_cast<float>(var_l)));
-      int window_ok = a.use_window && usable && (n_sub_i >= 256) && (var_l > 0.0) && isfinite(sigma) &&
+      const float cxx = q[0] * inv_sub_f - ex * ex, cyy = q[1] * inv_sub_f - ey * ey, cxy = q[2] * inv_sub_f - ex * ey;
+      const float var_l = h0f * h0f * cxx + 2.0f * h0f * h1f * cxy + h1f * h1f * cyy;
+      const float sigma = sqrtf(var_l);
+      int window_ok = a.use_window && usable && (n_sub_i >= 256) && (var_l > 0.f) && isfinite(sigma) &&
                       (rows_all * kPerLoad <= 32 * kMaskWords);
-      const double t_lo = __dadd_rn(mu_l + a.z_lo * sigma, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
-      const double t_hi = __dadd_rn(mu_l + a.z_hi * sigma, 0.0);
+      // thresholds in shifted coordinates, p = h_a.(xi - first):  a_lo <-> t_lo,  a_hi <-> t_hi  (a_hi <= a_lo)
+      const float pm = fmaf(h1f, mr1f, h0f * mr0f);
+      const float a_lo = pm - static_cast<float>(a.z_lo) * sigma, a_hi = pm - static_cast<float>(a.z_hi) * sigma;
+      const double c = static_cast<double>(h0f) * f0 + static_cast<double>(h1f) * f1;   // h_a . first
+      const double t_lo = __dadd_rn(-static_cast<double>(a_lo) - c, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
+      const double t_hi = __dadd_rn(-static_cast<double>(a_hi) - c, 0.0);
       // fp32 classification of p32 = fma(h1f, dy, h0f*dx), d = fl32(xi - first)  (p = h.xi = h.first + h.d = -L):
-      //   |p32 - h_a.d| <= 5 * 2^-24 * (|h0| + |h1|) * max|d|; we allow 2^-19 (32x) plus the rounding of the thresholds,
-      //   plus |h_a - h| (|first| + max|d|) for the canonical h the director is computing meanwhile.
+      //   |p32 - h_a.d_true| <= 5 * 2^-24 * (|h0f| + |h1f|) * max|d|; we allow 2^-19 (32x);
+      //   |h.xi - (c + h_a.d_true)| <= err_h (|first| + max|d|) (1-norms); the fp64 roundings of c, t and L are ~1e-16 relative.
       //   p32 <  thr_above  =>  L > t_hi  for sure;    p32 > thr_keep  =>  L < t_lo  for sure.
-      const float h0f = static_cast<float>(h0), h1f = static_cast<float>(h1);
       const float dmax = sqrtf(b2) * 1.0001f;
-      const double c = h0 * f0 + h1 * f1;
-      const double a_lo = -t_lo - c, a_hi = -t_hi - c;
-      const double eps64 = (fabs(h0 * f0) + fabs(h1 * f1) + (fabs(h0) + fabs(h1)) * static_cast<double>(dmax)) * 1e-15 +
-                           rel * 1.5 * (fabs(f0) + fabs(f1) + 2.0 * static_cast<double>(dmax));
-      const float bound = (fabsf(h0f) + fabsf(h1f)) * dmax * 1.9073486e-06f + 1.1754944e-38f +
-                          static_cast<float>(eps64) * 1.0001f;
-      const float thr_keep = static_cast<float>(a_lo) + (bound + fabsf(static_cast<float>(a_lo)) * 2.3841858e-07f);
-      const float thr_above = static_cast<float>(a_hi) - (bound + fabsf(static_cast<float>(a_hi)) * 2.3841858e-07f);
+      const float af0 = fabsf(static_cast<float>(f0)) * 1.0001f, af1 = fabsf(static_cast<float>(f1)) * 1.0001f;
+      const float habs = fabsf(h0f) + fabsf(h1f);
+      const float eps = (habs * (af0 + af1 + dmax)) * 1e-15f + err_h * 1.5f * (af0 + af1 + 2.0f * dmax);
+      const float bound = habs * dmax * 1.9073486e-06f + 1.1754944e-38f + eps * 1.0001f;
+      const float thr_keep = a_lo + (bound + fabsf(a_lo) * 2.3841858e-07f);
+      const float thr_above = a_hi - (bound + fabsf(a_hi) * 2.3841858e-07f);
       const unsigned long long klo = key_of(t_lo), khi = key_of(t_hi);
       const unsigned long long span = khi - klo;
       const int bits = span ? 64 - __clzll(static_cast<long long>(span)) : 0;
-      window_ok = window_ok && isfinite(thr_keep) && isfinite(thr_above) && (khi >= klo) && (thr_above <= thr_keep);
+      window_ok = window_ok && isfinite(thr_keep) && isfinite(thr_above) && (khi >= klo) && (thr_above <= thr_keep) &&
+                  isfinite(t_lo) && isfinite(t_hi);
       if (lane == 0) {
         ctl->f0 = f0; ctl->f1 = f1;
         ctl->t_lo = t_lo;
