@@ -249,6 +249,27 @@ __device__ __forceinline__ double warp_sum_canon(double v) {  // xor 1,2,4,8,16 
   return v;
 }
 
+// Two canonical warp sums for the price of one: the first butterfly stage swaps x against y between lane pairs, so that
+// even lanes go on with the x tree and odd lanes with the y tree.  Every addition has the same operands as in
+// warp_sum_canon (fp addition commutes), hence the same bits.  Result: sum of x in even lanes, sum of y in odd lanes.
+__device__ __forceinline__ double warp_sum_canon_pair(double x, double y, int lane) {
+  const bool odd = lane & 1;
+  double v = __dadd_rn(odd ? y : x, shfl_xor_d(odd ? x : y, 1));
+#pragma unroll
+  for (int m = 2; m <= 16; m <<= 1) v = __dadd_rn(v, shfl_xor_d(v, m));
+  return v;
+}
+// Four (non-canonical) float warp sums in 6 shuffles: totals of a, c, b, d end up in lanes with (lane & 3) = 0, 1, 2, 3.
+__device__ __forceinline__ float warp_sum_any4(float a, float b, float c, float d, int lane) {
+  const bool b0 = lane & 1, b1 = lane & 2;
+  const float k0 = (b0 ? c : a) + __shfl_xor_sync(kFull, b0 ? a : c, 1);
+  const float k1 = (b0 ? d : b) + __shfl_xor_sync(kFull, b0 ? b : d, 1);
+  float v = (b1 ? k1 : k0) + __shfl_xor_sync(kFull, b1 ? k0 : k1, 2);
+#pragma unroll
+  for (int m = 4; m <= 16; m <<= 1) v += __shfl_xor_sync(kFull, v, m);
+  return v;
+}
+
 // Histogram scan by ONE warp: finds the bucket (from the top) that holds rank r (1-based).
 __device__ __forceinline__ void scan_hist_warp(const unsigned* hist, int r, int lane, int& bstar, int& rprime, int& cnt_in) {
   int run = 0, row = -1, r_row = 0;
@@ -784,22 +805,22 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       u_y = __dadd_rn(s01, s11);
     }
     {
-      // canonical: xor-butterfly inside each group of 32; the 8 group totals are tree-added by warps 0 and 1
-      const double tx = warp_sum_canon(u_x);
-      const double ty = warp_sum_canon(u_y);
-      const float mxx = warp_sum_any(static_cast<float>(q_xx)), myy = warp_sum_any(static_cast<float>(q_yy));
-      const float mxy = warp_sum_any(static_cast<float>(q_xy));
+      // canonical: xor-butterfly inside each group of 32 (x in even lanes, y in odd lanes); the 8 group totals are
+      // tree-added by the director (canonical) and by warp 0 (window placement)
+      const double txy = warp_sum_canon_pair(u_x, u_y, lane);
+      const float mq = warp_sum_any4(static_cast<float>(q_xx), static_cast<float>(q_yy), static_cast<float>(q_xy), 0.f, lane);
       const unsigned bnd = __reduce_max_sync(kFull, __float_as_uint(bound2));
       float mdx = 0.f, mdy = 0.f;
       if constexpr (!kF32) {
         mdx = warp_sum_any(static_cast<float>(q_dx));
         mdy = warp_sum_any(static_cast<float>(q_dy));
       }
+      double* w = red + warp * 8;
+      float* wf = reinterpret_cast<float*>(w);
+      if (lane < 2) w[lane] = txy;                                   // lane 0: x total, lane 1: y total
+      if (lane < 3) wf[4 + ((lane & 1) << 1) + (lane >> 1)] = mq;    // lane 0: qxx -> [4], lane 1: qxy -> [6], lane 2: qyy -> [5]
       if (lane == 0) {
-        double* w = red + warp * 8;
-        float* wf = reinterpret_cast<float*>(w);
-        w[0] = tx; w[1] = ty;
-        wf[4] = mxx; wf[5] = myy; wf[6] = mxy; wf[7] = __uint_as_float(bnd);
+        wf[7] = __uint_as_float(bnd);
         wf[8] = mdx; wf[9] = mdy;
         if (kF32) {   // shift origin for the director
           w[6] = static_cast<double>(first.x);
