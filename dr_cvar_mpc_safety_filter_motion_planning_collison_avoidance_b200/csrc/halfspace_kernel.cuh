@@ -58,6 +58,7 @@ constexpr int kResolveMax = 32;                      // a bucket this small is r
 constexpr int kMaskWords = 4;                        // per-thread "needs exact loss" mask: 128 bits
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kBulkChunk = 32768;
+constexpr int kRowsPerChunk = kBulkChunk / (16 * 256);   // a row = one 16-byte load per sweep thread = 4 KB
 
 constexpr int kStatusNonfinite = 1;
 constexpr int kStatusGeneral = 2;
@@ -102,7 +103,8 @@ struct Ctl {                        // one per parity buffer
 };
 
 struct Bars {
-  unsigned long long data;         // bulk copy landed
+  unsigned long long data;         // bulk copy landed (all chunks after the first)
+  unsigned long long data0;        // first 32 KB chunk landed: sweep A starts on it while the rest is in flight
   unsigned long long full[2];      // sweep team -> finisher
   unsigned long long empty[2];     // finisher -> sweep team
   unsigned long long adone[2];     // sweep team -> director: lane sums of sweep A are in red[par]
@@ -438,6 +440,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
 
   if (tid == 0) {
     mbar_init(&bars->data, 1);
+    mbar_init(&bars->data0, 1);
     mbar_init(&bars->full[0], 1);
     mbar_init(&bars->full[1], 1);
     mbar_init(&bars->empty[0], 1);
@@ -457,10 +460,15 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   auto issue_bulk = [&](long long b) {
     const unsigned char* src =
         reinterpret_cast<const unsigned char*>(a.samples) + static_cast<size_t>(b) * a.stride_b * sizeof(T);
-    mbar_expect_tx(&bars->data, copy_bytes);
-    for (uint32_t off = 0; off < copy_bytes; off += kBulkChunk) {
-      const uint32_t n = copy_bytes - off < kBulkChunk ? copy_bytes - off : kBulkChunk;
-      bulk_g2s(smem_raw + off, src + off, n, &bars->data);
+    const uint32_t n0 = copy_bytes < kBulkChunk ? copy_bytes : kBulkChunk;
+    mbar_expect_tx(&bars->data0, n0);
+    bulk_g2s(smem_raw, src, n0, &bars->data0);
+    if (copy_bytes > n0) {
+      mbar_expect_tx(&bars->data, copy_bytes - n0);
+      for (uint32_t off = n0; off < copy_bytes; off += kBulkChunk) {
+        const uint32_t n = copy_bytes - off < kBulkChunk ? copy_bytes - off : kBulkChunk;
+        bulk_g2s(smem_raw + off, src + off, n, &bars->data);
+      }
     }
   };
 
@@ -706,8 +714,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
 
     // ------------------------------------------------------------------ stage
     if (a.bulk) {
-      mbar_wait(&bars->data, phase);
-      phase ^= 1u;
+      mbar_wait(&bars->data0, phase);   // the first chunk; the rest is awaited inside sweep A
     } else {
       team_sync();   // every warp is done with the previous halfspace's samples
       const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
@@ -727,6 +734,14 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     // ------------------------------------------------------------------ sweep A: canonical lane sums + second moments
     // Row r = the 16-byte vector r*256 + tid.  fp32: samples 2(r*256+tid)+{0,1} = lanes 2 slot + {0,1} of tile r/2,
     // slot = (r&1)*256 + tid.  fp64: sample r*256 + tid = slot (r&1)*256 + tid of tile r/2.
+    bool rest_pending = a.bulk != 0;
+    auto wait_rest = [&]() {   // chunks 1.. of halfspace b (a no-op when the whole copy fits the first chunk)
+      if (rest_pending) {
+        if (copy_bytes > kBulkChunk) mbar_wait(&bars->data, phase);
+        phase ^= 1u;
+        rest_pending = false;
+      }
+    };
     const V2 first = sm[0];
     double u_x, u_y;                 // this thread's value in the 256-wide tree: slot tid + slot tid+256
     double q_xx, q_yy, q_xy;         // second moments of (xi - first): all samples (fp32) / every 4th row (fp64)
@@ -750,6 +765,15 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         sxy = fmaf(d1.x, d1.y, sxy);
       };
       int r = 0;
+      if (full_rows >= kRowsPerChunk) {   // the first chunk while the others land
+#pragma unroll
+        for (; r < kRowsPerChunk; r += 2) {
+          const float4 va = sm4[r * kSweepThreads + tid], vb = sm4[(r + 1) * kSweepThreads + tid];
+          body(va, 0);
+          body(vb, 1);
+        }
+      }
+      wait_rest();
 #pragma unroll 2
       for (; r + 1 < full_rows; r += 2) {
         const float4 va = sm4[r * kSweepThreads + tid], vb = sm4[(r + 1) * kSweepThreads + tid];
@@ -781,6 +805,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
       q_xx = q_yy = q_xy = 0.0;
       for (int r = 0; r < rows_all; ++r) {
+        if (r == kRowsPerChunk) wait_rest();
         const int i = r * kRowSamples + tid;
         if (i < N) {
           const V2 v = sm[i];
@@ -804,6 +829,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       u_x = __dadd_rn(s00, s10);
       u_y = __dadd_rn(s01, s11);
     }
+    wait_rest();
     {
       // canonical: xor-butterfly inside each group of 32 (x in even lanes, y in odd lanes); the 8 group totals are
       // tree-added by the director (canonical) and by warp 0 (window placement)
@@ -1165,12 +1191,14 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         // rare: the window was placed but missed, and the slot has already been handed back -> fetch halfspace b again
         if (a.bulk) {
           if (b_next < a.B) {   // the director's prefetch of b_next is landing in the slot: let it finish, then overwrite
-            mbar_wait(&bars->data, phase);
+            mbar_wait(&bars->data0, phase);
+            if (copy_bytes > kBulkChunk) mbar_wait(&bars->data, phase);
             phase ^= 1u;
           }
           team_sync();
           if (tid == 0) issue_bulk(b);
-          mbar_wait(&bars->data, phase);
+          mbar_wait(&bars->data0, phase);
+          if (copy_bytes > kBulkChunk) mbar_wait(&bars->data, phase);
           phase ^= 1u;
           redo_bulk = true;
         } else {
