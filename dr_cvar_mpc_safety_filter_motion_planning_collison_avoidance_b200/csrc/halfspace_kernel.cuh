@@ -105,11 +105,8 @@ struct Ctl {                        // one per parity buffer
 struct Bars {
   unsigned long long data;         // bulk copy landed (all chunks after the first)
   unsigned long long data0;        // first 32 KB chunk landed: sweep A starts on it while the rest is in flight
-  unsigned long long full[2];      // sweep team -> finisher
   unsigned long long empty[2];     // finisher -> sweep team
-  unsigned long long adone[2];     // sweep team -> director: lane sums of sweep A are in red[par]
   unsigned long long hdone[2];     // director -> sweep team: canonical h / mean / flags are in ctl[par]
-  unsigned long long slotfree;     // 8 sweep warps -> director: nobody reads the sample slot any more
 };
 
 template <typename T> struct Vec2;
@@ -188,6 +185,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// Named barriers 2..7 (one per parity): handshakes towards the two helper warps.  The producer side arrives without
+// waiting (bar.arrive), the helper blocks in hardware (bar.sync) instead of polling an mbarrier.  A barrier id is
+// re-armed two halfspaces later, after the waits on empty[] / hdone[] have proved that the helper consumed it.
+constexpr int kBarFull = 2;       // warp 0 of the team (32) + finisher (32)
+constexpr int kBarADone = 4;      // warp 0 of the team (32) + director (32)
+constexpr int kBarSlotFree = 6;   // the 8 sweep warps (256) + director (32)
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 // barrier 1: the sweep team only (the finisher warp never joins it)
 __device__ __forceinline__ void team_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kSweepThreads) : "memory"); }
 __device__ __forceinline__ int team_sync_or(int pred) {
@@ -441,15 +446,10 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   if (tid == 0) {
     mbar_init(&bars->data, 1);
     mbar_init(&bars->data0, 1);
-    mbar_init(&bars->full[0], 1);
-    mbar_init(&bars->full[1], 1);
     mbar_init(&bars->empty[0], 1);
     mbar_init(&bars->empty[1], 1);
-    mbar_init(&bars->adone[0], 1);
-    mbar_init(&bars->adone[1], 1);
     mbar_init(&bars->hdone[0], 1);
     mbar_init(&bars->hdone[1], 1);
-    mbar_init(&bars->slotfree, kSweepWarps);
     mbar_fence_init();
   }
   for (int i = tid; i < 2 * kHistBuckets; i += kThreads) hist_base[i] = 0;
@@ -477,14 +477,14 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     int iter = 0;
     PH_DECL
     for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
-      const int par = iter & 1, use = iter >> 1;
+      const int par = iter & 1;
       Ctl* ctl = ctl_base + par;
       unsigned* hist = hist_base + par * kHistBuckets;
       const double* cand = cand_base + par * kWarpCand * kSweepWarps;
       const double* fin = fin_base + par * kFinDoubles;
       const int* ired = ired_base + par * 2 * kSweepWarps;
       double* small = small_base + par * kResolveMax;
-      mbar_wait_idle(&bars->full[par], use & 1);
+      bar_sync(kBarFull + par, 64);   // warp 0 of the team hands halfspace b over
       PH_MARK(0)
       if (ctl->mode == kModeFinish) {
         const int cnt_hi = ctl->cnt_hi;
@@ -612,10 +612,10 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   if (warp == kDirectorWarp) {
     int iter = 0;
     for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
-      const int par = iter & 1, use = iter >> 1;
+      const int par = iter & 1;
       Ctl* ctl = ctl_base + par;
       const double* red = red_base + par * kRedDoubles;
-      mbar_wait_idle(&bars->adone[par], use & 1);
+      bar_sync(kBarADone + par, 64);   // red[par] is complete
       double w[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -661,9 +661,9 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->hdone[par]);
+      // TMA producer: as soon as all 8 sweep warps are done with the sample slot, fetch the next halfspace
+      bar_sync(kBarSlotFree + par, kSweepThreads + 32);
       if (a.bulk) {
-        // TMA producer: as soon as all 8 sweep warps are done with the sample slot, fetch the next halfspace
-        mbar_wait_idle(&bars->slotfree, iter & 1);
         const long long b_next = b + gridDim.x;
         if (lane == 0 && b_next < a.B) issue_bulk(b_next);
       }
@@ -859,7 +859,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     PH_MARK(2)
 
     // ------------------------------------------------------------------ window placement (warp 0); canonical h: director warp
-    if (tid == 0) mbar_arrive(&bars->adone[par]);   // red[par] is complete (S1): the director starts the canonical chain
+    if (warp == 0) bar_arrive(kBarADone + par, 64);   // red[par] is complete (S1): the director starts the canonical chain
     if (warp == 0) {
       // Everything here only PLACES the window (speed, never the result) except the fp32 thresholds, which carry
       // rigorous error bounds against the canonical direction the director is computing meanwhile.  The direction used
@@ -1101,7 +1101,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       __syncwarp();
       if (!kTail) {
         // the masked samples were copied out: the slot can be refilled while phase 2b and the select run
-        if (lane == 0) mbar_arrive(&bars->slotfree);
+        bar_arrive(kBarSlotFree + par, kSweepThreads + 32);
         released = true;
       }
       need_h();
@@ -1169,11 +1169,14 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       }
       fast = !ovf && cnt_hi < a.kc && a.kc <= cnt_hi + ncand;
       if (fast) {
-        if (tid == 0) {
-          ctl->mode = kModeFinish;
-          ctl->cnt_hi = cnt_hi;
-          ctl->status = status;
-          mbar_arrive(&bars->full[par]);   // hand halfspace b to the finisher warp
+        if (warp == 0) {
+          if (lane == 0) {
+            ctl->mode = kModeFinish;
+            ctl->cnt_hi = cnt_hi;
+            ctl->status = status;
+          }
+          __syncwarp();
+          bar_arrive(kBarFull + par, 64);   // hand halfspace b to the finisher warp
         }
         if (kTail) {
           // parity mode: the sweep team needs T and the total count to emit the tail indices
@@ -1336,15 +1339,18 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     // ------------------------------------------------------------------ release the slot / keep the pipeline in step
     if (!fast) {
       team_sync();
-      if (tid == 0) {
-        ctl->mode = kModeSkip;   // result already written by the team: the finisher only recycles the buffers
-        mbar_arrive(&bars->full[par]);
-        if (redo_bulk && b_next < a.B) issue_bulk(b_next);   // the re-fetch of b displaced the director's prefetch
+      if (warp == 0) {
+        if (lane == 0) {
+          ctl->mode = kModeSkip;   // result already written by the team: the finisher only recycles the buffers
+          if (redo_bulk && b_next < a.B) issue_bulk(b_next);   // the re-fetch of b displaced the director's prefetch
+        }
+        __syncwarp();
+        bar_arrive(kBarFull + par, 64);
       }
     }
     if (!released) {
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->slotfree);
+      bar_arrive(kBarSlotFree + par, kSweepThreads + 32);
     }
   }
 #ifdef DRCVAR_PROFILE_PHASES
