@@ -86,7 +86,13 @@ bool plan_window(long long n, long long kc, double* z_lo, double* z_hi) {
   const double z = inv_norm_cdf(1.0 - p);
   const double phi = std::exp(-0.5 * z * z) / std::sqrt(2.0 * M_PI);
   const double sq = std::sqrt(p * (1.0 - p) / static_cast<double>(n)) / phi;  // std of the sample quantile
-  const double w = 6.0 * sq + 0.012 + 0.012 * std::fabs(z);  // quantile noise + moment-estimate error (all samples)
+  // (actual - predicted) quantile in z units, predicted = mean^ + z sigma^ from the sample moments.  For Gaussian losses
+  // the sample mean and sigma are independent of the studentised quantile (Basu), so their variances SUBTRACT from the
+  // quantile noise: var = p(1-p)/(n phi^2) - 1/n - z^2/(2n).  5 sigma + slack for non-normality; floor at half the
+  // quantile noise.  (A miss only costs a re-fetch + the general select, never the result.)
+  const double nn = static_cast<double>(n);
+  const double var = std::max(sq * sq - 1.0 / nn - 0.5 * z * z / nn, 0.25 * sq * sq);
+  const double w = 4.0 * std::sqrt(var) + 0.002;
   const double expect = static_cast<double>(n) * 2.0 * w * phi;
   if (expect > 0.6 * drcvar::kCandCap * drcvar::kSweepWarps) return false;  // per-warp lists: ~6 sigma headroom
   *z_lo = z - w;
@@ -161,6 +167,8 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   a.kc = static_cast<int>(kc);
   a.use_window = 0;
   if (!(c.flags & DRCVAR_FLAG_GENERAL_ONLY)) a.use_window = plan_window(c.N, kc, &a.z_lo, &a.z_hi) ? 1 : 0;
+  a.z_lo_f = static_cast<float>(a.z_lo);
+  a.z_hi_f = static_cast<float>(a.z_hi);
   const size_t row_bytes = static_cast<size_t>(c.N) * 2 * sizeof(T);
   const bool contiguous = (c.stride_c == 1 && c.stride_n == 2);
   a.bulk = contiguous && !(c.flags & DRCVAR_FLAG_NO_BULK) && (reinterpret_cast<uintptr_t>(c.samples) % 16 == 0) &&

@@ -78,6 +78,7 @@ struct KernelArgs {
   int kc;
   int use_window;
   double z_lo, z_hi;
+  float z_lo_f, z_hi_f;   // the same, rounded once on the host
   int bulk;
   double* h_out;
   double* h_mean_out;
@@ -238,6 +239,11 @@ __device__ __forceinline__ double loss_of(double h0, double h1, double x, double
 }
 __device__ __forceinline__ double norm2_canon(double a, double b) {
   return __dsqrt_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+}
+__device__ __forceinline__ float sqrt_approx(float x) {   // one MUFU.SQRT (<= 2 ulp), no fix-up / slow path
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(kFull, v, m); }
 __device__ __forceinline__ double warp_sum_any(double v) {
@@ -687,6 +693,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     const int n_sub0 = (r4 - 1) * kSweepThreads + (N - last < kSweepThreads ? N - last : kSweepThreads);
     inv_sub = 1.0 / static_cast<double>(n_sub0 > 0 ? n_sub0 : 1);
   }
+  const float inv_sub_f = static_cast<float>(inv_sub);
   PH_DECL
 
   for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
@@ -930,7 +937,6 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       // heuristic window around the expected kc-th largest loss
       int n_sub_i;
       float ex, ey;
-      const float inv_sub_f = static_cast<float>(inv_sub);
       if (kF32) {
         n_sub_i = N;
         ex = mr0f;
@@ -944,12 +950,12 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       }
       const float cxx = q[0] * inv_sub_f - ex * ex, cyy = q[1] * inv_sub_f - ey * ey, cxy = q[2] * inv_sub_f - ex * ey;
       const float var_l = h0f * h0f * cxx + 2.0f * h0f * h1f * cxy + h1f * h1f * cyy;
-      const float sigma = sqrtf(var_l);
+      const float sigma = sqrt_approx(var_l);   // placement only
       int window_ok = a.use_window && usable && (n_sub_i >= 256) && (var_l > 0.f) && isfinite(sigma) &&
                       (rows_all * kPerLoad <= 32 * kMaskWords);
       // thresholds in shifted coordinates, p = h_a.(xi - first):  a_lo <-> t_lo,  a_hi <-> t_hi  (a_hi <= a_lo)
       const float pm = fmaf(h1f, mr1f, h0f * mr0f);
-      const float a_lo = pm - static_cast<float>(a.z_lo) * sigma, a_hi = pm - static_cast<float>(a.z_hi) * sigma;
+      const float a_lo = pm - a.z_lo_f * sigma, a_hi = pm - a.z_hi_f * sigma;
       const double c = static_cast<double>(h0f) * f0 + static_cast<double>(h1f) * f1;   // h_a . first
       const double t_lo = __dadd_rn(-static_cast<double>(a_lo) - c, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
       const double t_hi = __dadd_rn(-static_cast<double>(a_hi) - c, 0.0);
@@ -957,7 +963,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       //   |p32 - h_a.d_true| <= 5 * 2^-24 * (|h0f| + |h1f|) * max|d|; we allow 2^-19 (32x);
       //   |h.xi - (c + h_a.d_true)| <= err_h (|first| + max|d|) (1-norms); the fp64 roundings of c, t and L are ~1e-16 relative.
       //   p32 <  thr_above  =>  L > t_hi  for sure;    p32 > thr_keep  =>  L < t_lo  for sure.
-      const float dmax = sqrtf(b2) * 1.0001f;
+      const float dmax = sqrt_approx(b2) * 1.0001f;   // 2 ulp, inside the 1e-4 margin
       const float af0 = fabsf(static_cast<float>(f0)) * 1.0001f, af1 = fabsf(static_cast<float>(f1)) * 1.0001f;
       const float habs = fabsf(h0f) + fabsf(h1f);
       const float eps = (habs * (af0 + af1 + dmax)) * 1e-15f + err_h * 1.5f * (af0 + af1 + 2.0f * dmax);
