@@ -100,7 +100,9 @@ struct Ctl {                        // one per parity buffer
   int hist_shift;
   int bstar, rprime, cnt_in, small_n;
   int window_ok, nonfinite, degenerate, c_tot;
-  int mode, cnt_hi, status, pad;
+  int mode, cnt_hi, status;
+  int acc_hi, acc_nc;              // team totals (shared atomics): sure-above count, window candidates
+  int pad;
 };
 
 struct Bars {
@@ -983,6 +985,8 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         ctl->key_lo = klo;
         ctl->hist_shift = bits > 8 ? bits - 8 : 0;
         ctl->window_ok = window_ok;
+        ctl->acc_hi = 0;
+        ctl->acc_nc = 0;
       }
     }
     team_sync();  // S2
@@ -1158,8 +1162,10 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           pe = warp_sum_any(s_gt);
         }
         if (lane == 0) {
-          ired[warp * 2] = wc;
-          ired[warp * 2 + 1] = nc < kCandCap ? nc : kCandCap;
+          const int ncc = nc < kCandCap ? nc : kCandCap;
+          ired[warp * 2 + 1] = ncc;
+          atomicAdd(&ctl->acc_hi, wc);
+          atomicAdd(&ctl->acc_nc, ncc);
           fin[warp * 4 + 2] = pe;
           fin[warp * 4 + 3] = kF32 ? static_cast<double>(wc) : 0.0;
         }
@@ -1167,12 +1173,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       PH_MARK(6)
       const int ovf = team_sync_or(overflow);  // S3: the sample slot is no longer read on the fast path
       PH_MARK(7)
-      int cnt_hi = 0, ncand = 0;
-#pragma unroll
-      for (int w = 0; w < kSweepWarps; ++w) {
-        cnt_hi += ired[w * 2];
-        ncand += ired[w * 2 + 1];
-      }
+      const int cnt_hi = ctl->acc_hi, ncand = ctl->acc_nc;
       fast = !ovf && cnt_hi < a.kc && a.kc <= cnt_hi + ncand;
       if (fast) {
         if (warp == 0) {
