@@ -80,7 +80,7 @@ double inv_norm_cdf(double p) {
 
 // Candidate window [z_lo, z_hi] (in loss-sigma units around the loss mean) expected to bracket the kc-th
 // largest loss.  Purely a speed heuristic: a miss is detected on the device and the general select runs.
-bool plan_window(long long n, long long kc, double* z_lo, double* z_hi) {
+bool plan_window(long long n, long long kc, long long n_sigma, double* z_lo, double* z_hi) {
   const double p = static_cast<double>(kc) / static_cast<double>(n);  // upper-tail fraction
   if (n < 1024 || kc < 16 || n - kc < 16 || p < 1e-3 || p > 0.999) return false;
   const double z = inv_norm_cdf(1.0 - p);
@@ -91,7 +91,9 @@ bool plan_window(long long n, long long kc, double* z_lo, double* z_hi) {
   // quantile noise: var = p(1-p)/(n phi^2) - 1/n - z^2/(2n).  5 sigma + slack for non-normality; floor at half the
   // quantile noise.  (A miss only costs a re-fetch + the general select, never the result.)
   const double nn = static_cast<double>(n);
-  const double var = std::max(sq * sq - 1.0 / nn - 0.5 * z * z / nn, 0.25 * sq * sq);
+  // sigma^ taken from a subsample of n_sigma <= n samples (fp64 inputs: every 4th row) adds z^2 (1/(2 n_sigma) - 1/(2n))
+  const double extra = 0.5 * z * z * (1.0 / static_cast<double>(n_sigma) - 1.0 / nn);
+  const double var = std::max(sq * sq - 1.0 / nn - 0.5 * z * z / nn, 0.25 * sq * sq) + std::max(extra, 0.0);
   const double w = 4.0 * std::sqrt(var) + 0.002;
   const double expect = static_cast<double>(n) * 2.0 * w * phi;
   if (expect > 0.6 * drcvar::kCandCap * drcvar::kSweepWarps) return false;  // per-warp lists: ~6 sigma headroom
@@ -166,7 +168,12 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   a.k_f = k_f;
   a.kc = static_cast<int>(kc);
   a.use_window = 0;
-  if (!(c.flags & DRCVAR_FLAG_GENERAL_ONLY)) a.use_window = plan_window(c.N, kc, &a.z_lo, &a.z_hi) ? 1 : 0;
+  long long n_sigma = c.N;   // samples behind the kernel's second moments: all (fp32) / rows 0, 4, 8, ... of 256 (fp64)
+  if (sizeof(T) == 8) {
+    const long long rows = (c.N + 255) / 256, r4 = (rows + 3) / 4, last = (r4 - 1) * 4 * 256;
+    n_sigma = (r4 - 1) * 256 + std::min<long long>(256, c.N - last);
+  }
+  if (!(c.flags & DRCVAR_FLAG_GENERAL_ONLY)) a.use_window = plan_window(c.N, kc, n_sigma, &a.z_lo, &a.z_hi) ? 1 : 0;
   a.z_lo_f = static_cast<float>(a.z_lo);
   a.z_hi_f = static_cast<float>(a.z_hi);
   const size_t row_bytes = static_cast<size_t>(c.N) * 2 * sizeof(T);

@@ -813,28 +813,33 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     } else {
       double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
       q_xx = q_yy = q_xy = 0.0;
-      for (int r = 0; r < rows_all; ++r) {
-        if (r == kRowsPerChunk) wait_rest();
-        const int i = r * kRowSamples + tid;
-        if (i < N) {
-          const V2 v = sm[i];
-          if ((r & 1) == 0) {
-            s00 = __dadd_rn(s00, v.x);
-            s01 = __dadd_rn(s01, v.y);
-          } else {
-            s10 = __dadd_rn(s10, v.x);
-            s11 = __dadd_rn(s11, v.y);
-          }
-          if ((r & 3) == 0) {
-            const double dx = v.x - first.x, dy = v.y - first.y;
-            q_dx += dx;
-            q_dy += dy;
-            q_xx = fma(dx, dx, q_xx);
-            q_yy = fma(dy, dy, q_yy);
-            q_xy = fma(dx, dy, q_xy);
+      auto rows = [&](int r_lo, int r_hi) {
+        for (int r = r_lo; r < r_hi; ++r) {
+          const int i = r * kRowSamples + tid;
+          if (i < N) {
+            const V2 v = sm[i];
+            if ((r & 1) == 0) {
+              s00 = __dadd_rn(s00, v.x);
+              s01 = __dadd_rn(s01, v.y);
+            } else {
+              s10 = __dadd_rn(s10, v.x);
+              s11 = __dadd_rn(s11, v.y);
+            }
+            if ((r & 3) == 0) {
+              const double dx = v.x - first.x, dy = v.y - first.y;
+              q_dx += dx;
+              q_dy += dy;
+              q_xx = fma(dx, dx, q_xx);
+              q_yy = fma(dy, dy, q_yy);
+              q_xy = fma(dx, dy, q_xy);
+            }
           }
         }
-      }
+      };
+      const int r_first = rows_all < kRowsPerChunk ? rows_all : kRowsPerChunk;
+      rows(0, r_first);        // the first chunk while the others land
+      wait_rest();
+      rows(r_first, rows_all);
       u_x = __dadd_rn(s00, s10);
       u_y = __dadd_rn(s01, s11);
     }
