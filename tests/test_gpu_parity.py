@@ -190,6 +190,57 @@ def test_window_miss_falls_back_exactly(eng):
     assert (r3.status & _lib.STATUS_GENERAL).any()
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_adversarial_scales_and_offsets(eng, dtype):
+    """Stress the rigorous fp32 screening bounds: large coordinate offsets, tiny / large spreads, ego next to the mean
+    (cancellation in m - ego), explicit non-unit normals, extreme alpha.  Threshold and tail sets must stay exact."""
+    rng = np.random.RandomState(23)
+    n = 10000
+    cases = []
+    for offset in (0.0, 50.0, 1.0e3, 1.0e5):
+        for sigma in (1.0e-3, 0.1, 5.0):
+            for near in (False, True):
+                cases.append((offset, sigma, near))
+    B = len(cases)
+    s = np.empty((B, n, 2))
+    ego = np.empty((B, 2))
+    for b, (offset, sigma, near) in enumerate(cases):
+        ang = rng.uniform(0, 2 * np.pi)
+        mu = offset * np.array([np.cos(ang), np.sin(ang)]) + rng.uniform(-1, 1, size=2)
+        s[b] = mu + sigma * rng.standard_normal((n, 2)) * np.array([1.0, rng.uniform(0.2, 3.0)])
+        ego[b] = mu + (2.0 * sigma * rng.standard_normal(2) if near else -mu)   # next to the mean / at the origin
+    s = s.astype(dtype)
+    for alpha in (0.1, 0.002, 0.9):
+        p = dict(PARAMS, alpha=alpha, epsilon=0.01)
+        res = eng.compute_halfspaces(s, ego, want_tail=True, **p)
+        fast = eng.compute_halfspaces(s, ego, **p)                  # the timed configuration (early slot release)
+        assert np.array_equal(fast.var, res.var) and np.array_equal(fast.h, res.h)
+        if alpha == 0.1:
+            assert fast.status[cases.index((0.0, 0.1, False))] == 0     # the window path is the one under test
+            print('window-path halfspaces:', int((fast.status == 0).sum()), 'of', B)
+        for b, (offset, sigma, near) in enumerate(cases):
+            o = cf.halfspace(s[b], ego[b], p["alpha"], p["delta"], p["epsilon"], p["robot_radius"], p["obstacle_radius"])
+            assert np.array_equal(res.h[b], o.h) and np.array_equal(res.h_mean[b], o.h_mean), (cases[b], alpha)
+            assert res.var[b] == o.var, (cases[b], alpha, res.var[b], o.var)
+            assert np.array_equal(res.tail_idx[b], o.tail_idx), (cases[b], alpha)
+            if dtype == np.float32:
+                tol = 1e-6 * max(1.0, sigma)
+                assert abs(res.cvar[b] - o.cvar) <= tol and abs(fast.cvar[b] - o.cvar) <= tol, (cases[b], alpha, res.cvar[b], o.cvar)
+            else:
+                assert rel_close(res.cvar[b], o.cvar) and rel_close(fast.cvar[b], o.cvar), (cases[b], alpha)
+    # explicit normals that are far from unit length, and normals with one tiny component
+    for h in ((1.0e-3, 2.0e-3), (3.0e3, -1.0e3), (1.0, 1.0e-12), (0.0, -2.5)):
+        p = dict(PARAMS, alpha=0.1, epsilon=0.01)
+        res = eng.compute_halfspaces(s, None, want_tail=True, h=h, **p)
+        for b in range(0, B, 3):
+            o = cf.halfspace(s[b], np.zeros(2), p["alpha"], p["delta"], p["epsilon"], p["robot_radius"],
+                             p["obstacle_radius"], np.array(h))
+            assert res.var[b] == o.var and np.array_equal(res.tail_idx[b], o.tail_idx), (h, cases[b])
+            scale = max(abs(h[0]), abs(h[1])) * max(1.0, cases[b][1])
+            tol = (1e-6 * max(1.0, scale)) if dtype == np.float32 else 1e-9 * max(1.0, abs(o.cvar))
+            assert abs(res.cvar[b] - o.cvar) <= tol, (h, cases[b], res.cvar[b], o.cvar)
+
+
 def test_degenerate_direction_and_nonfinite(eng):
     from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
     s = np.tile(np.array([[4.0, 0.0]]), (3, 20, 1))
