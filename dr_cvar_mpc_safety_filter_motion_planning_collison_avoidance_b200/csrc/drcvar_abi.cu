@@ -246,6 +246,8 @@ struct HostCtx {
   size_t h_pack_cap[2] = {0, 0};
   unsigned char* d_io[2] = {nullptr, nullptr};  // ego/h_in + outputs
   size_t d_io_cap[2] = {0, 0};
+  void* h_out_stage[2] = {nullptr, nullptr};    // pinned: the whole output block of a chunk comes back in ONE copy
+  size_t h_out_cap[2] = {0, 0};
   double last_stage_ms = 0, last_kernel_ms = 0;
   long long last_h2d = 0, last_d2h = 0;
 };
@@ -260,6 +262,8 @@ int ensure_host_ctx(HostCtx& hc) {
       if (hc.d_samples[i]) cudaFree(hc.d_samples[i]);
       if (hc.d_io[i]) cudaFree(hc.d_io[i]);
       if (hc.h_pack[i]) cudaFreeHost(hc.h_pack[i]);
+      if (hc.h_out_stage[i]) cudaFreeHost(hc.h_out_stage[i]);
+      hc.h_out_stage[i] = nullptr; hc.h_out_cap[i] = 0;
       hc.d_samples[i] = nullptr; hc.d_samples_cap[i] = 0;
       hc.d_io[i] = nullptr; hc.d_io_cap[i] = 0;
       hc.h_pack[i] = nullptr; hc.h_pack_cap[i] = 0;
@@ -319,13 +323,40 @@ int run_host(const Call& c) {
   chunk_b = std::min(chunk_b, c.B);
   const long long n_chunks = (c.B + chunk_b - 1) / chunk_b;
 
+  struct Pending {
+    bool live;
+    long long b0, nb;
+    size_t off_h, off_hm, off_g, off_cvar, off_var, off_gs, off_st, off_tail;
+  } pending[2] = {};
+  auto drain = [&](int s) {   // scatter the staged output block of slot s into the caller's arrays
+    Pending& q = pending[s];
+    if (!q.live) return;
+    const unsigned char* base = static_cast<const unsigned char*>(hc.h_out_stage[s]) - q.off_h;
+    const size_t dbl = sizeof(double);
+    auto put = [&](void* host, size_t off, size_t bytes) {
+      if (host) std::memcpy(host, base + off, bytes);
+    };
+    put(c.h_out + 2 * q.b0, q.off_h, q.nb * 2 * dbl);
+    put(c.h_mean_out ? c.h_mean_out + 2 * q.b0 : nullptr, q.off_hm, q.nb * 2 * dbl);
+    put(c.g_out + 3 * q.b0, q.off_g, q.nb * 3 * dbl);
+    put(c.cvar_out ? c.cvar_out + q.b0 : nullptr, q.off_cvar, q.nb * dbl);
+    put(c.var_out ? c.var_out + q.b0 : nullptr, q.off_var, q.nb * dbl);
+    put(c.gstar_out ? c.gstar_out + q.b0 : nullptr, q.off_gs, q.nb * dbl);
+    put(c.status_out ? c.status_out + q.b0 : nullptr, q.off_st, q.nb * sizeof(int32_t));
+    put(c.tail_idx_out ? c.tail_idx_out + q.b0 * kc : nullptr, q.off_tail, static_cast<size_t>(q.nb) * kc * sizeof(int32_t));
+    q.live = false;
+  };
+
   CUDA_TRY(cudaEventRecord(hc.ev_start, hc.streams[0]));
   for (long long ci = 0; ci < n_chunks; ++ci) {
     const int s = static_cast<int>(ci & 1);
     cudaStream_t st = hc.streams[s];
     const long long b0 = ci * chunk_b, nb = std::min(chunk_b, c.B - b0);
-    // buffers of this slot are reused: wait for the chunk that used them two iterations ago
-    if (ci >= 2) CUDA_TRY(cudaStreamSynchronize(st));
+    // buffers of this slot are reused: wait for the chunk that used them two iterations ago and hand its results over
+    if (ci >= 2) {
+      CUDA_TRY(cudaStreamSynchronize(st));
+      drain(s);
+    }
     rc = grow_dev(&hc.d_samples[s], &hc.d_samples_cap[s], static_cast<size_t>(nb) * row_pitch);
     if (rc) return rc;
     // io block layout: ego[nb,2] h_in[nb,2] | h[nb,2] hm[nb,2] g[nb,3] cvar[nb] var[nb] gstar[nb] status[nb] tail[nb,kc]
@@ -387,23 +418,19 @@ int run_host(const Call& c) {
     rc = launch_on_device<T>(d, hc.device, st);
     if (rc) return rc;
 
-    // ---- results D2H
-    auto back = [&](void* host, size_t off, size_t bytes) -> cudaError_t {
-      if (!host) return cudaSuccess;
-      hc.last_d2h += static_cast<long long>(bytes);
-      return cudaMemcpyAsync(host, io + off, bytes, cudaMemcpyDeviceToHost, st);
-    };
-    CUDA_TRY(back(c.h_out + 2 * b0, off_h, nb * 2 * dbl));
-    CUDA_TRY(back(c.h_mean_out ? c.h_mean_out + 2 * b0 : nullptr, off_hm, nb * 2 * dbl));
-    CUDA_TRY(back(c.g_out + 3 * b0, off_g, nb * 3 * dbl));
-    CUDA_TRY(back(c.cvar_out ? c.cvar_out + b0 : nullptr, off_cvar, nb * dbl));
-    CUDA_TRY(back(c.var_out ? c.var_out + b0 : nullptr, off_var, nb * dbl));
-    CUDA_TRY(back(c.gstar_out ? c.gstar_out + b0 : nullptr, off_gs, nb * dbl));
-    CUDA_TRY(back(c.status_out ? c.status_out + b0 : nullptr, off_st, nb * sizeof(int32_t)));
-    CUDA_TRY(back(c.tail_idx_out ? c.tail_idx_out + b0 * kc : nullptr, off_tail, static_cast<size_t>(nb) * kc * sizeof(int32_t)));
+    // ---- results D2H: one copy of the contiguous output block into pinned memory, scattered to the caller's arrays
+    //      once the chunk's stream has been synchronised (drain)
+    const size_t out_bytes = io_bytes - off_h;
+    rc = grow_pinned(&hc.h_out_stage[s], &hc.h_out_cap[s], out_bytes);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(hc.h_out_stage[s], io + off_h, out_bytes, cudaMemcpyDeviceToHost, st));
+    hc.last_d2h += static_cast<long long>(out_bytes);
+    pending[s] = {true, b0, nb, off_h, off_hm, off_g, off_cvar, off_var, off_gs, off_st, off_tail};
   }
   CUDA_TRY(cudaStreamSynchronize(hc.streams[0]));
   CUDA_TRY(cudaStreamSynchronize(hc.streams[1]));
+  drain(0);
+  drain(1);
   CUDA_TRY(cudaEventRecord(hc.ev_stop, hc.streams[0]));
   CUDA_TRY(cudaEventSynchronize(hc.ev_stop));
   float ms = 0.f;
