@@ -80,7 +80,7 @@ double inv_norm_cdf(double p) {
 
 // Candidate window [z_lo, z_hi] (in loss-sigma units around the loss mean) expected to bracket the kc-th
 // largest loss.  Purely a speed heuristic: a miss is detected on the device and the general select runs.
-bool plan_window(long long n, long long kc, long long n_sigma, double* z_lo, double* z_hi) {
+bool plan_window(long long n, long long kc, long long n_sigma, double cand_capacity, double* z_lo, double* z_hi) {
   const double p = static_cast<double>(kc) / static_cast<double>(n);  // upper-tail fraction
   if (n < 1024 || kc < 16 || n - kc < 16 || p < 1e-3 || p > 0.999) return false;
   const double z = inv_norm_cdf(1.0 - p);
@@ -96,7 +96,7 @@ bool plan_window(long long n, long long kc, long long n_sigma, double* z_lo, dou
   const double var = std::max(sq * sq - 1.0 / nn - 0.5 * z * z / nn, 0.25 * sq * sq) + std::max(extra, 0.0);
   const double w = 4.0 * std::sqrt(var) + 0.002;
   const double expect = static_cast<double>(n) * 2.0 * w * phi;
-  if (expect > 0.6 * drcvar::kCandCap * drcvar::kSweepWarps) return false;  // per-warp lists: ~6 sigma headroom
+  if (expect > cand_capacity) return false;  // per-warp candidate lists: leave headroom for the spread between warps
   *z_lo = z - w;
   *z_hi = z + w;
   return true;
@@ -173,7 +173,9 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
     const long long rows = (c.N + 255) / 256, r4 = (rows + 3) / 4, last = (r4 - 1) * 4 * 256;
     n_sigma = (r4 - 1) * 256 + std::min<long long>(256, c.N - last);
   }
-  if (!(c.flags & DRCVAR_FLAG_GENERAL_ONLY)) a.use_window = plan_window(c.N, kc, n_sigma, &a.z_lo, &a.z_hi) ? 1 : 0;
+  const double cand_capacity = streaming ? 0.5 * kStreamCand * kStreamWarps : 0.6 * kCandCap * kSweepWarps;
+  if (!(c.flags & DRCVAR_FLAG_GENERAL_ONLY))
+    a.use_window = plan_window(c.N, kc, n_sigma, cand_capacity, &a.z_lo, &a.z_hi) ? 1 : 0;
   a.z_lo_f = static_cast<float>(a.z_lo);
   a.z_hi_f = static_cast<float>(a.z_hi);
   const size_t row_bytes = static_cast<size_t>(c.N) * 2 * sizeof(T);
@@ -198,10 +200,12 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   const bool tail = c.tail_idx_out != nullptr;
   if (streaming) {
     auto sk = tail ? streaming_kernel<T, true> : streaming_kernel<T, false>;
-    a.use_window = 0;
-    a.bulk = contiguous && (reinterpret_cast<uintptr_t>(c.samples) % (2 * sizeof(T)) == 0) &&
-             ((static_cast<size_t>(c.stride_b) * sizeof(T)) % (2 * sizeof(T)) == 0 || c.B == 1);   // vector loads
-    const long long sgrid = std::min<long long>(c.B, static_cast<long long>(di->sms) * 8);
+    a.bulk = contiguous && (reinterpret_cast<uintptr_t>(c.samples) % 16 == 0) &&
+             ((static_cast<size_t>(c.stride_b) * sizeof(T)) % 16 == 0 || c.B == 1);   // 16-byte vector loads
+    int s_per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_per_sm, sk, kStreamThreads, 0));
+    if (s_per_sm < 1) return fail(DRCVAR_ERR_UNSUPPORTED, "streaming kernel does not fit on an SM");
+    const long long sgrid = std::min<long long>(c.B, static_cast<long long>(di->sms) * s_per_sm);
     sk<<<static_cast<unsigned>(sgrid), kStreamThreads, 0, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);

@@ -1,9 +1,14 @@
-// streaming_kernel.cuh — fallback kernel for sample counts that do not fit one CTA's shared memory
+// streaming_kernel.cuh — kernel for sample counts that do not fit one CTA's shared memory
 // (N > drcvar_max_samples(): e.g. BASELINE config 5, N = 100 000).
 //
-// Same arithmetic contract and outputs as halfspace_kernel, but the samples stay in global memory and are streamed
-// several times (canonical sums, key range, 2-4 histogram passes of the exact radix select, final sum): correct for any
-// N, ~6 reads of the samples instead of one.  One 256-thread CTA per halfspace, grid-stride over the batch.
+// Same arithmetic contract and outputs as halfspace_kernel, but the samples stay in global memory.  One 512-thread
+// CTA per halfspace, grid-stride over the batch:
+//   pass 1  canonical lane sums + second moments            (read 1: HBM)
+//   warp 0  canonical mean / direction, mean halfspace, statistical window [t_lo, t_hi] (placement only)
+//   pass 2  exact canonical fp64 loss of every sample: above the window -> count + sum, inside -> per-warp
+//           candidate lists in shared memory                (read 2: HBM or L2)
+//   select  exact rank among the candidates (range-narrowing radix select in shared memory), CVaR, offsets
+// If the window misses (or GENERAL_ONLY): the exact multi-pass radix select over all samples (2-4 more reads).
 // The single-read cluster / DSMEM kernel for large N is the planned replacement.
 #pragma once
 
@@ -11,29 +16,37 @@
 
 namespace drcvar {
 
-constexpr int kStreamThreads = 256;
+constexpr int kStreamThreads = 512;
+constexpr int kStreamWarps = kStreamThreads / 32;
+constexpr int kStreamCand = 256;    // window candidates per warp (doubles)
+constexpr int kStreamUnroll = 8;    // 16-byte loads in flight per thread in pass 2
 
 template <typename T, bool kTail>
-__global__ void __launch_bounds__(kStreamThreads) streaming_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const KernelArgs a) {
   using V2 = typename Vec2<T>::type;
   constexpr bool kF32 = sizeof(T) == 4;
-  constexpr int kPerLoad = kF32 ? 2 : 1;
-  constexpr int kRowSamples = kStreamThreads * kPerLoad;
-  constexpr int kW = kStreamThreads / 32;
+  constexpr int kPerLoad = kF32 ? 2 : 1;                  // samples per 16-byte load
+  constexpr int kRowSamples = kSweepThreads * kPerLoad;   // canonical row: 256 loads (the resident kernel's lane map)
+  constexpr int kW = kStreamWarps;
   __shared__ unsigned hist[kHistBuckets];
   __shared__ double small[kResolveMax];
   __shared__ double red[kW * 8];
+  __shared__ float mom[kW * 8];
+  __shared__ double xch[kSweepThreads * 2];
+  __shared__ double cand[kW * kStreamCand];
   __shared__ int iscr[4 * kW];
   __shared__ Ctl ctl_s;
   Ctl* ctl = &ctl_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = tid >> 8, lt = tid & (kSweepThreads - 1);   // half 0: even canonical rows, half 1: odd rows
   const int N = a.N;
+  const int full_rows = N / kRowSamples;
   const int rows_all = (N + kRowSamples - 1) / kRowSamples;
   auto sync = [] { __syncthreads(); };
 
   for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
     const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
-    const bool vec = a.bulk != 0;   // contiguous (x, y) pairs aligned to sizeof(V2): one vector load per sample
+    const bool vec = a.bulk != 0;   // contiguous (x, y) pairs, 16-byte aligned rows: vector loads
     auto load = [&](int i) {
       if (vec) return reinterpret_cast<const V2*>(base)[i];
       const T* p = base + static_cast<long long>(i) * a.stride_n;
@@ -42,73 +55,115 @@ __global__ void __launch_bounds__(kStreamThreads) streaming_kernel(const KernelA
       v.y = p[a.stride_c];
       return v;
     };
-    // ------------------------------------------------------------------ canonical lane sums (same lane map as the resident kernel)
+    // ------------------------------------------------------------------ pass 1: canonical lane sums + moments
+    // Thread (half, lt) owns slot half*256 + lt: rows r = half, half+2, ... in increasing order (the canonical order).
     const V2 first = load(0);
-    double u_x, u_y;
+    double s_x, s_y;                       // this thread's slot sums
+    float q_xx = 0.f, q_yy = 0.f, q_xy = 0.f, q_dx = 0.f, q_dy = 0.f;
     if constexpr (kF32) {
-      float2 acc[2][2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) acc[q][0] = acc[q][1] = make_float2(0.f, 0.f);
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f), sq = make_float2(0.f, 0.f);
+      float sxy = 0.f;
       const float2 nf = make_float2(-first.x, -first.y);
-      for (int r = 0; r < rows_all; ++r) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int i = r * kRowSamples + 2 * tid + e;
-          if (i < N) {
-            const float2 d = __fadd2_rn(load(i), nf);
-            if ((r & 1) == 0) acc[0][e] = __fadd2_rn(acc[0][e], d); else acc[1][e] = __fadd2_rn(acc[1][e], d);
-          }
+      auto body = [&](float2 v, float2& acc) {
+        const float2 d = __fadd2_rn(v, nf);
+        acc = __fadd2_rn(acc, d);
+        sq = __ffma2_rn(d, d, sq);
+        sxy = fmaf(d.x, d.y, sxy);
+      };
+      int r = half;
+      if (vec) {
+        const float4* g4 = reinterpret_cast<const float4*>(base);
+#pragma unroll 8
+        for (; r < full_rows; r += 2) {
+          const float4 v = g4[r * kSweepThreads + lt];
+          body(make_float2(v.x, v.y), acc0);
+          body(make_float2(v.z, v.w), acc1);
+        }
+      } else {
+        for (; r < full_rows; r += 2) {
+          const int i0 = r * kRowSamples + 2 * lt;
+          body(load(i0), acc0);
+          body(load(i0 + 1), acc1);
         }
       }
-      const double s0x = __dadd_rn(static_cast<double>(acc[0][0].x), static_cast<double>(acc[0][1].x));
-      const double s0y = __dadd_rn(static_cast<double>(acc[0][0].y), static_cast<double>(acc[0][1].y));
-      const double s1x = __dadd_rn(static_cast<double>(acc[1][0].x), static_cast<double>(acc[1][1].x));
-      const double s1y = __dadd_rn(static_cast<double>(acc[1][0].y), static_cast<double>(acc[1][1].y));
-      u_x = __dadd_rn(s0x, s1x);
-      u_y = __dadd_rn(s0y, s1y);
+      if (r == full_rows && full_rows < rows_all) {   // ragged last row (only the half with its parity)
+        const int i0 = r * kRowSamples + 2 * lt;
+        if (i0 < N) body(load(i0), acc0);
+        if (i0 + 1 < N) body(load(i0 + 1), acc1);
+      }
+      s_x = __dadd_rn(static_cast<double>(acc0.x), static_cast<double>(acc1.x));   // lanes 2 slot, 2 slot + 1
+      s_y = __dadd_rn(static_cast<double>(acc0.y), static_cast<double>(acc1.y));
+      q_xx = sq.x;
+      q_yy = sq.y;
+      q_xy = sxy;
     } else {
-      double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-      for (int r = 0; r < rows_all; ++r) {
-        const int i = r * kRowSamples + tid;
+      s_x = 0.0;
+      s_y = 0.0;
+      double dxx = 0.0, dyy = 0.0, dxy = 0.0, ddx = 0.0, ddy = 0.0;
+#pragma unroll 8
+      for (int r = half; r < rows_all; r += 2) {
+        const int i = r * kRowSamples + lt;
         if (i < N) {
           const V2 v = load(i);
-          if ((r & 1) == 0) {
-            s00 = __dadd_rn(s00, v.x);
-            s01 = __dadd_rn(s01, v.y);
-          } else {
-            s10 = __dadd_rn(s10, v.x);
-            s11 = __dadd_rn(s11, v.y);
+          s_x = __dadd_rn(s_x, v.x);
+          s_y = __dadd_rn(s_y, v.y);
+          if ((r & 3) == 0) {   // second moments on every 4th row (as in the resident kernel: n_sigma on the host)
+            const double dx = v.x - first.x, dy = v.y - first.y;
+            ddx += dx;
+            ddy += dy;
+            dxx = fma(dx, dx, dxx);
+            dyy = fma(dy, dy, dyy);
+            dxy = fma(dx, dy, dxy);
           }
         }
       }
-      u_x = __dadd_rn(s00, s10);
-      u_y = __dadd_rn(s01, s11);
+      q_xx = static_cast<float>(dxx);
+      q_yy = static_cast<float>(dyy);
+      q_xy = static_cast<float>(dxy);
+      q_dx = static_cast<float>(ddx);
+      q_dy = static_cast<float>(ddy);
     }
     {
-      const double tx = warp_sum_canon(u_x), ty = warp_sum_canon(u_y);
+      const float mxx = warp_sum_any(q_xx), myy = warp_sum_any(q_yy), mxy = warp_sum_any(q_xy);
+      const float mdx = warp_sum_any(q_dx), mdy = warp_sum_any(q_dy);
+      if (lane == 0) {
+        float* w = mom + warp * 8;
+        w[0] = mxx; w[1] = myy; w[2] = mxy; w[3] = mdx; w[4] = mdy;
+      }
+    }
+    if (half == 1) {
+      xch[2 * lt] = s_x;
+      xch[2 * lt + 1] = s_y;
+    }
+    __syncthreads();
+    if (half == 0) {   // u[j] = s[j] + s[j + 256], then the canonical butterfly inside each group of 32
+      const double tx = warp_sum_canon(__dadd_rn(s_x, xch[2 * lt]));
+      const double ty = warp_sum_canon(__dadd_rn(s_y, xch[2 * lt + 1]));
       if (lane == 0) {
         red[warp * 8] = tx;
         red[warp * 8 + 1] = ty;
       }
     }
     __syncthreads();
+    // ------------------------------------------------------------------ warp 0: canonical mean / direction, window
     if (warp == 0) {
       double w[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        double t[kW];
+        double t[kSweepWarps];
 #pragma unroll
-        for (int g = 0; g < kW; ++g) t[g] = red[g * 8 + j];
+        for (int g = 0; g < kSweepWarps; ++g) t[g] = red[g * 8 + j];
 #pragma unroll
-        for (int n = kW; n > 1; n >>= 1)
+        for (int n = kSweepWarps; n > 1; n >>= 1)
 #pragma unroll
           for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);
         w[j] = t[0];
       }
+      const double f0 = static_cast<double>(first.x), f1 = static_cast<double>(first.y);
       double m0 = __ddiv_rn(w[0], static_cast<double>(N)), m1 = __ddiv_rn(w[1], static_cast<double>(N));
       if constexpr (kF32) {
-        m0 = __dadd_rn(static_cast<double>(first.x), m0);
-        m1 = __dadd_rn(static_cast<double>(first.y), m1);
+        m0 = __dadd_rn(f0, m0);
+        m1 = __dadd_rn(f1, m1);
       }
       int nonfinite = !(isfinite(m0) && isfinite(m1));
       int degenerate = 0;
@@ -130,76 +185,226 @@ __global__ void __launch_bounds__(kStreamThreads) streaming_kernel(const KernelA
         }
       }
       nonfinite |= !(isfinite(h0) && isfinite(h1));
+      // window placement (heuristic: affects speed only): loss mean and sigma from the sample moments
+      double q[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int g = 0; g < kW; ++g)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) q[j] += static_cast<double>(mom[g * 8 + j]);
+      double n_sub, ex, ey;
+      if (kF32) {
+        n_sub = static_cast<double>(N);
+        ex = m0 - f0;
+        ey = m1 - f1;
+      } else {
+        const int r4 = (rows_all + 3) / 4;
+        const int last = (r4 - 1) * 4 * kRowSamples;
+        n_sub = static_cast<double>((r4 - 1) * kSweepThreads + (N - last < kSweepThreads ? N - last : kSweepThreads));
+        ex = q[3] / n_sub;
+        ey = q[4] / n_sub;
+      }
+      const double cxx = q[0] / n_sub - ex * ex, cyy = q[1] / n_sub - ey * ey, cxy = q[2] / n_sub - ex * ey;
+      const double var_l = h0 * h0 * cxx + 2.0 * h0 * h1 * cxy + h1 * h1 * cyy;
+      const double sigma = sqrt(var_l);
+      const double mu_l = -(h0 * m0 + h1 * m1);
+      const double t_lo = __dadd_rn(mu_l + a.z_lo * sigma, 0.0);   // +0.0: never -0.0 (canonical losses are +0)
+      const double t_hi = __dadd_rn(mu_l + a.z_hi * sigma, 0.0);
+      const int window_ok = a.use_window && !nonfinite && n_sub >= 256.0 && var_l > 0.0 && isfinite(t_lo) &&
+                            isfinite(t_hi) && t_lo <= t_hi;
       if (lane == 0) {
         ctl->h0 = h0; ctl->h1 = h1; ctl->m0 = m0; ctl->m1 = m1;
         ctl->nonfinite = nonfinite;
         ctl->degenerate = degenerate;
+        ctl->t_lo = t_lo;
+        ctl->t_hi = t_hi;
+        ctl->window_ok = window_ok;
         write_mean_outputs(a, b, m0, m1);
       }
     }
     __syncthreads();
     const double h0 = ctl->h0, h1 = ctl->h1;
     const bool nonfinite = ctl->nonfinite != 0;
-    const int status = (nonfinite ? kStatusNonfinite : 0) | (ctl->degenerate ? kStatusDegenerate : 0) | kStatusGeneral;
+    int status = (nonfinite ? kStatusNonfinite : 0) | (ctl->degenerate ? kStatusDegenerate : 0);
     auto loss_at = [&](int i) {
       const V2 v = load(i);
       return loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
     };
 
-    double T_thr = 0.0, s_gt = 0.0;
-    int c_gt = 0;
-    if (!nonfinite) {
-      unsigned long long kmin = ~0ull, kmax = 0ull;
-      for (int i = tid; i < N; i += kStreamThreads) {
-        const unsigned long long k = key_of(loss_at(i));
-        kmin = k < kmin ? k : kmin;
-        kmax = k > kmax ? k : kmax;
-      }
-#pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) {
-        const unsigned long long o1 = __shfl_xor_sync(kFull, kmin, m), o2 = __shfl_xor_sync(kFull, kmax, m);
-        kmin = o1 < kmin ? o1 : kmin;
-        kmax = o2 > kmax ? o2 : kmax;
-      }
-      unsigned long long* kred = reinterpret_cast<unsigned long long*>(red);
-      __syncthreads();
-      if (lane == 0) {
-        kred[warp * 2] = kmin;
-        kred[warp * 2 + 1] = kmax;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int w = 0; w < kW; ++w) {
-        kmin = kred[w * 2] < kmin ? kred[w * 2] : kmin;
-        kmax = kred[w * 2 + 1] > kmax ? kred[w * 2 + 1] : kmax;
-      }
-      T_thr = select_rank(
-          [&](auto&& f) {
-            for (int i = tid; i < N; i += kStreamThreads) f(loss_at(i));
-          },
-          sync, warp == 0, tid, kStreamThreads, kmin, kmax, a.kc, hist, small, ctl);
-      for (int i = tid; i < N; i += kStreamThreads) {
-        const double L = loss_at(i);
-        if (L > T_thr) {
+    double T_thr = 0.0;
+    int c_tot = 0;
+    double s_tot = 0.0;
+    bool fast = false;
+    if (ctl->window_ok && !nonfinite) {
+      // ---------------------------------------------------------------- pass 2: exact classification against the window
+      const double t_lo = ctl->t_lo, t_hi = ctl->t_hi;
+      double* wcand = cand + warp * kStreamCand;
+      int c_gt = 0, nc = 0;
+      double s_gt = 0.0;
+      auto classify = [&](bool valid, double L) {
+        const bool up = valid && (L > t_hi);
+        const bool cd = valid && !up && (L >= t_lo);
+        if (up) {
           ++c_gt;
           s_gt += L;
         }
-      }
-    }
-    const int wc = __reduce_add_sync(kFull, c_gt);
-    const double ws = warp_sum_any(s_gt);
-    __syncthreads();
-    if (lane == 0) {
-      iscr[warp] = wc;
-      red[warp] = ws;
-    }
-    __syncthreads();
-    int c_tot = 0;
-    double s_tot = 0.0;
+        const unsigned bal = __ballot_sync(kFull, cd);
+        if (bal) {
+          const int pos = nc + __popc(bal & ((1u << lane) - 1u));
+          if (cd && pos < kStreamCand) wcand[pos] = L;
+          nc += __popc(bal);
+        }
+      };
+      const int n_items = kF32 ? (N + 1) / 2 : N;   // 16-byte items: sample pairs (fp32) / samples (fp64)
+      for (int it0 = 0; it0 < n_items; it0 += kStreamThreads * kStreamUnroll) {
+        V2 v[kStreamUnroll][kPerLoad];
+        bool ok[kStreamUnroll][kPerLoad];
 #pragma unroll
-    for (int w = 0; w < kW; ++w) {
-      c_tot += iscr[w];
-      s_tot += red[w];
+        for (int u = 0; u < kStreamUnroll; ++u) {
+          const int it = it0 + u * kStreamThreads + tid;
+#pragma unroll
+          for (int e = 0; e < kPerLoad; ++e) {
+            ok[u][e] = false;
+            v[u][e] = first;
+          }
+          if (it < n_items) {
+            if constexpr (kF32) {
+              const int i0 = 2 * it;
+              if (vec && i0 + 1 < N) {
+                const float4 p = reinterpret_cast<const float4*>(base)[it];
+                v[u][0] = make_float2(p.x, p.y);
+                v[u][1] = make_float2(p.z, p.w);
+                ok[u][0] = ok[u][1] = true;
+              } else {
+                v[u][0] = load(i0);
+                ok[u][0] = true;
+                if (i0 + 1 < N) {
+                  v[u][1] = load(i0 + 1);
+                  ok[u][1] = true;
+                }
+              }
+            } else {
+              v[u][0] = load(it);
+              ok[u][0] = true;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kStreamUnroll; ++u)
+#pragma unroll
+          for (int e = 0; e < kPerLoad; ++e)
+            classify(ok[u][e], loss_of(h0, h1, static_cast<double>(v[u][e].x), static_cast<double>(v[u][e].y)));
+      }
+      const int wc = __reduce_add_sync(kFull, c_gt);
+      const double ws = warp_sum_any(s_gt);
+      if (lane == 0) {
+        iscr[warp] = wc;
+        iscr[kW + warp] = nc;
+        red[warp] = ws;
+      }
+      __syncthreads();
+      int cnt_hi = 0, ncand = 0, ovf = 0;
+      double s_hi = 0.0;
+#pragma unroll
+      for (int w = 0; w < kW; ++w) {
+        cnt_hi += iscr[w];
+        ncand += iscr[kW + w];
+        ovf |= iscr[kW + w] > kStreamCand;
+        s_hi += red[w];
+      }
+      fast = !ovf && cnt_hi < a.kc && a.kc <= cnt_hi + ncand;
+      if (fast) {
+        const int my_nc = iscr[kW + warp];
+        auto each = [&](auto&& f) {
+          for (int j = lane; j < my_nc; j += 32) f(wcand[j]);
+        };
+        T_thr = select_rank(each, sync, warp == 0, tid, kStreamThreads, key_of(t_lo), key_of(t_hi), a.kc - cnt_hi, hist,
+                            small, ctl);
+        int c4 = 0;
+        double s4 = 0.0;
+        each([&](double L) {
+          if (L > T_thr) {
+            ++c4;
+            s4 += L;
+          }
+        });
+        const int wc4 = __reduce_add_sync(kFull, c4);
+        const double ws4 = warp_sum_any(s4);
+        __syncthreads();   // iscr / red were read above by everybody
+        if (lane == 0) {
+          iscr[2 * kW + warp] = wc4;
+          red[kW + warp] = ws4;
+        }
+        __syncthreads();
+        c_tot = cnt_hi;
+        double s_c = 0.0;
+#pragma unroll
+        for (int w = 0; w < kW; ++w) {
+          c_tot += iscr[2 * kW + w];
+          s_c += red[kW + w];
+        }
+        s_tot = s_hi + s_c;
+      }
+      __syncthreads();
+    }
+
+    if (!fast) {
+      // ------------------------------------------------------------------ general path: exact multi-pass radix select
+      status |= kStatusGeneral;
+      int c_gt = 0;
+      double s_gt = 0.0;
+      if (!nonfinite) {
+        unsigned long long kmin = ~0ull, kmax = 0ull;
+        for (int i = tid; i < N; i += kStreamThreads) {
+          const unsigned long long k = key_of(loss_at(i));
+          kmin = k < kmin ? k : kmin;
+          kmax = k > kmax ? k : kmax;
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+          const unsigned long long o1 = __shfl_xor_sync(kFull, kmin, m), o2 = __shfl_xor_sync(kFull, kmax, m);
+          kmin = o1 < kmin ? o1 : kmin;
+          kmax = o2 > kmax ? o2 : kmax;
+        }
+        unsigned long long* kred = reinterpret_cast<unsigned long long*>(xch);
+        __syncthreads();
+        if (lane == 0) {
+          kred[warp * 2] = kmin;
+          kred[warp * 2 + 1] = kmax;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kW; ++w) {
+          kmin = kred[w * 2] < kmin ? kred[w * 2] : kmin;
+          kmax = kred[w * 2 + 1] > kmax ? kred[w * 2 + 1] : kmax;
+        }
+        T_thr = select_rank(
+            [&](auto&& f) {
+              for (int i = tid; i < N; i += kStreamThreads) f(loss_at(i));
+            },
+            sync, warp == 0, tid, kStreamThreads, kmin, kmax, a.kc, hist, small, ctl);
+        for (int i = tid; i < N; i += kStreamThreads) {
+          const double L = loss_at(i);
+          if (L > T_thr) {
+            ++c_gt;
+            s_gt += L;
+          }
+        }
+      }
+      const int wc = __reduce_add_sync(kFull, c_gt);
+      const double ws = warp_sum_any(s_gt);
+      __syncthreads();
+      if (lane == 0) {
+        iscr[warp] = wc;
+        red[warp] = ws;
+      }
+      __syncthreads();
+      c_tot = 0;
+      s_tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < kW; ++w) {
+        c_tot += iscr[w];
+        s_tot += red[w];
+      }
     }
     if (tid == 0) write_risk_outputs(a, b, ctl, nonfinite, s_tot, c_tot, T_thr, status);
 

@@ -296,6 +296,7 @@ def test_large_n_streaming_kernel(eng, dtype):
     res = eng.compute_halfspaces(s, ego, want_tail=True, **p)
     check_batch(res, s, ego, p)
     assert res.tail_idx.shape == (3, 10000)
+    assert not (res.status & _lib.STATUS_GENERAL).any()          # two-pass window path, not the multi-pass select
     # forced on small N it must agree bit for bit with the shared-memory kernel's general path
     for nn in (10000, 777, 20, 1):
         ss = (rng.uniform(-4, 4, size=(16, 1, 2)) + 0.1 * rng.standard_normal((16, nn, 2))).astype(dtype)
