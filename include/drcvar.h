@@ -54,7 +54,7 @@ extern "C" {
 #define DRCVAR_FLAG_SYNC 1u          /* device pointers: synchronise the stream before returning */
 #define DRCVAR_FLAG_GENERAL_ONLY 2u  /* disable the statistical candidate window (always use the general select) */
 #define DRCVAR_FLAG_NO_BULK 4u       /* disable cp.async.bulk staging (use the generic strided loader) */
-#define DRCVAR_FLAG_FORCE_STREAMING 8u /* use the multi-pass streaming kernel even when one CTA could hold N samples */
+#define DRCVAR_FLAG_FORCE_STREAMING 8u /* use the two-pass streaming kernel even when one CTA could hold N samples */
 
 /* per-halfspace status bits written to status_out */
 #define DRCVAR_STATUS_NONFINITE 1   /* non-finite input: sentinel 100.0 emitted (core/risk_metrics.py:177,265,303,338) */
@@ -76,7 +76,7 @@ int drcvar_reduction_lanes(void);
 int64_t drcvar_tail_count(double alpha, int64_t n_samples, double* k_f_out);
 
 /* Largest N the single-read shared-memory kernel holds for a sample dtype of `elem_bytes` (4 or 8) on `device`;
- * larger N is served by the multi-pass streaming kernel (same results, several reads of the samples). */
+ * larger N is served by the two-pass streaming kernel (same results, two reads of the samples). */
 int64_t drcvar_max_samples(int elem_bytes, int device);
 
 /*
