@@ -1057,9 +1057,9 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           unsigned mk = 0;
           classify_f32(p0, thr_above, thr_keep, d0.x, d0.y, ax, ay, cf, mk, bit0);
           classify_f32(p1, thr_above, thr_keep, d1.x, d1.y, ax, ay, cf, mk, bit0 + bit0);
+          const int wr = (2 * r) >> 5;
 #pragma unroll
-          for (int w2 = 0; w2 < kMaskWords; ++w2)
-            if (w2 == ((2 * r) >> 5)) mask[w2] |= mk;
+          for (int w2 = 0; w2 < kMaskWords; ++w2) mask[w2] |= (w2 == wr) ? mk : 0u;   // selects keep mask[] in registers
         }
       } else {
 #pragma unroll
@@ -1089,26 +1089,40 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
 #pragma unroll
       for (int wd = 0; wd < kMaskWords; ++wd)
         if (wd * 32 < rows_all * kPerLoad) mine_n += __popc(mask[wd]);
-      int incl = mine_n;
+      // exclusive prefix over the lanes.  Counts are tiny (~0.6 per lane): three independent ballots (one per bit plane)
+      // instead of a dependent 5-stage shuffle scan; the shuffle scan remains for counts >= 8.
+      int excl, n_list;
+      const unsigned lt_mask = (1u << lane) - 1u;
+      if (__ballot_sync(kFull, mine_n >= 8) == 0u) {
+        const unsigned b0 = __ballot_sync(kFull, mine_n & 1), b1 = __ballot_sync(kFull, mine_n & 2),
+                       b2 = __ballot_sync(kFull, mine_n & 4);
+        excl = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+        n_list = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+      } else {
+        int incl = mine_n;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(kFull, incl, d);
-        if (lane >= d) incl += t;
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(kFull, incl, d);
+          if (lane >= d) incl += t;
+        }
+        n_list = __shfl_sync(kFull, incl, 31);
+        excl = incl - mine_n;
       }
-      const int n_list = __shfl_sync(kFull, incl, 31);
       bool overflow = n_list > kWarpList;
       if (!overflow) {
-        int pos = incl - mine_n;
+        V2* dst = wlist + excl;
+        // byte address of mask bit P = 32 wd + bp:  fp32: (P>>1) rows of 4 KB + 16 tid + 8 (P&1);  fp64: P rows + 16 tid
+        const unsigned char* tbase = smem_raw + 16u * tid;
 #pragma unroll
         for (int wd = 0; wd < kMaskWords; ++wd) {
           if (wd * 32 < rows_all * kPerLoad) {
             unsigned mm = mask[wd];
+            const unsigned char* wbase = tbase + (kF32 ? 16u : 32u) * 4096u * wd;
             while (mm) {
               const unsigned bp = 31u - static_cast<unsigned>(__clz(static_cast<int>(mm)));   // highest set bit (one FLO)
               mm ^= 1u << bp;
-              const unsigned P = 32u * wd + bp;
-              const unsigned i = kF32 ? ((P >> 1) * kRowSamples + 2u * tid + (P & 1u)) : (P * kRowSamples + tid);
-              wlist[pos++] = sm[i];
+              const unsigned off = kF32 ? (((bp & 30u) << 11) | ((bp & 1u) << 3)) : (bp << 12);
+              *dst++ = *reinterpret_cast<const V2*>(wbase + off);
             }
           }
         }
