@@ -789,16 +789,24 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         body(va, 0);
         body(vb, 1);
       }
-      // remaining rows (an odd full row and/or the ragged last row): same vector path; samples beyond N are replaced
-      // by the first sample, whose shifted value is +0 and adds nothing (the slot is followed by other shared arrays,
-      // so the 16-byte load itself stays inside the CTA's allocation)
-      for (; r < rows_all; ++r) {
-        float4 v = sm4[r * kSweepThreads + tid];
-        const int i0 = r * kRowSamples + 2 * tid;
+      // remaining rows (a last pair whose second row is ragged, and/or a single last row): same vector path; samples
+      // beyond N are replaced by the first sample, whose shifted value is +0 and adds nothing (the slot is followed by
+      // other shared arrays, so the 16-byte load itself stays inside the CTA's allocation).  r is even here, so the
+      // tile parity of every row is static.
+      auto masked = [&](int row) {
+        float4 v = sm4[row * kSweepThreads + tid];
+        const int i0 = row * kRowSamples + 2 * tid;
         if (i0 >= N) { v.x = first.x; v.y = first.y; }
         if (i0 + 1 >= N) { v.z = first.x; v.w = first.y; }
-        if (r & 1) body(v, 1); else body(v, 0);
+        return v;
+      };
+      if (r + 1 < rows_all) {
+        const float4 va = sm4[r * kSweepThreads + tid], vb = masked(r + 1);
+        body(va, 0);
+        body(vb, 1);
+        r += 2;
       }
+      if (r < rows_all) body(masked(r), 0);
       // adjacent fp32 lanes (2 slot, 2 slot + 1) widened and added in fp64, then slot tid + slot tid+256
       const double s0x = __dadd_rn(static_cast<double>(acc[0][0].x), static_cast<double>(acc[0][1].x));
       const double s0y = __dadd_rn(static_cast<double>(acc[0][0].y), static_cast<double>(acc[0][1].y));
@@ -1030,10 +1038,11 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         const float4* sm4 = reinterpret_cast<const float4*>(smem_raw);
         const float h0f = ctl->h0f, h1f = ctl->h1f, thr_keep = ctl->thr_keep, thr_above = ctl->thr_above;
         const float2 nf = make_float2(-first.x, -first.y);
+        const int full4 = full_rows & ~3;   // rows in complete groups of 4 that need no masking
 #pragma unroll
         for (int wd = 0; wd < kMaskWords; ++wd) {
           const int r_lo = wd * kRowsPerWord;
-          const int r_hi = full_rows < r_lo + kRowsPerWord ? full_rows : r_lo + kRowsPerWord;
+          const int r_hi = full4 < r_lo + kRowsPerWord ? full4 : r_lo + kRowsPerWord;
           unsigned bit = 1u;
 #pragma unroll 4
           for (int r = r_lo; r < r_hi; ++r) {
@@ -1045,21 +1054,28 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
             bit <<= 2;
           }
         }
-        if (full_rows < rows_all) {  // ragged last row: same vector path, samples beyond N can neither be "above" nor kept
-          const int r = full_rows;
-          const float4 v = sm4[r * kSweepThreads + tid];
-          const int i0 = r * kRowSamples + 2 * tid;
-          const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nf), d1 = __fadd2_rn(make_float2(v.z, v.w), nf);
-          float p0 = fmaf(h1f, d0.y, h0f * d0.x), p1 = fmaf(h1f, d1.y, h0f * d1.x);
-          if (i0 >= N) p0 = __int_as_float(0x7f800000);
-          if (i0 + 1 >= N) p1 = __int_as_float(0x7f800000);
-          const unsigned bit0 = 1u << ((2 * r) & 31);
+        if (full4 < rows_all) {
+          // last group (1-4 rows, the last one possibly ragged): four loads in flight like every other group; samples
+          // beyond N get p = +inf (neither "above" nor kept); rows beyond the data re-read the last row (masked anyway)
           unsigned mk = 0;
-          classify_f32(p0, thr_above, thr_keep, d0.x, d0.y, ax, ay, cf, mk, bit0);
-          classify_f32(p1, thr_above, thr_keep, d1.x, d1.y, ax, ay, cf, mk, bit0 + bit0);
-          const int wr = (2 * r) >> 5;
+          unsigned bit = 1u << ((2 * full4) & 31);
 #pragma unroll
-          for (int w2 = 0; w2 < kMaskWords; ++w2) mask[w2] |= (w2 == wr) ? mk : 0u;   // selects keep mask[] in registers
+          for (int k = 0; k < 4; ++k) {
+            const int row = full4 + k;
+            const int rr = row < rows_all ? row : rows_all - 1;
+            const float4 v = sm4[rr * kSweepThreads + tid];
+            const int i0 = row * kRowSamples + 2 * tid;
+            const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nf), d1 = __fadd2_rn(make_float2(v.z, v.w), nf);
+            float p0 = fmaf(h1f, d0.y, h0f * d0.x), p1 = fmaf(h1f, d1.y, h0f * d1.x);
+            if (i0 >= N) p0 = __int_as_float(0x7f800000);
+            if (i0 + 1 >= N) p1 = __int_as_float(0x7f800000);
+            classify_f32(p0, thr_above, thr_keep, d0.x, d0.y, ax, ay, cf, mk, bit);
+            classify_f32(p1, thr_above, thr_keep, d1.x, d1.y, ax, ay, cf, mk, bit + bit);
+            bit <<= 2;
+          }
+          const int wg = (2 * full4) >> 5;   // a group of 4 rows never straddles a mask word
+#pragma unroll
+          for (int w2 = 0; w2 < kMaskWords; ++w2) mask[w2] |= (w2 == wg) ? mk : 0u;   // selects keep mask[] in registers
         }
       } else {
 #pragma unroll
