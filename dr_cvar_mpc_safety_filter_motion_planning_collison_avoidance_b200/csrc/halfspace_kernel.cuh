@@ -1044,7 +1044,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           const int r_lo = wd * kRowsPerWord;
           const int r_hi = full4 < r_lo + kRowsPerWord ? full4 : r_lo + kRowsPerWord;
           unsigned bit = 1u;
-#pragma unroll 4
+#pragma unroll 8
           for (int r = r_lo; r < r_hi; ++r) {
             const float4 v = sm4[r * kSweepThreads + tid];
             const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nf), d1 = __fadd2_rn(make_float2(v.z, v.w), nf);
