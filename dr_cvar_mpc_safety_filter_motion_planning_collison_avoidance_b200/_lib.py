@@ -43,6 +43,13 @@ SYMBOLS = {
     "drcvar_max_samples": (C.c_int64, [C.c_int, C.c_int]),
     "drcvar_halfspaces_f32": (C.c_int, [C.c_void_p] + _HALFSPACE_TAIL),
     "drcvar_halfspaces_f64": (C.c_int, [C.c_void_p] + _HALFSPACE_TAIL),
+    "drcvar_halfspaces_generated_f32": (C.c_int, [
+        C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int64,     # mean, chol, seed, index_offset, B, N
+        C.c_void_p, C.c_void_p,                                                   # ego, h_in
+        C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint32,   # alpha .. r_obs, flags
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,   # h, h_mean, g, cvar, var, gstar
+        C.c_void_p, C.c_void_p, C.c_void_p,                                       # status, tail_idx, samples_out
+        C.c_int, C.c_void_p]),                                                    # device, stream
     "drcvar_trajectory_f64": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                         C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint32,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

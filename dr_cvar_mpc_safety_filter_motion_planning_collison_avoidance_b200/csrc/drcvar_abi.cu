@@ -137,6 +137,12 @@ struct Call {
   double *h_out, *h_mean_out, *g_out, *cvar_out, *var_out, *gstar_out;
   int32_t* status_out;
   int32_t* tail_idx_out;
+  // generate mode (samples == nullptr): see drcvar_halfspaces_generated_f32
+  const double* gen_mean = nullptr;
+  const double* gen_chol = nullptr;
+  uint64_t gen_seed = 0;
+  long long gen_index_offset = 0;
+  float* gen_samples_out = nullptr;
 };
 
 template <typename T>
@@ -191,6 +197,16 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   a.gstar_out = c.gstar_out;
   a.status_out = c.status_out;
   a.tail_idx_out = c.tail_idx_out;
+  a.gen_mean = c.gen_mean;
+  a.gen_chol = c.gen_chol;
+  a.gen_seed = c.gen_seed;
+  a.gen_index_offset = c.gen_index_offset;
+  a.gen_samples_out = c.gen_samples_out;
+  if (c.gen_mean != nullptr) {
+    if (sizeof(T) != 4) return fail(DRCVAR_ERR_UNSUPPORTED, "generate mode is fp32 only");
+    if (streaming) return fail(DRCVAR_ERR_UNSUPPORTED, "generate mode needs N <= drcvar_max_samples(4): N=%lld", c.N);
+    a.bulk = 0;   // the sweep team fills the slot itself
+  }
 
 #ifdef DRCVAR_PROFILE_PHASES
   a.phase_cycles = g_phase_cycles;
@@ -212,6 +228,9 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
     return DRCVAR_OK;
   }
   auto kern = tail ? halfspace_kernel<T, true> : halfspace_kernel<T, false>;
+  if constexpr (sizeof(T) == 4) {
+    if (c.gen_mean != nullptr) kern = tail ? halfspace_kernel<float, true, true> : halfspace_kernel<float, false, true>;
+  }
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
@@ -231,8 +250,9 @@ int check_common(const Call& c) {
   if (c.N < 1) return fail(DRCVAR_ERR_INVALID, "N must be >= 1");
   if (c.N > 0x7fffff00LL) return fail(DRCVAR_ERR_UNSUPPORTED, "N too large");
   if (!(c.alpha > 0.0) || !(c.alpha <= 1.0)) return fail(DRCVAR_ERR_INVALID, "alpha must be in (0, 1]");
-  if (c.B > 0 && (!c.samples || !c.h_out || !c.g_out))
+  if (c.B > 0 && ((!c.samples && !c.gen_mean) || !c.h_out || !c.g_out))
     return fail(DRCVAR_ERR_INVALID, "samples, h_out and g_out must be non-null");
+  if (c.gen_mean && !c.gen_chol) return fail(DRCVAR_ERR_INVALID, "generate mode needs mean and chol");
   if (c.stride_n < 0 || c.stride_c < 0 || c.stride_b < 0) return fail(DRCVAR_ERR_INVALID, "negative strides are not supported");
   return DRCVAR_OK;
 }
@@ -443,6 +463,89 @@ int run_host(const Call& c) {
   return DRCVAR_OK;
 }
 
+// DRCVAR_HOST path of the generate mode: the inputs are tiny (mean, chol, ego per halfspace), one stream, no chunking.
+int run_host_generated(const Call& c) {
+  HostCtx& hc = g_host;
+  std::lock_guard<std::mutex> lk(hc.mu);
+  int rc = ensure_host_ctx(hc);
+  if (rc) return rc;
+  double k_f;
+  long long kc;
+  if (!tail_count(c.alpha, c.N, &k_f, &kc)) return fail(DRCVAR_ERR_INVALID, "alpha must be in (0,1] and N >= 1");
+  hc.last_stage_ms = hc.last_kernel_ms = 0;
+  hc.last_h2d = hc.last_d2h = 0;
+  if (c.B == 0) return DRCVAR_OK;
+  cudaStream_t st = hc.streams[0];
+  const size_t nb = static_cast<size_t>(c.B), dbl = sizeof(double);
+  const size_t off_mean = 0, off_chol = off_mean + nb * 2 * dbl, off_ego = off_chol + nb * 3 * dbl,
+               off_hin = off_ego + nb * 2 * dbl, off_h = off_hin + nb * 2 * dbl, off_hm = off_h + nb * 2 * dbl,
+               off_g = off_hm + nb * 2 * dbl, off_cvar = off_g + nb * 3 * dbl, off_var = off_cvar + nb * dbl,
+               off_gs = off_var + nb * dbl, off_st = off_gs + nb * dbl,
+               off_tail = align_up(off_st + nb * sizeof(int32_t), 16),
+               io_bytes = off_tail + (c.tail_idx_out ? nb * kc * sizeof(int32_t) : 0);
+  rc = grow_dev(reinterpret_cast<void**>(&hc.d_io[0]), &hc.d_io_cap[0], io_bytes);
+  if (rc) return rc;
+  unsigned char* io = hc.d_io[0];
+  const size_t dump_bytes = c.gen_samples_out ? nb * static_cast<size_t>(c.N) * 2 * sizeof(float) : 0;
+  if (dump_bytes) {
+    rc = grow_dev(&hc.d_samples[0], &hc.d_samples_cap[0], dump_bytes);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaEventRecord(hc.ev_start, st));
+  auto up = [&](size_t off, const double* host, size_t bytes) -> cudaError_t {
+    if (!host) return cudaSuccess;
+    hc.last_h2d += static_cast<long long>(bytes);
+    return cudaMemcpyAsync(io + off, host, bytes, cudaMemcpyHostToDevice, st);
+  };
+  CUDA_TRY(up(off_mean, c.gen_mean, nb * 2 * dbl));
+  CUDA_TRY(up(off_chol, c.gen_chol, nb * 3 * dbl));
+  CUDA_TRY(up(off_ego, c.ego, nb * 2 * dbl));
+  CUDA_TRY(up(off_hin, c.h_in, nb * 2 * dbl));
+  Call d = c;
+  d.gen_mean = reinterpret_cast<const double*>(io + off_mean);
+  d.gen_chol = reinterpret_cast<const double*>(io + off_chol);
+  d.ego = c.ego ? reinterpret_cast<const double*>(io + off_ego) : nullptr;
+  d.h_in = c.h_in ? reinterpret_cast<const double*>(io + off_hin) : nullptr;
+  d.h_out = reinterpret_cast<double*>(io + off_h);
+  d.h_mean_out = reinterpret_cast<double*>(io + off_hm);
+  d.g_out = reinterpret_cast<double*>(io + off_g);
+  d.cvar_out = reinterpret_cast<double*>(io + off_cvar);
+  d.var_out = reinterpret_cast<double*>(io + off_var);
+  d.gstar_out = reinterpret_cast<double*>(io + off_gs);
+  d.status_out = reinterpret_cast<int32_t*>(io + off_st);
+  d.tail_idx_out = c.tail_idx_out ? reinterpret_cast<int32_t*>(io + off_tail) : nullptr;
+  d.gen_samples_out = dump_bytes ? static_cast<float*>(hc.d_samples[0]) : nullptr;
+  rc = launch_on_device<float>(d, hc.device, st);
+  if (rc) return rc;
+  const size_t out_bytes = io_bytes - off_h;
+  rc = grow_pinned(&hc.h_out_stage[0], &hc.h_out_cap[0], out_bytes);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(hc.h_out_stage[0], io + off_h, out_bytes, cudaMemcpyDeviceToHost, st));
+  hc.last_d2h += static_cast<long long>(out_bytes);
+  if (dump_bytes) {
+    CUDA_TRY(cudaMemcpyAsync(c.gen_samples_out, hc.d_samples[0], dump_bytes, cudaMemcpyDeviceToHost, st));
+    hc.last_d2h += static_cast<long long>(dump_bytes);
+  }
+  CUDA_TRY(cudaEventRecord(hc.ev_stop, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const unsigned char* base = static_cast<const unsigned char*>(hc.h_out_stage[0]) - off_h;
+  auto put = [&](void* host, size_t off, size_t bytes) {
+    if (host) std::memcpy(host, base + off, bytes);
+  };
+  put(c.h_out, off_h, nb * 2 * dbl);
+  put(c.h_mean_out, off_hm, nb * 2 * dbl);
+  put(c.g_out, off_g, nb * 3 * dbl);
+  put(c.cvar_out, off_cvar, nb * dbl);
+  put(c.var_out, off_var, nb * dbl);
+  put(c.gstar_out, off_gs, nb * dbl);
+  put(c.status_out, off_st, nb * sizeof(int32_t));
+  put(c.tail_idx_out, off_tail, nb * kc * sizeof(int32_t));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, hc.ev_start, hc.ev_stop));
+  hc.last_kernel_ms = ms;
+  return DRCVAR_OK;
+}
+
 template <typename T>
 int entry(const T* samples, int64_t B, int64_t N, int64_t stride_b, int64_t stride_n, int64_t stride_c,
           const double* ego, const double* h_in, double alpha, double delta, double epsilon, double r_robot,
@@ -519,6 +622,35 @@ int drcvar_halfspaces_f64(const double* samples, int64_t B, int64_t N, int64_t s
   return entry<double>(samples, B, N, stride_b, stride_n, stride_c, ego, h_in, alpha, delta, epsilon, r_robot, r_obs,
                        flags, h_out, h_mean_out, g_out, cvar_out, var_out, gstar_out, status_out, tail_idx_out, device,
                        stream);
+}
+
+int drcvar_halfspaces_generated_f32(const double* mean, const double* chol, uint64_t seed, int64_t index_offset, int64_t B,
+                                    int64_t N, const double* ego, const double* h_in, double alpha, double delta,
+                                    double epsilon, double r_robot, double r_obs, uint32_t flags, double* h_out,
+                                    double* h_mean_out, double* g_out, double* cvar_out, double* var_out,
+                                    double* gstar_out, int32_t* status_out, int32_t* tail_idx_out, float* samples_out,
+                                    int device, void* stream) {
+  Call c{nullptr, B, N, 2 * N, 2, 1, ego, h_in, alpha, delta, epsilon, r_robot, r_obs, flags,
+         h_out, h_mean_out, g_out, cvar_out, var_out, gstar_out, status_out, tail_idx_out};
+  c.gen_mean = mean;
+  c.gen_chol = chol;
+  c.gen_seed = seed;
+  c.gen_index_offset = index_offset;
+  c.gen_samples_out = samples_out;
+  if (B > 0 && (!mean || !chol)) return fail(DRCVAR_ERR_INVALID, "mean and chol must be non-null");
+  int rc = check_common(c);
+  if (rc) return rc;
+  if (device == DRCVAR_HOST) return run_host_generated(c);
+  int prev = 0;
+  CUDA_TRY(cudaGetDevice(&prev));
+  if (prev != device) CUDA_TRY(cudaSetDevice(device));
+  rc = launch_on_device<float>(c, device, static_cast<cudaStream_t>(stream));
+  if (rc == DRCVAR_OK && (flags & DRCVAR_FLAG_SYNC)) {
+    cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) rc = fail(DRCVAR_ERR_CUDA, "stream synchronize failed: %s", cudaGetErrorString(e));
+  }
+  if (prev != device) cudaSetDevice(prev);
+  return rc;
 }
 
 int drcvar_trajectory_f64(const double* const* traj, int64_t n_obs, int64_t N, int64_t T1, int64_t n_steps,

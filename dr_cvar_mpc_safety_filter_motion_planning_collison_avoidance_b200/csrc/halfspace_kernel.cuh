@@ -31,6 +31,8 @@
 #pragma once
 
 #include <cuda_runtime.h>
+
+#include "sample_gen.cuh"
 #include <stdint.h>
 
 // Optional phase timing (profiling builds only: -DDRCVAR_PROFILE_PHASES; see profiles/phase_cycles.py)
@@ -89,6 +91,12 @@ struct KernelArgs {
   int* status_out;
   int* tail_idx_out;
   long long* phase_cycles;   // profiling builds: [grid][2][12] accumulated cycles (sweep warp 2, finisher)
+  // generate mode (fp32 only, samples == nullptr): samples are drawn on the device, see sample_gen.cuh
+  const double* gen_mean;    // [B,2] nominal obstacle position of each halfspace
+  const double* gen_chol;    // [B,3] lower Cholesky factor (l00, l10, l11) of the noise covariance
+  unsigned long long gen_seed;
+  long long gen_index_offset;   // global index of halfspace 0 of this launch (shards reproduce the unsharded stream)
+  float* gen_samples_out;    // optional [B,N,2] dump of the generated samples (parity tests)
 };
 
 struct Ctl {                        // one per parity buffer
@@ -429,7 +437,7 @@ __device__ __forceinline__ void write_risk_outputs(const KernelArgs& a, long lon
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-template <typename T, bool kTail>
+template <typename T, bool kTail, bool kGen = false>
 __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs a) {
   using V2 = typename Vec2<T>::type;
   constexpr bool kF32 = sizeof(T) == 4;
@@ -696,6 +704,47 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     inv_sub = 1.0 / static_cast<double>(n_sub0 > 0 ? n_sub0 : 1);
   }
   const float inv_sub_f = static_cast<float>(inv_sub);
+  // Non-bulk staging of halfspace b into the slot by the team: strided loader for arbitrary element strides, or — in
+  // generate mode (fp32) — the samples themselves: nominal position + L z, z from Philox4x32-10 + Box-Muller
+  // (sample_gen.cuh; one Philox call per pair of samples), optionally dumped for the parity tests.
+  auto stage_generic = [&](long long b) {
+    if constexpr (kF32 && kGen) {   // separate instantiation: the resident kernel's code is untouched
+      {
+        const float mx = static_cast<float>(a.gen_mean[2 * b]), my = static_cast<float>(a.gen_mean[2 * b + 1]);
+        const float l00 = static_cast<float>(a.gen_chol[3 * b]), l10 = static_cast<float>(a.gen_chol[3 * b + 1]),
+                    l11 = static_cast<float>(a.gen_chol[3 * b + 2]);
+        const unsigned long long gb = static_cast<unsigned long long>(b + a.gen_index_offset);
+        const uint32_t k0 = static_cast<uint32_t>(a.gen_seed), k1 = static_cast<uint32_t>(a.gen_seed >> 32);
+        const int n_pairs = (N + 1) >> 1;
+        float4* sm4w = reinterpret_cast<float4*>(smem_raw);
+        float* dump = a.gen_samples_out ? a.gen_samples_out + static_cast<size_t>(b) * N * 2 : nullptr;
+        for (int j = tid; j < n_pairs; j += kSweepThreads) {
+          const Philox4 r = philox4x32_10(static_cast<uint32_t>(j), static_cast<uint32_t>(gb),
+                                          static_cast<uint32_t>(gb >> 32), kGenStreamTag, k0, k1);
+          const float2 s0 = gen_sample(r.x, r.y, mx, my, l00, l10, l11);
+          const float2 s1 = gen_sample(r.z, r.w, mx, my, l00, l10, l11);
+          sm4w[j] = make_float4(s0.x, s0.y, s1.x, s1.y);   // an odd N leaves >= 8 spare bytes in the 128-byte rounded slot
+          if (dump) {
+            dump[4 * j] = s0.x;
+            dump[4 * j + 1] = s0.y;
+            if (2 * j + 1 < N) {
+              dump[4 * j + 2] = s1.x;
+              dump[4 * j + 3] = s1.y;
+            }
+          }
+        }
+        return;
+      }
+    }
+    const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
+    for (int i = tid; i < N; i += kSweepThreads) {
+      const T* p = base + static_cast<long long>(i) * a.stride_n;
+      V2 v;
+      v.x = p[0];
+      v.y = p[a.stride_c];
+      sm[i] = v;
+    }
+  };
   PH_DECL
 
   for (long long b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
@@ -726,14 +775,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       mbar_wait(&bars->data0, phase);   // the first chunk; the rest is awaited inside sweep A
     } else {
       team_sync();   // every warp is done with the previous halfspace's samples
-      const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
-      for (int i = tid; i < N; i += kSweepThreads) {
-        const T* p = base + static_cast<long long>(i) * a.stride_n;
-        V2 v;
-        v.x = p[0];
-        v.y = p[a.stride_c];
-        sm[i] = v;
-      }
+      stage_generic(b);
       team_sync();
     }
     // parity buffers must have been handed back by the finisher (two iterations ago)
@@ -1248,14 +1290,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           redo_bulk = true;
         } else {
           team_sync();
-          const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
-          for (int i = tid; i < N; i += kSweepThreads) {
-            const T* p = base + static_cast<long long>(i) * a.stride_n;
-            V2 v;
-            v.x = p[0];
-            v.y = p[a.stride_c];
-            sm[i] = v;
-          }
+          stage_generic(b);
           team_sync();
         }
       }

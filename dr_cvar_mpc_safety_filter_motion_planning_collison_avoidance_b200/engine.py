@@ -29,6 +29,7 @@ class HalfspaceBatch:
     g_star: object       # [B]  DR-CVaR LP optimum before the radius is subtracted
     status: object       # [B]  int32 STATUS_* bits
     tail_idx: Optional[object] = None   # [B, kc] int32, ascending (parity mode)
+    samples: Optional[object] = None    # [B, N, 2] float32: the generated samples (generate mode, want_samples=True)
 
     @property
     def g_mean(self):
@@ -156,6 +157,81 @@ def _compute_device(lib, s, ego, alpha, delta, epsilon, rr, ro, h, want_tail, fl
             C.c_void_p(stream))
     _lib.check(rc)
     return out
+
+
+def cholesky2(cov):
+    """(l00, l10, l11) of 2x2 covariance matrices [..., 2, 2] (fp64): the `chol` argument of the generate mode."""
+    cov = np.asarray(cov, dtype=np.float64)
+    l00 = np.sqrt(cov[..., 0, 0])
+    l10 = np.where(l00 > 0, cov[..., 1, 0] / np.where(l00 > 0, l00, 1.0), 0.0)
+    l11 = np.sqrt(np.maximum(cov[..., 1, 1] - l10 * l10, 0.0))
+    return np.stack([l00, l10, l11], axis=-1)
+
+
+def compute_halfspaces_generated(mean, noise_cov, n_samples, seed, ego=None, *, alpha, delta, epsilon, robot_radius,
+                                 obstacle_radius, h=None, index_offset=0, want_tail=False, want_samples=False,
+                                 flags=0, device=None, stream=None):
+    """
+    Fused Monte-Carlo sampling + halfspaces: halfspace b draws `n_samples` points  mean[b] + N(0, noise_cov[b])  inside
+    the kernel (never stored) — generate_obstacle_sample_trajectories (simulation/obstacles.py:43-77) followed by the
+    *SafeHalfspace.create calls (core/halfspaces.py:70-194), for B (obstacle, step) pairs in one launch.
+
+    mean: [B,2] nominal positions; noise_cov: [2,2] or [B,2,2]; seed: 64-bit key of the Philox stream; index_offset:
+    global index of halfspace 0 (so that a shard reproduces its slice of the unsharded batch).
+    device=None: host path (numpy outputs); device=int or torch.device: outputs are torch CUDA tensors on it.
+    Returns a HalfspaceBatch; with want_samples=True also the generated float32 samples [B,N,2] as `.samples`.
+    """
+    lib = _lib.load()
+    mean_a = np.ascontiguousarray(np.atleast_2d(np.asarray(mean, dtype=np.float64)))
+    B = mean_a.shape[0]
+    if mean_a.shape != (B, 2):
+        raise ValueError("mean must be [B,2]")
+    cov = np.asarray(noise_cov, dtype=np.float64)
+    bcast = lambda x, w: np.array(np.broadcast_to(np.asarray(x, dtype=np.float64), (B, w)), order="C")  # noqa: E731
+    chol_a = bcast(cholesky2(cov), 3)
+    N = int(n_samples)
+    ego_a = None if ego is None else bcast(ego, 2)
+    h_a = None if h is None else bcast(h, 2)
+    _, kc = tail_count(alpha, N)
+    scal = (float(alpha), float(delta), float(epsilon), float(robot_radius), float(obstacle_radius), int(flags))
+    if device is None:
+        res = HalfspaceBatch(
+            h=np.empty((B, 2)), h_mean=np.empty((B, 2)), g=np.empty((B, 3)), cvar=np.empty(B), var=np.empty(B),
+            g_star=np.empty(B), status=np.zeros(B, dtype=np.int32),
+            tail_idx=np.empty((B, kc), dtype=np.int32) if want_tail else None)
+        samples = np.empty((B, N, 2), dtype=np.float32) if want_samples else None
+        p = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+        rc = lib.drcvar_halfspaces_generated_f32(
+            p(mean_a), p(chol_a), int(seed) & (2 ** 64 - 1), int(index_offset), B, N, p(ego_a), p(h_a), *scal,
+            p(res.h), p(res.h_mean), p(res.g), p(res.cvar), p(res.var), p(res.g_star), p(res.status), p(res.tail_idx),
+            p(samples), _lib.HOST, None)
+        _lib.check(rc)
+        res.samples = samples
+        return res
+    import torch
+    dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+    f64 = dict(dtype=torch.float64, device=dev)
+    to = lambda a: None if a is None else torch.as_tensor(a, device=dev)  # noqa: E731
+    mean_t, chol_t, ego_t, h_t = to(mean_a), to(chol_a), to(ego_a), to(h_a)
+    res = HalfspaceBatch(
+        h=torch.empty((B, 2), **f64), h_mean=torch.empty((B, 2), **f64), g=torch.empty((B, 3), **f64),
+        cvar=torch.empty(B, **f64), var=torch.empty(B, **f64), g_star=torch.empty(B, **f64),
+        status=torch.zeros(B, dtype=torch.int32, device=dev),
+        tail_idx=torch.empty((B, kc), dtype=torch.int32, device=dev) if want_tail else None)
+    samples = torch.empty((B, N, 2), dtype=torch.float32, device=dev) if want_samples else None
+    if stream is None:
+        stream = torch.cuda.current_stream(dev).cuda_stream
+    elif hasattr(stream, "cuda_stream"):
+        stream = stream.cuda_stream
+    p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    rc = lib.drcvar_halfspaces_generated_f32(
+        p(mean_t), p(chol_t), int(seed) & (2 ** 64 - 1), int(index_offset), B, N, p(ego_t), p(h_t), *scal,
+        p(res.h), p(res.h_mean), p(res.g), p(res.cvar), p(res.var), p(res.g_star), p(res.status), p(res.tail_idx),
+        p(samples), dev.index if dev.index is not None else torch.cuda.current_device(), C.c_void_p(stream))
+    _lib.check(rc)
+    res.samples = samples
+    res._keepalive = (mean_t, chol_t, ego_t, h_t)   # inputs of the still-running launch
+    return res
 
 
 def launch_count() -> int:

@@ -132,6 +132,28 @@ int drcvar_trajectory_f64(const double* const* traj, int64_t n_obs, int64_t N, i
                           uint32_t flags,
                           double* h_out, double* h_mean_out, double* g_out, int32_t* status_out);
 
+/*
+ * Fused sample generation + halfspaces (fp32 samples, never materialised in HBM) — replaces, for B (obstacle, step)
+ * pairs at once, generate_obstacle_sample_trajectories                              simulation/obstacles.py:43-77
+ * followed by the halfspace entry points above: halfspace b draws N samples  mean[b] + L[b] z,  z ~ N(0, I2), inside the
+ * kernel's staging step and feeds them to the same sweeps.  The reference draws from numpy's sequential MT19937
+ * stream (not reproducible by independent threads); here z comes from counter-based Philox4x32-10 + Box-Muller with a
+ * fully specified fp32 arithmetic (oracle/sample_gen.py restates it bit for bit), counter = (pair index, index_offset +
+ * b), key = seed.
+ *   mean [B,2] double nominal positions (nominal_trajectory[t], obstacles.py:75; rounded to fp32 by the kernel)
+ *   chol [B,3] double (l00, l10, l11): lower Cholesky factor of noise_cov (obstacles.py:68-72); zeros = no noise (t = 0)
+ *   samples_out [B,N,2] float or NULL: dump of the generated samples (parity tests; costs the HBM write)
+ * Other arguments and outputs as drcvar_halfspaces_f32.  N must be <= drcvar_max_samples(4, device).
+ */
+int drcvar_halfspaces_generated_f32(const double* mean, const double* chol, uint64_t seed, int64_t index_offset,
+                                    int64_t B, int64_t N, const double* ego, const double* h_in,
+                                    double alpha, double delta, double epsilon, double r_robot, double r_obs,
+                                    uint32_t flags,
+                                    double* h_out, double* h_mean_out, double* g_out,
+                                    double* cvar_out, double* var_out, double* gstar_out,
+                                    int32_t* status_out, int32_t* tail_idx_out, float* samples_out,
+                                    int device, void* stream);
+
 /* Pinned host memory for callers that want full-speed host->device staging through DRCVAR_HOST calls. */
 void* drcvar_host_alloc(size_t bytes);
 void drcvar_host_free(void* p);
