@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--e2e-halfspaces", type=int, default=4096, help="host batch per end-to-end step")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-generated", action="store_true", help="skip the generate-mode leg (samples drawn in-kernel)")
     return ap.parse_args()
 
 
@@ -336,6 +337,55 @@ def run_ours(a):
     torch.cuda.synchronize(device)
     assert np.array_equal(hres.g, out.g[:Be].cpu().numpy()), "host path and device path disagree"
 
+    # ---- generate mode: the same batch with the samples drawn inside the kernel — no sample bytes
+    #      in HBM or over PCIe; compute-bound (Philox + Box-Muller), reported beside the headline, not instead of it
+    generated = None
+    if a.dtype == "f32" and not a.no_generated and N <= pkg.max_samples(np.float32):
+        import ctypes as C
+        lib = _lib.load()
+        g = torch.Generator(device=device).manual_seed(4242 + rank)
+        ang = torch.rand(B, generator=g, device=device, dtype=torch.float64) * (2 * np.pi)
+        rad = 1.0 + 4.0 * torch.rand(B, generator=g, device=device, dtype=torch.float64)
+        mean_t = torch.stack([rad * torch.cos(ang), rad * torch.sin(ang)], dim=1).contiguous()
+        chol_t = torch.tensor([0.1, 0.0, 0.1], dtype=torch.float64, device=device).repeat(B, 1).contiguous()
+        gout = pkg.HalfspaceBatch(h=torch.empty_like(out.h), h_mean=torch.empty_like(out.h_mean), g=torch.empty_like(out.g),
+                                  cvar=None, var=None, g_star=None, status=torch.zeros_like(out.status))
+
+        def gen_step():
+            rc = lib.drcvar_halfspaces_generated_f32(
+                mean_t.data_ptr(), chol_t.data_ptr(), 42, rank * B, B, N, ego.data_ptr(), None,
+                RISK["alpha"], RISK["delta"], RISK["epsilon"], RISK["robot_radius"], RISK["obstacle_radius"], 0,
+                gout.h.data_ptr(), gout.h_mean.data_ptr(), gout.g.data_ptr(), None, None, None,
+                gout.status.data_ptr(), None, None, local_rank, C.c_void_p(stream.cuda_stream))
+            _lib.check(rc)
+
+        gen_step()
+        torch.cuda.synchronize(device)
+        g_steps = 3
+        gs, ge = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gs.record(stream)
+        for _ in range(g_steps):
+            gen_step()
+        ge.record(stream)
+        torch.cuda.synchronize(device)
+        g_ms = gs.elapsed_time(ge) / g_steps
+        # end to end from HOST inputs (nominal positions, covariance, ego: 56 B per halfspace) to HOST outputs
+        Bg = min(B, 65536)
+        mean_h, ego_g = mean_t[:Bg].cpu().numpy(), np.zeros((Bg, 2))
+        cov_h = np.diag([0.01, 0.01])
+        pkg.compute_halfspaces_generated(mean_h, cov_h, N, 42, ego=ego_g, **RISK)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            gres = pkg.compute_halfspaces_generated(mean_h, cov_h, N, 42, ego=ego_g, **RISK)
+        g_e2e = 3 * Bg / (time.perf_counter() - t0)
+        generated = {"value": world * B / (g_ms * 1e-3), "unit": UNIT, "ms_per_launch": g_ms,
+                     "samples_per_s": world * B * N / (g_ms * 1e-3),
+                     "e2e": {"value": world * g_e2e, "unit": UNIT, "halfspaces_per_step": Bg,
+                             "h2d_bytes_per_step": Bg * 56, "d2h_bytes_per_step": Bg * 84},
+                     "fallback_halfspaces": int((gres.status & 2 != 0).sum()),
+                     "note": "samples drawn in-kernel (Philox4x32-10 + fp32 Box-Muller, oracle/sample_gen.py); "
+                             "per-rank numbers scaled by world size"}
+
     # ---- roofline of the (single) kernel
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -386,7 +436,7 @@ def run_ours(a):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "halfspaces_per_step": Be, "steps": e2e_steps,
                     "note": "compute_halfspaces() on pinned host numpy buffers: chunked H2D + kernel + D2H inside the timed region"},
-            "gpu_launches": launches, "clocks": clocks, "hbm_gbs_aggregate": achieved * world,
+            "gpu_launches": launches, "clocks": clocks, "hbm_gbs_aggregate": achieved * world, "generated": generated,
             "gather_ms": gather_ms, "parity_spot_check": parity,
             "status_fallback_halfspaces": int((out.status != 0).sum().item()),
         }
