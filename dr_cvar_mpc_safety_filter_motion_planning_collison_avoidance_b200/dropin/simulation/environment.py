@@ -65,10 +65,15 @@ class SafetyFilteringEnvironment:
                 for k in out:
                     out[k][t] = rows[t][k]
             return out
-        info = {'setup_time': 0.0, 'solve_time': time.time() - t0}
+        return self._wrap(h, hm, g, n_steps, len(trajs), time.time() - t0)
+
+    def _wrap(self, h, hm, g, n_steps, n_obs, elapsed):
+        out = {'mean': [[] for _ in range(n_steps)], 'cvar': [[] for _ in range(n_steps)],
+               'dr_cvar': [[] for _ in range(n_steps)]}
+        info = {'setup_time': 0.0, 'solve_time': elapsed}
         zero = {'setup_time': 0, 'solve_time': 0, 'solve_call_time': 0}
         for t in range(n_steps):
-            for i in range(len(trajs)):
+            for i in range(n_obs):
                 m = MeanSafeHalfspace(np.array(hm[t, i]), float(g[t, i, 0]))
                 m.info = dict(zero)
                 c = CVaRSafeHalfspace(np.array(h[t, i]), float(g[t, i, 1]))
@@ -79,6 +84,34 @@ class SafetyFilteringEnvironment:
                 out['cvar'][t].append(c)
                 out['dr_cvar'][t].append(d)
         return out
+
+    def compute_safe_halfspaces_for_nominal(self, obstacle_nominal_trajectories, ego_ref_trajectory, noise_cov,
+                                            n_samples, seed=0):
+        """
+        EXTENSION (not in the reference): the same result structure as
+        compute_safe_halfspaces_for_trajectory, but from the NOMINAL obstacle trajectories [T+1, 2] and the noise
+        covariance — the Monte-Carlo samples that generate_obstacle_sample_trajectories (simulation/obstacles.py:43-77)
+        would have produced (nominal[t] + N(0, noise_cov); exactly nominal[0] at t = 0, obstacles.py:63) are drawn
+        inside the kernel and never stored.  `seed` selects the Philox stream (oracle/sample_gen.py).
+        """
+        n_steps = min(len(ego_ref_trajectory), self.HORIZON)
+        noms = [np.asarray(tr, dtype=np.float64) for tr in obstacle_nominal_trajectories]
+        n_obs = len(noms)
+        if n_steps == 0 or n_obs == 0:
+            return {'mean': [[] for _ in range(n_steps)], 'cvar': [[] for _ in range(n_steps)],
+                    'dr_cvar': [[] for _ in range(n_steps)]}
+        ego_steps = np.stack([self.C @ np.asarray(ego_ref_trajectory[t]) for t in range(n_steps)])
+        mean = np.stack([noms[i][t, :2] for t in range(n_steps) for i in range(n_obs)])
+        ego = np.repeat(ego_steps, n_obs, axis=0)
+        chol = np.tile(_engine.cholesky2(np.asarray(noise_cov, dtype=np.float64)), (n_steps * n_obs, 1))
+        chol[:n_obs] = 0.0            # t = 0: every sample is the initial position
+        t0 = time.time()
+        res = _engine.compute_halfspaces_generated(mean, None, int(n_samples), int(seed), ego=ego, chol=chol,
+                                                   alpha=self.ALPHA, delta=self.DELTA, epsilon=self.EPSILON,
+                                                   robot_radius=self.ROBOT_RADIUS, obstacle_radius=self.OBSTACLE_RADIUS)
+        shape = (n_steps, n_obs)
+        return self._wrap(res.h.reshape(shape + (2,)), res.h_mean.reshape(shape + (2,)), res.g.reshape(shape + (3,)),
+                          n_steps, n_obs, time.time() - t0)
 
     def compute_distance_to_collision(self, ego_trajectory, obstacle_trajectories):
         """Minimum clearance (centre distance minus both radii) over the obstacles, per time step."""

@@ -169,15 +169,16 @@ def cholesky2(cov):
 
 
 def compute_halfspaces_generated(mean, noise_cov, n_samples, seed, ego=None, *, alpha, delta, epsilon, robot_radius,
-                                 obstacle_radius, h=None, index_offset=0, want_tail=False, want_samples=False,
-                                 flags=0, device=None, stream=None):
+                                 obstacle_radius, h=None, chol=None, index_offset=0, want_tail=False,
+                                 want_samples=False, flags=0, device=None, stream=None):
     """
     Fused Monte-Carlo sampling + halfspaces: halfspace b draws `n_samples` points  mean[b] + N(0, noise_cov[b])  inside
     the kernel (never stored) — generate_obstacle_sample_trajectories (simulation/obstacles.py:43-77) followed by the
     *SafeHalfspace.create calls (core/halfspaces.py:70-194), for B (obstacle, step) pairs in one launch.
 
-    mean: [B,2] nominal positions; noise_cov: [2,2] or [B,2,2]; seed: 64-bit key of the Philox stream; index_offset:
-    global index of halfspace 0 (so that a shard reproduces its slice of the unsharded batch).
+    mean: [B,2] nominal positions; noise_cov: [2,2] or [B,2,2] (or None with chol = [B,3] / [3] Cholesky factors
+    (l00, l10, l11) given directly); seed: 64-bit key of the Philox stream; index_offset: global index of halfspace 0
+    (so that a shard reproduces its slice of the unsharded batch).
     device=None: host path (numpy outputs); device=int or torch.device: outputs are torch CUDA tensors on it.
     Returns a HalfspaceBatch; with want_samples=True also the generated float32 samples [B,N,2] as `.samples`.
     """
@@ -186,9 +187,8 @@ def compute_halfspaces_generated(mean, noise_cov, n_samples, seed, ego=None, *, 
     B = mean_a.shape[0]
     if mean_a.shape != (B, 2):
         raise ValueError("mean must be [B,2]")
-    cov = np.asarray(noise_cov, dtype=np.float64)
     bcast = lambda x, w: np.array(np.broadcast_to(np.asarray(x, dtype=np.float64), (B, w)), order="C")  # noqa: E731
-    chol_a = bcast(cholesky2(cov), 3)
+    chol_a = bcast(cholesky2(np.asarray(noise_cov, dtype=np.float64)) if chol is None else chol, 3)
     N = int(n_samples)
     ego_a = None if ego is None else bcast(ego, 2)
     h_a = None if h is None else bcast(h, 2)

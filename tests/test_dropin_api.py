@@ -190,3 +190,33 @@ def test_trajectory_driver_matches_reference(dropin, golden_dir, name):
     for i in range(n_obs):
         assert row["dr_cvar"][i].g_tilde == hs["dr_cvar"][t][i].g_tilde
         assert np.array_equal(row["cvar"][i].h, hs["cvar"][t][i].h)
+
+
+@pytest.mark.gpu
+def test_nominal_trajectory_extension(dropin, golden_dir):
+    """compute_safe_halfspaces_for_nominal (SURVEY §8-f2 extension): same structure as the trajectory driver, values equal
+    to the halfspaces of the samples the generator is specified to draw (oracle/sample_gen.py)."""
+    from oracle import closed_form as cf
+    from oracle import sample_gen as sg
+    env_mod = dropin["simulation.environment"]
+    z = np.load(os.path.join(golden_dir, "multi_obstacle_seed42.npz"))
+    alpha, delta, eps, rr, ro, horizon = (float(v) for v in z["params"])
+    env = env_mod.SafetyFilteringEnvironment(rr, ro, int(horizon), 0.2, alpha, delta, eps)
+    traj = z["sample_trajectories"]                               # [n_obs, N, T+1, 2]: nominal = sample mean at t = 0
+    n_obs, T1 = traj.shape[0], traj.shape[2]
+    nominal = [np.stack([traj[i][0, 0, :] + 0.05 * t * np.array([1.0, -0.5]) for t in range(T1)]) for i in range(n_obs)]
+    cov = np.array([[0.01, 0.002], [0.002, 0.01]])
+    n, seed = 2000, 17
+    res = env.compute_safe_halfspaces_for_nominal(nominal, z["x_ref"], cov, n, seed=seed)
+    n_steps = min(len(z["x_ref"]), int(horizon))
+    assert set(res) == {"mean", "cvar", "dr_cvar"} and len(res["dr_cvar"]) == n_steps and len(res["cvar"][0]) == n_obs
+    chol = sg.cholesky2(cov)
+    for t in (0, 1, n_steps - 1):
+        for i in range(n_obs):
+            b = t * n_obs + i
+            s = sg.generate(nominal[i][t][None], np.zeros((1, 3)) if t == 0 else chol[None], n, seed, index_offset=b)[0]
+            o = cf.halfspace(s, z["x_ref"][t][:2], alpha, delta, eps, rr, ro)
+            hs = res["dr_cvar"][t][i]
+            assert np.array_equal(hs.h, o.h) and abs(hs.g_tilde - o.g_dr) <= 1e-6
+            assert abs(res["cvar"][t][i].g_tilde - o.g_cvar) <= 1e-6
+            assert abs(res["mean"][t][i].g_tilde - o.g_mean) <= 1e-9
