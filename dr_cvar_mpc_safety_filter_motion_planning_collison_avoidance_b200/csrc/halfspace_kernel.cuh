@@ -2,23 +2,26 @@
 //
 // One CTA per (scenario, obstacle, step) halfspace, persistent over the batch; two CTAs per SM.
 // A CTA is a team of 8 "sweep" warps plus a "finisher" warp and a "director" warp, pipelined over consecutive
-// halfspaces through two parity buffers and shared-memory mbarriers, so the select + epilogue of halfspace j and
-// the slow IEEE div/sqrt chain of the canonical direction overlap the load and sweeps around them.
+// halfspaces through two parity buffers, so the select + epilogue of halfspace j, the slow IEEE div/sqrt chain of the
+// canonical direction and the bulk copy of halfspace j+1 overlap the sweeps around them.  Synchronisation: transaction
+// mbarriers for the TMA copies, mbarriers empty[]/hdone[] towards the team, named barrier 1 inside the team, named
+// barriers 2-7 (bar.arrive / bar.sync) towards the two helper warps (they block in hardware, no polling).
 //
 // sweep team, per halfspace:
-//   stage   N samples -> shared memory with cp.async.bulk (TMA bulk copy, mbarrier completion) or a strided loader
-//   sweep A canonical lane sums of the coordinates (fp32 inputs: shifted by the first sample, packed fp32 lane
-//           partials, fp64 cross-lane tree; fp64 inputs: fp64 throughout) + second moments              -> mean m
-//   h       warp 0: fp64-accurate (1e-15) direction WITHOUT div/sqrt, only to place the window and the fp32 thresholds
+//   stage   N samples -> shared memory: cp.async.bulk (TMA, issued by the director as soon as the slot is free), a strided
+//           loader, or — generate mode — drawn in place (sample_gen.cuh)
+//   sweep A starts on the first 32 KB chunk; canonical lane sums of the coordinates (fp32 inputs: shifted by the first
+//           sample, packed fp32 lane partials, fp64 cross-lane tree; fp64 inputs: fp64 throughout) + second moments
+//   window  warp 0: fp32 direction h_a with a rigorous bound |h_a - h| <= err_h, statistical window [t_lo, t_hi] around
+//           the predicted kc-th largest loss, fp32 classification thresholds
 //           director warp (concurrently): the canonical h = unit(m - ego) with IEEE div/sqrt  core/geometry.py:35-53
 //           and the mean halfspace                                                            core/halfspaces.py:70-106
-//   sweep B classify every sample against a statistical window [t_lo, t_hi] around the expected kc-th largest
-//           loss.  fp32 inputs: a rigorous fp32 bound decides "surely above" (count + shifted coordinate sums; the
-//           loss sum follows from linearity), "surely below" (ignored) or "needs the exact fp64 loss" (a bit in a
-//           per-thread mask).  fp64 inputs: exact canonical loss for every sample.
-//   phase 2 masked samples are compacted per warp and get the canonical fp64 loss L_i = -(h.xi_i) (no FMA); window
-//           losses go to warp-private candidate lists and a 256-bucket histogram; the sample slot is released
-//           and the next halfspace's bulk copy is issued
+//   sweep B classify every sample.  fp32 inputs: the rigorous fp32 bound decides "surely above" (count + shifted
+//           coordinate sums; the loss sum follows from linearity), "surely below" (ignored) or "needs the exact fp64
+//           loss" (a bit in a per-thread mask).  fp64 inputs: exact canonical loss for every sample.
+//   phase 2 masked samples are copied to per-warp lists (2a), THE SLOT IS RELEASED, then they get the canonical fp64
+//           loss L_i = -(h.xi_i) (no FMA) (2b); window losses go to warp-private candidate lists and a 256-bucket
+//           histogram
 // finisher warp, per halfspace:
 //   select  exact kc-th largest loss T: histogram scan -> bucket -> all-pairs rank inside the bucket
 //   finish  CVaR = (sum_{L>T} L + (k_f - #{L>T}) T) / k_f  and the CVaR / DR-CVaR offsets  core/risk_metrics.py:84-338
