@@ -204,7 +204,6 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   a.gen_samples_out = c.gen_samples_out;
   if (c.gen_mean != nullptr) {
     if (sizeof(T) != 4) return fail(DRCVAR_ERR_UNSUPPORTED, "generate mode is fp32 only");
-    if (streaming) return fail(DRCVAR_ERR_UNSUPPORTED, "generate mode needs N <= drcvar_max_samples(4): N=%lld", c.N);
     a.bulk = 0;   // the sweep team fills the slot itself
   }
 
@@ -216,6 +215,9 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   const bool tail = c.tail_idx_out != nullptr;
   if (streaming) {
     auto sk = tail ? streaming_kernel<T, true> : streaming_kernel<T, false>;
+    if constexpr (sizeof(T) == 4) {
+      if (c.gen_mean != nullptr) sk = tail ? streaming_kernel<float, true, true> : streaming_kernel<float, false, true>;
+    }
     a.bulk = contiguous && (reinterpret_cast<uintptr_t>(c.samples) % 16 == 0) &&
              ((static_cast<size_t>(c.stride_b) * sizeof(T)) % 16 == 0 || c.B == 1);   // 16-byte vector loads
     int s_per_sm = 0;

@@ -21,7 +21,7 @@ constexpr int kStreamWarps = kStreamThreads / 32;
 constexpr int kStreamCand = 256;    // window candidates per warp (doubles)
 constexpr int kStreamUnroll = 8;    // 16-byte loads in flight per thread in pass 2
 
-template <typename T, bool kTail>
+template <typename T, bool kTail, bool kGen = false>
 __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const KernelArgs a) {
   using V2 = typename Vec2<T>::type;
   constexpr bool kF32 = sizeof(T) == 4;
@@ -46,15 +46,63 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
 
   for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
     const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
-    const bool vec = a.bulk != 0;   // contiguous (x, y) pairs, 16-byte aligned rows: vector loads
-    auto load = [&](int i) {
-      if (vec) return reinterpret_cast<const V2*>(base)[i];
-      const T* p = base + static_cast<long long>(i) * a.stride_n;
-      V2 v;
-      v.x = p[0];
-      v.y = p[a.stride_c];
-      return v;
+    const bool vec = kGen || a.bulk != 0;   // contiguous (x, y) pairs, 16-byte aligned rows: vector loads
+    // generate mode (fp32): the samples are drawn on the fly in EVERY pass (sample_gen.cuh; one Philox call per pair)
+    float gmx = 0.f, gmy = 0.f, gl00 = 0.f, gl10 = 0.f, gl11 = 0.f;
+    unsigned long long gb = 0;
+    if constexpr (kGen) {
+      gmx = static_cast<float>(a.gen_mean[2 * b]);
+      gmy = static_cast<float>(a.gen_mean[2 * b + 1]);
+      gl00 = static_cast<float>(a.gen_chol[3 * b]);
+      gl10 = static_cast<float>(a.gen_chol[3 * b + 1]);
+      gl11 = static_cast<float>(a.gen_chol[3 * b + 2]);
+      gb = static_cast<unsigned long long>(b + a.gen_index_offset);
+    }
+    auto gen_pair = [&](int j) {   // samples 2j, 2j+1
+      const Philox4 r = philox4x32_10(static_cast<uint32_t>(j), static_cast<uint32_t>(gb), static_cast<uint32_t>(gb >> 32),
+                                      kGenStreamTag, static_cast<uint32_t>(a.gen_seed),
+                                      static_cast<uint32_t>(a.gen_seed >> 32));
+      const float2 s0 = gen_sample(r.x, r.y, gmx, gmy, gl00, gl10, gl11);
+      const float2 s1 = gen_sample(r.z, r.w, gmx, gmy, gl00, gl10, gl11);
+      return make_float4(s0.x, s0.y, s1.x, s1.y);
     };
+    auto load4 = [&](int j) {      // 16-byte item j (vec path only)
+      if constexpr (kGen) {
+        return gen_pair(j);
+      } else {
+        return reinterpret_cast<const float4*>(base)[j];
+      }
+    };
+    auto load = [&](int i) {
+      if constexpr (kGen) {
+        const float4 p = gen_pair(i >> 1);
+        V2 v;
+        v.x = (i & 1) ? p.z : p.x;
+        v.y = (i & 1) ? p.w : p.y;
+        return v;
+      } else {
+        if (vec) return reinterpret_cast<const V2*>(base)[i];
+        const T* p = base + static_cast<long long>(i) * a.stride_n;
+        V2 v;
+        v.x = p[0];
+        v.y = p[a.stride_c];
+        return v;
+      }
+    };
+    if constexpr (kGen) {
+      if (a.gen_samples_out) {   // parity tests: dump the generated samples (extra pass)
+        float* dump = a.gen_samples_out + static_cast<size_t>(b) * N * 2;
+        for (int j = tid; j < (N + 1) / 2; j += kStreamThreads) {
+          const float4 p = gen_pair(j);
+          dump[4 * j] = p.x;
+          dump[4 * j + 1] = p.y;
+          if (2 * j + 1 < N) {
+            dump[4 * j + 2] = p.z;
+            dump[4 * j + 3] = p.w;
+          }
+        }
+      }
+    }
     // ------------------------------------------------------------------ pass 1: canonical lane sums + moments
     // Thread (half, lt) owns slot half*256 + lt: rows r = half, half+2, ... in increasing order (the canonical order).
     const V2 first = load(0);
@@ -72,10 +120,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
       };
       int r = half;
       if (vec) {
-        const float4* g4 = reinterpret_cast<const float4*>(base);
 #pragma unroll 8
         for (; r < full_rows; r += 2) {
-          const float4 v = g4[r * kSweepThreads + lt];
+          const float4 v = load4(r * kSweepThreads + lt);
           body(make_float2(v.x, v.y), acc0);
           body(make_float2(v.z, v.w), acc1);
         }
@@ -270,7 +317,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
             if constexpr (kF32) {
               const int i0 = 2 * it;
               if (vec && i0 + 1 < N) {
-                const float4 p = reinterpret_cast<const float4*>(base)[it];
+                const float4 p = kGen ? gen_pair(it) : reinterpret_cast<const float4*>(base)[it];
                 v[u][0] = make_float2(p.x, p.y);
                 v[u][1] = make_float2(p.z, p.w);
                 ok[u][0] = ok[u][1] = true;

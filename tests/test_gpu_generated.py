@@ -86,6 +86,22 @@ def test_generated_bad_arguments(eng):
     from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
     mean = np.zeros((1, 2))
     with pytest.raises(_lib.DrcvarError):
-        eng.compute_halfspaces_generated(mean, np.eye(2), 10 ** 6, seed=1, **P)       # does not fit one CTA's slot
-    with pytest.raises(_lib.DrcvarError):
         eng.compute_halfspaces_generated(mean, np.eye(2), 100, seed=1, **dict(P, alpha=0.0))
+
+
+def test_generated_large_n_streaming(eng):
+    """N beyond one CTA's shared memory (BASELINE config 5, N = 100 000): the streaming kernel re-draws the samples in
+    every pass; same bit-exact samples, same halfspace bars."""
+    n, B = 100000, 3
+    assert n > eng.max_samples(np.float32)
+    mean, ego = scenario(B, 77)
+    cov = np.array([[0.01, -0.002], [-0.002, 0.015]])
+    res = eng.compute_halfspaces_generated(mean, cov, n, seed=5, ego=ego, want_tail=True, want_samples=True, **P)
+    want = sg.generate(mean, sg.cholesky2(cov), n, seed=5)
+    assert np.array_equal(res.samples.view(np.uint32), want.view(np.uint32))
+    fast = eng.compute_halfspaces_generated(mean, cov, n, seed=5, ego=ego, **P)
+    for b in range(B):
+        o = cf.halfspace(want[b], ego[b], P["alpha"], P["delta"], P["epsilon"], P["robot_radius"], P["obstacle_radius"])
+        assert np.array_equal(res.h[b], o.h) and res.var[b] == o.var and np.array_equal(res.tail_idx[b], o.tail_idx)
+        assert abs(res.cvar[b] - o.cvar) <= ABS32 and abs(fast.cvar[b] - o.cvar) <= ABS32
+    assert np.array_equal(fast.var, res.var)
