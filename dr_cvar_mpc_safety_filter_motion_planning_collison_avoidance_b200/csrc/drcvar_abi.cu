@@ -182,8 +182,11 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   const double cand_capacity = streaming ? 0.5 * kStreamCand * kStreamWarps : 0.6 * kCandCap * kSweepWarps;
   if (!(c.flags & DRCVAR_FLAG_GENERAL_ONLY))
     a.use_window = plan_window(c.N, kc, n_sigma, cand_capacity, &a.z_lo, &a.z_hi) ? 1 : 0;
-  a.z_lo_f = static_cast<float>(a.z_lo);
-  a.z_hi_f = static_cast<float>(a.z_hi);
+  a.z_mid_f = static_cast<float>(0.5 * (a.z_lo + a.z_hi));
+  a.z_half_f = static_cast<float>(0.5 * (a.z_hi - a.z_lo));
+  // learned-centre mode (non-Gaussian samples): the Basu cancellation does not hold and the density at the quantile is
+  // unknown -> 2.5 x the Gaussian half-width, capped by what the per-warp lists hold
+  a.z_half_adapt_f = 2.5f * a.z_half_f;
   const size_t row_bytes = static_cast<size_t>(c.N) * 2 * sizeof(T);
   const bool contiguous = (c.stride_c == 1 && c.stride_n == 2);
   a.bulk = contiguous && !(c.flags & DRCVAR_FLAG_NO_BULK) && (reinterpret_cast<uintptr_t>(c.samples) % 16 == 0) &&

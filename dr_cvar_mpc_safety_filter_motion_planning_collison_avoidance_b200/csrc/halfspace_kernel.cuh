@@ -83,7 +83,8 @@ struct KernelArgs {
   int kc;
   int use_window;
   double z_lo, z_hi;
-  float z_lo_f, z_hi_f;   // the same, rounded once on the host
+  float z_mid_f, z_half_f;   // window centre / half-width in z units (Gaussian plan, host), fp32
+  float z_half_adapt_f;      // half-width used once the window centre is LEARNED from earlier halfspaces (non-Gaussian data)
   int bulk;
   double* h_out;
   double* h_mean_out;
@@ -113,7 +114,11 @@ struct Ctl {                        // one per parity buffer
   int window_ok, nonfinite, degenerate, c_tot;
   int mode, cnt_hi, status;
   int acc_hi, acc_nc;              // team totals (shared atomics): sure-above count, window candidates
-  int pad;
+  int z_learned;                   // the window centre is taken from z_est (set after two consecutive misses; persists)
+  int z_missrun;                   // consecutive window misses of this parity chain
+  float z_est;                     // learned (T - mean loss) / sigma of the CTA's earlier halfspaces
+  float pm, sigma, pad_f;          // this halfspace: mean and sigma of p = h_a.(xi - first) (window placement)
+  double c_shift;                  // h_a . first
 };
 
 struct Bars {
@@ -472,7 +477,12 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     mbar_fence_init();
   }
   for (int i = tid; i < 2 * kHistBuckets; i += kThreads) hist_base[i] = 0;
-  if (tid < 2) ctl_base[tid].small_n = 0;
+  if (tid < 2) {
+    ctl_base[tid].small_n = 0;
+    ctl_base[tid].z_learned = 0;
+    ctl_base[tid].z_missrun = 0;
+    ctl_base[tid].z_est = 0.f;
+  }
   __syncthreads();
 
   const uint32_t copy_bytes = static_cast<uint32_t>(static_cast<size_t>(N) * sizeof(V2));
@@ -606,6 +616,13 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           const double s_tot = ((s_e + s_lin) + s3t) + s4;
           const int c_tot = cnt_hi + c3t + c4;
           write_risk_outputs(a, b, ctl, false, s_tot, c_tot, T_thr, ctl->status);
+          {   // learn where the threshold sits in z units: (T - mean loss) / sigma = (pm + T + c) / sigma
+            ctl->z_missrun = 0;
+            if (ctl->z_learned) {
+              const float zT = (ctl->pm + static_cast<float>(T_thr + ctl->c_shift)) / ctl->sigma;
+              ctl->z_est = 0.5f * (ctl->z_est + zT);
+            }
+          }
           if (kTail) {
             ctl->T = T_thr;
             ctl->c_tot = c_tot;
@@ -1015,7 +1032,17 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
                       (rows_all * kPerLoad <= 32 * kMaskWords);
       // thresholds in shifted coordinates, p = h_a.(xi - first):  a_lo <-> t_lo,  a_hi <-> t_hi  (a_hi <= a_lo)
       const float pm = fmaf(h1f, mr1f, h0f * mr0f);
-      const float a_lo = pm - a.z_lo_f * sigma, a_hi = pm - a.z_hi_f * sigma;
+      // window centre: the Gaussian plan of the host, or — after two CONSECUTIVE misses in this CTA's parity chain, i.e.
+      // samples that are evidently not Gaussian — the position measured on the earlier halfspaces, with a wider window.
+      // (Isolated misses, 3e-5 of Gaussian halfspaces, change nothing: the window of a halfspace then depends on its own
+      // samples only and results are independent of how the batch is composed.)  The state was written two halfspaces
+      // ago in this parity buffer, so the choice is deterministic.  Speed only, never T or the tail set.
+      float z_c = a.z_mid_f, z_w = a.z_half_f;
+      if (ctl->z_learned && isfinite(ctl->z_est)) {
+        z_c = ctl->z_est;
+        z_w = a.z_half_adapt_f;
+      }
+      const float a_lo = pm - (z_c - z_w) * sigma, a_hi = pm - (z_c + z_w) * sigma;
       const double c = static_cast<double>(h0f) * f0 + static_cast<double>(h1f) * f1;   // h_a . first
       const double t_lo = __dadd_rn(-static_cast<double>(a_lo) - c, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
       const double t_hi = __dadd_rn(-static_cast<double>(a_hi) - c, 0.0);
@@ -1043,6 +1070,9 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         ctl->key_lo = klo;
         ctl->hist_shift = bits > 8 ? bits - 8 : 0;
         ctl->window_ok = window_ok;
+        ctl->pm = pm;
+        ctl->sigma = sigma;
+        ctl->c_shift = c;
         ctl->acc_hi = 0;
         ctl->acc_nc = 0;
       }
@@ -1362,7 +1392,13 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         c_tot += iscr[w];
         s_tot += red[w];
       }
-      if (tid == 0) write_risk_outputs(a, b, ctl, nonfinite, s_tot, c_tot, T_thr, status);
+      if (tid == 0) {
+        write_risk_outputs(a, b, ctl, nonfinite, s_tot, c_tot, T_thr, status);
+        if (ctl->window_ok && !nonfinite) {   // the window was placed and missed: measure where the threshold really is
+          ctl->z_est = (ctl->pm + static_cast<float>(T_thr + ctl->c_shift)) / ctl->sigma;
+          if (++ctl->z_missrun >= 2) ctl->z_learned = 1;
+        }
+      }
     } else if (kTail) {
       c_tot = ctl->c_tot;
     }

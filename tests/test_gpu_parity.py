@@ -241,6 +241,38 @@ def test_adversarial_scales_and_offsets(eng, dtype):
             assert abs(res.cvar[b] - o.cvar) <= tol, (h, cases[b], res.cvar[b], o.cvar)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_learned_window_on_non_gaussian_samples(eng, dtype):
+    """Laplace / uniform noise: the Gaussian window plan misses; after two consecutive misses a CTA learns where the
+    threshold sits and goes back to the single-sweep path.  Thresholds stay exact, values within the usual bars."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    rng = np.random.RandomState(31)
+    n, B = 4096, 296 * 8                        # 8 halfspaces per CTA of the persistent grid
+    mu = rng.uniform(1.0, 4.0, size=(B, 1, 2))
+    lap = rng.laplace(scale=0.1 / np.sqrt(2), size=(B // 2, n, 2))
+    uni = rng.uniform(-0.1 * np.sqrt(3), 0.1 * np.sqrt(3), size=(B - B // 2, n, 2))
+    s = (mu + np.concatenate([lap, uni])).astype(dtype)
+    s = s[rng.permutation(B)]                   # mixed distributions inside every CTA's chain
+    ego = np.zeros((B, 2))
+    p = dict(PARAMS, alpha=0.1, epsilon=0.01)
+    res = eng.compute_halfspaces(s, ego, **p)
+    exact = eng.compute_halfspaces(s, ego, flags=_lib.FLAG_GENERAL_ONLY, **p)
+    assert np.array_equal(res.var, exact.var) and np.array_equal(res.h, exact.h)
+    tol = 1e-6 if dtype == np.float32 else 1e-9
+    assert np.abs(res.g - exact.g).max() <= tol and np.abs(res.cvar - exact.cvar).max() <= tol
+    frac_general = float(((res.status & _lib.STATUS_GENERAL) != 0).mean())
+    assert 0.0 < frac_general < 0.75, frac_general          # the first halfspaces of a chain miss, the later ones hit
+    for b in list(range(0, 8)) + list(range(B - 8, B)):
+        o = cf.halfspace(s[b], ego[b], p["alpha"], p["delta"], p["epsilon"], p["robot_radius"], p["obstacle_radius"])
+        assert res.var[b] == o.var and np.array_equal(res.h[b], o.h), b
+        assert abs(res.cvar[b] - o.cvar) <= tol * max(1.0, abs(o.cvar)), b
+    tail = eng.compute_halfspaces(s[:600], ego[:600], want_tail=True, **p)
+    assert np.array_equal(tail.var, exact.var[:600])
+    for b in (0, 299, 599):
+        o = cf.halfspace(s[b], ego[b], p["alpha"], p["delta"], p["epsilon"], p["robot_radius"], p["obstacle_radius"])
+        assert np.array_equal(tail.tail_idx[b], o.tail_idx), b
+
+
 def test_degenerate_direction_and_nonfinite(eng):
     from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
     s = np.tile(np.array([[4.0, 0.0]]), (3, 20, 1))
