@@ -184,6 +184,8 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
     a.use_window = plan_window(c.N, kc, n_sigma, cand_capacity, &a.z_lo, &a.z_hi) ? 1 : 0;
   a.z_mid_f = static_cast<float>(0.5 * (a.z_lo + a.z_hi));
   a.z_half_f = static_cast<float>(0.5 * (a.z_hi - a.z_lo));
+  a.z_lo_f = a.z_mid_f - a.z_half_f;
+  a.z_hi_f = a.z_mid_f + a.z_half_f;
   // learned-centre mode (non-Gaussian samples): the Basu cancellation does not hold and the density at the quantile is
   // unknown -> 2.5 x the Gaussian half-width, capped by what the per-warp lists hold
   a.z_half_adapt_f = 2.5f * a.z_half_f;

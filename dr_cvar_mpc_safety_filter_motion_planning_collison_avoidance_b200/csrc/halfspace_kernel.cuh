@@ -84,6 +84,7 @@ struct KernelArgs {
   int use_window;
   double z_lo, z_hi;
   float z_mid_f, z_half_f;   // window centre / half-width in z units (Gaussian plan, host), fp32
+  float z_lo_f, z_hi_f;      // = z_mid_f -/+ z_half_f
   float z_half_adapt_f;      // half-width used once the window centre is LEARNED from earlier halfspaces (non-Gaussian data)
   int bulk;
   double* h_out;
@@ -117,8 +118,12 @@ struct Ctl {                        // one per parity buffer
   int z_learned;                   // the window centre is taken from z_est (set after two consecutive misses; persists)
   int z_missrun;                   // consecutive window misses of this parity chain
   float z_est;                     // learned (T - mean loss) / sigma of the CTA's earlier halfspaces
-  float pm, sigma, pad_f;          // this halfspace: mean and sigma of p = h_a.(xi - first) (window placement)
-  double c_shift;                  // h_a . first
+  float z_lo_use, z_hi_use;        // window bounds in z units for the NEXT halfspace of this parity (Gaussian plan or learned)
+  float pad_f;
+  struct __align__(16) Place {     // this halfspace (one 16-byte store): mean and sigma of p = h_a.(xi - first), h_a . first
+    float pm, sigma;
+    double c_shift;
+  } pl;
 };
 
 struct Bars {
@@ -481,6 +486,8 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     ctl_base[tid].small_n = 0;
     ctl_base[tid].z_learned = 0;
     ctl_base[tid].z_missrun = 0;
+    ctl_base[tid].z_lo_use = a.z_mid_f - a.z_half_f;
+    ctl_base[tid].z_hi_use = a.z_mid_f + a.z_half_f;
     ctl_base[tid].z_est = 0.f;
   }
   __syncthreads();
@@ -619,8 +626,13 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           {   // learn where the threshold sits in z units: (T - mean loss) / sigma = (pm + T + c) / sigma
             ctl->z_missrun = 0;
             if (ctl->z_learned) {
-              const float zT = (ctl->pm + static_cast<float>(T_thr + ctl->c_shift)) / ctl->sigma;
-              ctl->z_est = 0.5f * (ctl->z_est + zT);
+              const float zT = (ctl->pl.pm + static_cast<float>(T_thr + ctl->pl.c_shift)) / ctl->pl.sigma;
+              const float ze = 0.5f * (ctl->z_est + zT);
+              ctl->z_est = ze;
+              if (isfinite(ze)) {
+                ctl->z_lo_use = ze - a.z_half_adapt_f;
+                ctl->z_hi_use = ze + a.z_half_adapt_f;
+              }
             }
           }
           if (kTail) {
@@ -1032,17 +1044,18 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
                       (rows_all * kPerLoad <= 32 * kMaskWords);
       // thresholds in shifted coordinates, p = h_a.(xi - first):  a_lo <-> t_lo,  a_hi <-> t_hi  (a_hi <= a_lo)
       const float pm = fmaf(h1f, mr1f, h0f * mr0f);
-      // window centre: the Gaussian plan of the host, or — after two CONSECUTIVE misses in this CTA's parity chain, i.e.
-      // samples that are evidently not Gaussian — the position measured on the earlier halfspaces, with a wider window.
-      // (Isolated misses, 3e-5 of Gaussian halfspaces, change nothing: the window of a halfspace then depends on its own
-      // samples only and results are independent of how the batch is composed.)  The state was written two halfspaces
-      // ago in this parity buffer, so the choice is deterministic.  Speed only, never T or the tail set.
-      float z_c = a.z_mid_f, z_w = a.z_half_f;
-      if (ctl->z_learned && isfinite(ctl->z_est)) {
-        z_c = ctl->z_est;
-        z_w = a.z_half_adapt_f;
+      // window bounds in z units: the Gaussian plan of the host, or — after two CONSECUTIVE misses in this CTA's parity
+      // chain, i.e. samples that are evidently not Gaussian — the position measured on the earlier halfspaces with a wider
+      // window (z_lo_use / z_hi_use, maintained by the finisher and the fallback path).  Isolated misses, 3e-5 of
+      // Gaussian halfspaces, change nothing: the window of a halfspace then depends on its own samples only and results
+      // are independent of how the batch is composed.  The state was written two halfspaces ago in this parity buffer,
+      // so the choice is deterministic.  Speed only, never T or the tail set.
+      float zlo = a.z_lo_f, zhi = a.z_hi_f;
+      if (ctl->z_learned) {   // rare, warp-uniform
+        zlo = ctl->z_lo_use;
+        zhi = ctl->z_hi_use;
       }
-      const float a_lo = pm - (z_c - z_w) * sigma, a_hi = pm - (z_c + z_w) * sigma;
+      const float a_lo = pm - zlo * sigma, a_hi = pm - zhi * sigma;
       const double c = static_cast<double>(h0f) * f0 + static_cast<double>(h1f) * f1;   // h_a . first
       const double t_lo = __dadd_rn(-static_cast<double>(a_lo) - c, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
       const double t_hi = __dadd_rn(-static_cast<double>(a_hi) - c, 0.0);
@@ -1070,9 +1083,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         ctl->key_lo = klo;
         ctl->hist_shift = bits > 8 ? bits - 8 : 0;
         ctl->window_ok = window_ok;
-        ctl->pm = pm;
-        ctl->sigma = sigma;
-        ctl->c_shift = c;
+        ctl->pl = Ctl::Place{pm, sigma, c};
         ctl->acc_hi = 0;
         ctl->acc_nc = 0;
       }
@@ -1395,8 +1406,13 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       if (tid == 0) {
         write_risk_outputs(a, b, ctl, nonfinite, s_tot, c_tot, T_thr, status);
         if (ctl->window_ok && !nonfinite) {   // the window was placed and missed: measure where the threshold really is
-          ctl->z_est = (ctl->pm + static_cast<float>(T_thr + ctl->c_shift)) / ctl->sigma;
+          const float ze = (ctl->pl.pm + static_cast<float>(T_thr + ctl->pl.c_shift)) / ctl->pl.sigma;
+          ctl->z_est = ze;
           if (++ctl->z_missrun >= 2) ctl->z_learned = 1;
+          if (ctl->z_learned && isfinite(ze)) {
+            ctl->z_lo_use = ze - a.z_half_adapt_f;
+            ctl->z_hi_use = ze + a.z_half_adapt_f;
+          }
         }
       }
     } else if (kTail) {
