@@ -342,6 +342,25 @@ def test_large_n_streaming_kernel(eng, dtype):
         assert np.array_equal(c.var, a.var)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_sample_counts_around_the_shared_memory_limit(eng, dtype):
+    """N = drcvar_max_samples (the largest resident slot, one CTA per SM), one more (first streaming size), and ragged
+    sizes just below: same bars on both sides of the kernel switch."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    nmax = eng.max_samples(dtype)
+    rng = np.random.RandomState(41)
+    p = dict(PARAMS, alpha=0.1, epsilon=0.01)
+    for n in (nmax, nmax + 1, nmax - 1, nmax - 511):
+        s = (rng.uniform(-3, 3, size=(3, 1, 2)) + 0.1 * rng.standard_normal((3, n, 2))).astype(dtype)
+        ego = rng.uniform(-1, 1, size=(3, 2))
+        res = eng.compute_halfspaces(s, ego, want_tail=True, **p)
+        check_batch(res, s, ego, p)
+        fast = eng.compute_halfspaces(s, ego, **p)
+        assert np.array_equal(fast.var, res.var) and np.array_equal(fast.h, res.h)
+        gen = eng.compute_halfspaces(s, ego, flags=_lib.FLAG_GENERAL_ONLY | _lib.FLAG_NO_BULK, **p)
+        assert np.array_equal(gen.var, res.var)
+
+
 def test_run_to_run_determinism(eng):
     rng = np.random.RandomState(5)
     s = (np.array([1.0, 3.0]) + 0.1 * rng.standard_normal((300, 10000, 2))).astype(np.float32)
