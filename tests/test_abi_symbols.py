@@ -75,3 +75,26 @@ def test_argument_validation_precedes_any_cuda_call(lib):
     rc = L.drcvar_halfspaces_f32(s.ctypes.data, 1, 0, 8, 2, 1, None, None, 0.2, 0.1, 0.1, 0.3, 0.3, 0,
                                  h.ctypes.data, None, g.ctypes.data, None, None, None, None, None, lib.HOST, None)
     assert rc == lib.ERR_INVALID
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """The product path must fail loudly (never fall back to the oracle or any CPU code) when there is no CUDA device."""
+    import numpy as np
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present: the compute path runs")
+    import dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 as pkg
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    risk = dict(alpha=0.2, delta=0.1, epsilon=0.1, robot_radius=0.3, obstacle_radius=0.3)
+    with pytest.raises(_lib.DrcvarError):
+        pkg.compute_halfspaces(np.zeros((1, 8, 2)), None, **risk)
+    with pytest.raises(_lib.DrcvarError):
+        pkg.compute_halfspaces_generated(np.zeros((1, 2)), np.eye(2), 100, 1, **risk)
+    # the shipped package never imports the test-only oracle
+    import glob
+    import os
+    pkg_dir = os.path.dirname(pkg.__file__)
+    for path in glob.glob(os.path.join(pkg_dir, "**", "*.py"), recursive=True):
+        src = open(path).read()
+        assert "import oracle" not in src and "from oracle" not in src, path
