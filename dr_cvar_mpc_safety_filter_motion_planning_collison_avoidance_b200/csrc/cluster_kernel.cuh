@@ -1,0 +1,646 @@
+// cluster_kernel.cuh — single-read kernel for sample counts beyond one CTA's shared memory (N > kOctantMinN; BASELINE
+// config 5, N = 100 000): ONE THREAD-BLOCK CLUSTER PER HALFSPACE, the samples spread over the distributed shared memory
+// of its 2 / 4 / 8 CTAs (one CTA per SM, each holding 8 / C octants of the canonical mean contract).
+//
+// Per CTA: 16 sweep warps (the team) + a producer warp + a director warp, persistent over the batch (cluster-strided).
+//   producer  1-D TMA bulk copies (cp.async.bulk, 32 KB chunks, one transaction mbarrier per chunk) of this CTA's part of
+//             halfspace b+1, each chunk issued the moment all 16 sweep warps have released it in sweep B of halfspace b
+//   sweep A   trails the chunks as they land: canonical lane sums per octant (shifted by the first sample, packed fp32
+//             partials, fp64 tree) + second moments
+//   exchange1 every CTA sends its octant totals + moments to every CTA (st.shared::cluster + remote mbarrier arrive with
+//             release.cluster); all CTAs then compute the SAME window / fp32 thresholds (warp 0) and the SAME canonical
+//             direction (director warp: IEEE div / sqrt chain, off the team's path)              core/geometry.py:35-53
+//   sweep B   fp32 classification with the rigorous bound of the resident kernel: surely above the window (count +
+//             shifted coordinate sums; the loss sum follows from linearity), surely below (ignored), or "needs the exact
+//             fp64 loss" -> raw copy into a per-warp list; every chunk is handed back to the producer as soon as the warp
+//             is past it
+//   phase 2b  canonical fp64 loss of the listed samples; window candidates are compacted per warp
+//   exchange2 partial counts / sums and the candidates go to the halfspace's leader CTA (rotating) through DSMEM
+//   finish    leader: exact rank among the candidates (radix narrowing), CVaR, offsets          core/risk_metrics.py:84-338
+// A window miss (3e-5 of Gaussian halfspaces), an overflow or non-finite data put the halfspace on a redo list that the
+// streaming kernel processes right after (exact general select, same arithmetic contract).  Tail indices and the
+// generate mode stay on the streaming kernel.  fp32 inputs only.
+#pragma once
+
+#include "halfspace_kernel.cuh"
+
+namespace drcvar {
+
+constexpr int kClTeamWarps = 16;
+constexpr int kClTeam = kClTeamWarps * 32;        // 512: thread t owns slot t of the canonical tree
+constexpr int kClThreads = kClTeam + 64;          // + producer warp + director warp
+constexpr int kClProducerWarp = kClTeamWarps;
+constexpr int kClDirectorWarp = kClTeamWarps + 1;
+constexpr int kClMaxCtas = 8;
+constexpr int kClMaxChunks = 8;                   // 32 KB chunks of one CTA's part (<= 227 KB)
+constexpr int kClWarpList = 48;                   // masked samples (raw copies) per sweep warp
+constexpr int kClPool = 1024;                     // candidate losses gathered at the leader (all CTAs together)
+constexpr int kClX1 = 12;                         // doubles per source CTA in exchange 1
+constexpr uint32_t kClLaneRow = 8192;             // one 16-byte load per team thread
+
+struct ClShared {
+  double pool[kClPool];                           // leader: candidates [src][cap]; sweep A: tree exchange (first 4 KB)
+  double x1[2][kClMaxCtas][kClX1];                // exchange 1 [parity][src]: octant totals (x, y)..., qxx, qyy, qxy, bound2
+  double x2[kClMaxCtas][4];                       // exchange 2 at the leader [src]: n_above, sum dx, sum dy, ncand (-1: overflow)
+  float2 list[kClTeamWarps][kClWarpList];
+  double red[kClTeamWarps * 2];
+  double octtot[kOctants * 2];
+  double wsum[kClTeamWarps * 4];
+  float mom[kClTeamWarps * 4];
+  int wcnt[kClTeamWarps * 2];
+  unsigned hist[kHistBuckets];
+  double small[kResolveMax];
+  Ctl ctl[2];
+  unsigned long long full[kClMaxChunks];
+  unsigned long long free_[kClMaxChunks];
+  unsigned long long xbar1[2];
+  unsigned long long xbar2;
+  unsigned long long hdone[2];
+};
+
+__host__ __device__ inline size_t cluster_smem_bytes(long long n, int ctas) {
+  const size_t part = static_cast<size_t>(kOctants / ctas) * static_cast<size_t>(octant_bytes(n, 4));
+  return ((part + 127) & ~static_cast<size_t>(127)) + sizeof(ClShared) + 128;
+}
+
+// ---------------------------------------------------------------------------------------------- cluster PTX helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cl_team_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kClTeam) : "memory"); }
+
+__device__ __forceinline__ double pair_tree8(const double* t_in, int stride) {
+  double t[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) t[g] = t_in[g * stride];
+#pragma unroll
+  for (int n = 8; n > 1; n >>= 1)
+#pragma unroll
+    for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);
+  return t[0];
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const KernelArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = a.N;
+  const int C = a.cl_ctas, O = kOctants / C;
+  const int lgO = 31 - __clz(O);   // O = 1, 2 or 4
+  const uint32_t rank = cluster_ctarank();
+  const long long q = blockIdx.x / C, n_clusters = gridDim.x / C;
+  const uint32_t oct_b = static_cast<uint32_t>(octant_bytes(N, 4));
+  const uint32_t row_b = static_cast<uint32_t>(N) * 8u;
+  const uint32_t part_cap = static_cast<uint32_t>(O) * oct_b;
+  const uint32_t part_lo = rank * part_cap;
+  const uint32_t part_b = row_b > part_lo ? (row_b - part_lo < part_cap ? row_b - part_lo : part_cap) : 0u;
+  const int n_chunks = static_cast<int>((part_b + kBulkChunk - 1) / kBulkChunk);
+  const size_t slot_bytes = (static_cast<size_t>(part_cap) + 127) & ~static_cast<size_t>(127);
+  ClShared* sh = reinterpret_cast<ClShared*>(smem_raw + slot_bytes);
+  const int cap = kClPool / C;   // candidates per source CTA in the leader's pool
+
+  if (tid == 0) {
+    for (int j = 0; j < kClMaxChunks; ++j) {
+      mbar_init(&sh->full[j], 1);
+      mbar_init(&sh->free_[j], kClTeamWarps);
+    }
+    mbar_init(&sh->xbar1[0], C);
+    mbar_init(&sh->xbar1[1], C);
+    mbar_init(&sh->xbar2, kClTeamWarps * C);
+    mbar_init(&sh->hdone[0], 1);
+    mbar_init(&sh->hdone[1], 1);
+    mbar_fence_init();
+  }
+  if (tid < 2 * kClTeamWarps) sh->wcnt[tid] = 0;
+  __syncthreads();
+  cluster_sync_all();   // every CTA's barriers exist before anybody arrives on them remotely
+
+  // ============================================================================================ producer warp
+  if (warp == kClProducerWarp) {
+    if (lane == 0) {
+      int it = 0;
+      for (long long b = q; b < a.B; b += n_clusters, ++it) {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.samples) +
+                                   static_cast<size_t>(b) * a.stride_b * sizeof(float) + part_lo;
+        for (int j = 0; j < n_chunks; ++j) {
+          if (it > 0) mbar_wait(&sh->free_[j], (it - 1) & 1);
+          const uint32_t off = static_cast<uint32_t>(j) * kBulkChunk;
+          const uint32_t n = part_b - off < kBulkChunk ? part_b - off : kBulkChunk;
+          mbar_expect_tx(&sh->full[j], n);
+          bulk_g2s(smem_raw + off, src + off, n, &sh->full[j]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ============================================================================================ director warp
+  if (warp == kClDirectorWarp) {
+    int it = 0;
+    for (long long b = q; b < a.B; b += n_clusters, ++it) {
+      const int par = it & 1;
+      Ctl* ctl = &sh->ctl[par];
+      const float* fp = reinterpret_cast<const float*>(a.samples) + b * a.stride_b;
+      const double f0 = static_cast<double>(__ldg(fp)), f1 = static_cast<double>(__ldg(fp + 1));
+      mbar_wait_cluster(&sh->xbar1[par], (it >> 1) & 1);
+      // octant o = src * O + k lives at x1[par][src][2k + j]
+      double w[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double t[kOctants];
+#pragma unroll
+        for (int o = 0; o < kOctants; ++o) t[o] = sh->x1[par][o >> lgO][2 * (o & (O - 1)) + j];
+#pragma unroll
+        for (int n = kOctants; n > 1; n >>= 1)
+#pragma unroll
+          for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);
+        w[j] = t[0];
+      }
+      const double m0 = __dadd_rn(f0, __ddiv_rn(w[0], static_cast<double>(N)));
+      const double m1 = __dadd_rn(f1, __ddiv_rn(w[1], static_cast<double>(N)));
+      int nonfinite = !(isfinite(m0) && isfinite(m1));
+      int degenerate = 0;
+      double h0, h1;
+      if (a.h_in != nullptr) {
+        h0 = a.h_in[2 * b];
+        h1 = a.h_in[2 * b + 1];
+      } else {
+        const double e0 = a.ego ? a.ego[2 * b] : 0.0, e1 = a.ego ? a.ego[2 * b + 1] : 0.0;
+        const double d0 = __dsub_rn(m0, e0), d1 = __dsub_rn(m1, e1);
+        const double nrm = norm2_canon(d0, d1);
+        if (nrm < 1e-10) {
+          h0 = 1.0;
+          h1 = 0.0;
+          degenerate = 1;
+        } else {
+          h0 = __ddiv_rn(d0, nrm);
+          h1 = __ddiv_rn(d1, nrm);
+        }
+      }
+      nonfinite |= !(isfinite(h0) && isfinite(h1));
+      if (lane == 0) {
+        ctl->h0 = h0; ctl->h1 = h1; ctl->m0 = m0; ctl->m1 = m1;
+        ctl->nonfinite = nonfinite;
+        ctl->degenerate = degenerate;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&sh->hdone[par]);
+        if (static_cast<int>(rank) == it % C) write_mean_outputs(a, b, m0, m1);
+      }
+    }
+    return;
+  }
+
+  // ============================================================================================ sweep team
+  const float4* slot4 = reinterpret_cast<const float4*>(smem_raw);
+  const uint32_t toff = 16u * tid;
+  const uint32_t woff = 16u * (tid & ~31);   // first byte of this warp inside a lane-row
+  float2* wlist = sh->list[warp];
+  int it = 0;
+  uint32_t x2_uses = 0;   // exchanges this CTA has received as the leader (phase of xbar2)
+  for (long long b = q; b < a.B; b += n_clusters, ++it) {
+    const int par = it & 1;
+    const int leader = it % C;
+    Ctl* ctl = &sh->ctl[par];
+    const float* fp = reinterpret_cast<const float*>(a.samples) + b * a.stride_b;
+    const float2 first = make_float2(__ldg(fp), __ldg(fp + 1));
+    double pre0 = 0.0, pre1 = 0.0;   // warp 0: ego (or the explicit normal), fetched early
+    if (warp == 0) {
+      if (a.h_in != nullptr) {
+        pre0 = a.h_in[2 * b];
+        pre1 = a.h_in[2 * b + 1];
+      } else if (a.ego != nullptr) {
+        pre0 = a.ego[2 * b];
+        pre1 = a.ego[2 * b + 1];
+      }
+    }
+    const float2 nf = make_float2(-first.x, -first.y);
+    const uint32_t fpar = it & 1;
+    int have = 0;   // chunks of halfspace b known to have landed
+    auto wait_upto = [&](uint32_t byte_off) {
+      const int c = static_cast<int>(byte_off >> 15);
+      while (have <= c) {
+        mbar_wait_spin(&sh->full[have], fpar);
+        ++have;
+      }
+    };
+
+    // ------------------------------------------------------------------ sweep A: canonical lane sums per octant + moments
+    float2 sq = make_float2(0.f, 0.f);
+    float sxy = 0.f;
+    for (int k = 0; k < O; ++k) {
+      const uint32_t ob = static_cast<uint32_t>(k) * oct_b;
+      const uint32_t oe = part_b < ob + oct_b ? part_b : ob + oct_b;
+      const uint32_t len = oe > ob ? oe - ob : 0u;
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+      auto body = [&](const float4 v) {
+        const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nf), d1 = __fadd2_rn(make_float2(v.z, v.w), nf);
+        acc0 = __fadd2_rn(acc0, d0);
+        acc1 = __fadd2_rn(acc1, d1);
+        sq = __ffma2_rn(d0, d0, sq);
+        sq = __ffma2_rn(d1, d1, sq);
+        sxy = fmaf(d0.x, d0.y, sxy);
+        sxy = fmaf(d1.x, d1.y, sxy);
+      };
+      const uint32_t n_lr = (len + kClLaneRow - 1) / kClLaneRow;
+      uint32_t lr = 0;
+      for (; (lr + 4) * kClLaneRow <= len; lr += 4) {
+        const uint32_t base = ob + lr * kClLaneRow + toff;
+        wait_upto(base + 3 * kClLaneRow);
+        const float4 v0 = slot4[base >> 4], v1 = slot4[(base + kClLaneRow) >> 4], v2 = slot4[(base + 2 * kClLaneRow) >> 4],
+                     v3 = slot4[(base + 3 * kClLaneRow) >> 4];
+        body(v0);
+        body(v1);
+        body(v2);
+        body(v3);
+      }
+      for (; lr < n_lr; ++lr) {   // last rows of the octant: possibly ragged; samples beyond the end count as `first` (d = +0)
+        const uint32_t off = ob + lr * kClLaneRow + toff;
+        float4 v = make_float4(first.x, first.y, first.x, first.y);
+        if (off + 8 <= oe) {
+          wait_upto(off);
+          v = slot4[off >> 4];
+          if (off + 16 > oe) {
+            v.z = first.x;
+            v.w = first.y;
+          }
+        }
+        body(v);
+      }
+      // slot tid = adjacent fp32 lanes widened and added; u[j] = s[j] + s[j + 256]; butterfly per group of 32; pair tree of 8
+      const double s_x = __dadd_rn(static_cast<double>(acc0.x), static_cast<double>(acc1.x));
+      const double s_y = __dadd_rn(static_cast<double>(acc0.y), static_cast<double>(acc1.y));
+      double* xch = sh->pool;
+      if (tid >= 256) {
+        xch[2 * (tid - 256)] = s_x;
+        xch[2 * (tid - 256) + 1] = s_y;
+      }
+      cl_team_sync();
+      if (tid < 256) {
+        const double txy = warp_sum_canon_pair(__dadd_rn(s_x, xch[2 * tid]), __dadd_rn(s_y, xch[2 * tid + 1]), lane);
+        if (lane < 2) sh->red[warp * 2 + lane] = txy;
+      }
+      cl_team_sync();
+      if (tid < 2) sh->octtot[2 * k + tid] = pair_tree8(sh->red + tid, 2);
+    }
+    {
+      const float mq = warp_sum_any4(sq.x, sq.y, sxy, 0.f, lane);   // lanes & 3: 0 qxx, 1 qxy, 2 qyy
+      const unsigned bnd = __reduce_max_sync(kFull, __float_as_uint(sq.x + sq.y));
+      if (lane < 3) sh->mom[warp * 4 + lane] = mq;
+      if (lane == 3) sh->mom[warp * 4 + 3] = __uint_as_float(bnd);
+    }
+    cl_team_sync();
+    // ------------------------------------------------------------------ exchange 1: totals + moments to every CTA
+    if (tid < C) {   // thread d serves destination CTA d
+      double qxx = 0.0, qxy = 0.0, qyy = 0.0;
+      float b2 = 0.f;
+      for (int w = 0; w < kClTeamWarps; ++w) {
+        qxx += static_cast<double>(sh->mom[w * 4]);
+        qxy += static_cast<double>(sh->mom[w * 4 + 1]);
+        qyy += static_cast<double>(sh->mom[w * 4 + 2]);
+        b2 = fmaxf(b2, sh->mom[w * 4 + 3]);
+      }
+      const uint32_t dst = mapa_u32(smem_u32(&sh->x1[par][rank][0]), static_cast<uint32_t>(tid));
+      for (int i = 0; i < 2 * O; ++i) st_cluster_f64(dst + 8u * i, sh->octtot[i]);
+      st_cluster_f64(dst + 64, qxx);
+      st_cluster_f64(dst + 72, qyy);
+      st_cluster_f64(dst + 80, qxy);
+      st_cluster_f64(dst + 88, static_cast<double>(b2));
+      mbar_arrive_remote(mapa_u32(smem_u32(&sh->xbar1[par]), static_cast<uint32_t>(tid)));
+    }
+    mbar_wait_cluster(&sh->xbar1[par], (it >> 1) & 1);
+
+    // ------------------------------------------------------------------ window placement (warp 0; identical in every CTA)
+    if (warp == 0) {
+      double w[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double t[kOctants];
+#pragma unroll
+        for (int o = 0; o < kOctants; ++o) t[o] = sh->x1[par][o >> lgO][2 * (o & (O - 1)) + j];
+#pragma unroll
+        for (int n = kOctants; n > 1; n >>= 1)
+#pragma unroll
+          for (int g = 0; g < n / 2; ++g) t[g] = t[2 * g] + t[2 * g + 1];
+        w[j] = t[0];
+      }
+      double qd[3] = {0.0, 0.0, 0.0};
+      float b2 = 0.f;
+      for (int s = 0; s < C; ++s) {
+        qd[0] += sh->x1[par][s][8];
+        qd[1] += sh->x1[par][s][9];
+        qd[2] += sh->x1[par][s][10];
+        b2 = fmaxf(b2, static_cast<float>(sh->x1[par][s][11]));
+      }
+      const double inv_n = 1.0 / static_cast<double>(N);
+      const float inv_nf = static_cast<float>(inv_n);
+      const double f0 = static_cast<double>(first.x), f1 = static_cast<double>(first.y);
+      const double mr0 = w[0] * inv_n, mr1 = w[1] * inv_n;   // mean relative to the first sample
+      const double m0 = mr0 + f0, m1 = mr1 + f1;
+      const float mr0f = static_cast<float>(mr0), mr1f = static_cast<float>(mr1);
+      bool usable = isfinite(m0) && isfinite(m1);
+      float h0f, h1f, err_h;
+      if (a.h_in != nullptr) {
+        h0f = static_cast<float>(pre0);
+        h1f = static_cast<float>(pre1);
+        err_h = fmaxf(fabsf(h0f), fabsf(h1f)) * 1.2e-7f + 1.5e-45f;
+      } else {
+        const double d0 = m0 - pre0, d1 = m1 - pre1;   // pre = ego
+        const float d0f = static_cast<float>(d0), d1f = static_cast<float>(d1);
+        const float n2 = fmaf(d0f, d0f, d1f * d1f);
+        if (n2 < 1.01e-20f) usable = false;   // degenerate direction (or too close to the switch): redo list
+        const float rn = rsqrtf(n2);
+        h0f = d0f * rn;
+        h1f = d1f * rn;
+        // fp32 chain: 2 conversions, fma, rsqrt (2 ulp), multiply  ->  < 5e-7; plus the fp64 cancellation in m - ego
+        const float mag = static_cast<float>(fabs(m0) + fabs(m1) + fabs(pre0) + fabs(pre1));
+        err_h = 1e-6f + 4e-15f * mag * rn;
+        usable = usable && isfinite(rn) && rn > 0.f && isfinite(mag);
+      }
+      usable = usable && isfinite(h0f) && isfinite(h1f) && err_h < 1e-3f;
+      const float cxx = static_cast<float>(qd[0]) * inv_nf - mr0f * mr0f, cyy = static_cast<float>(qd[1]) * inv_nf - mr1f * mr1f,
+                  cxy = static_cast<float>(qd[2]) * inv_nf - mr0f * mr1f;
+      const float var_l = h0f * h0f * cxx + 2.0f * h0f * h1f * cxy + h1f * h1f * cyy;
+      const float sigma = sqrt_approx(var_l);   // placement only
+      int window_ok = a.use_window && usable && (var_l > 0.f) && isfinite(sigma);
+      // thresholds in shifted coordinates, p = h_a.(xi - first):  a_lo <-> t_lo,  a_hi <-> t_hi  (a_hi <= a_lo)
+      const float pm = fmaf(h1f, mr1f, h0f * mr0f);
+      const float a_lo = pm - a.z_lo_f * sigma, a_hi = pm - a.z_hi_f * sigma;
+      const double c = static_cast<double>(h0f) * f0 + static_cast<double>(h1f) * f1;   // h_a . first
+      const double t_lo = __dadd_rn(-static_cast<double>(a_lo) - c, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
+      const double t_hi = __dadd_rn(-static_cast<double>(a_hi) - c, 0.0);
+      // rigorous fp32 classification bound: see halfspace_kernel.cuh (window placement); dmax from the per-thread sums
+      const float dmax = sqrt_approx(b2) * 1.0001f;
+      const float af0 = fabsf(static_cast<float>(f0)) * 1.0001f, af1 = fabsf(static_cast<float>(f1)) * 1.0001f;
+      const float habs = fabsf(h0f) + fabsf(h1f);
+      const float eps = (habs * (af0 + af1 + dmax)) * 1e-15f + err_h * 1.5f * (af0 + af1 + 2.0f * dmax);
+      const float bound = habs * dmax * 1.9073486e-06f + 1.1754944e-38f + eps * 1.0001f;
+      const float thr_keep = a_lo + (bound + fabsf(a_lo) * 2.3841858e-07f);
+      const float thr_above = a_hi - (bound + fabsf(a_hi) * 2.3841858e-07f);
+      const unsigned long long klo = key_of(t_lo), khi = key_of(t_hi);
+      window_ok = window_ok && isfinite(thr_keep) && isfinite(thr_above) && (khi >= klo) && (thr_above <= thr_keep) &&
+                  isfinite(t_lo) && isfinite(t_hi);
+      if (lane == 0) {
+        ctl->f0 = f0; ctl->f1 = f1;
+        ctl->t_lo = t_lo;
+        ctl->t_hi = t_hi;
+        ctl->h0f = h0f; ctl->h1f = h1f; ctl->thr_keep = thr_keep; ctl->thr_above = thr_above;
+        ctl->key_lo = klo;
+        ctl->window_ok = window_ok;
+      }
+    }
+    cl_team_sync();  // S2
+    const bool window = ctl->window_ok != 0;
+
+    int rel = 0;   // chunks this warp has handed back (warp-uniform)
+    auto release_upto = [&](int c) {   // chunks [rel, c) are no longer read by this warp
+      if (c > rel) {
+        __syncwarp();
+        if (lane == 0)
+          for (int j = rel; j < c; ++j) mbar_arrive(&sh->free_[j]);
+        rel = c;
+      }
+    };
+    if (!window) {
+      // no usable window (degenerate / non-finite / tiny tails): the streaming kernel redoes this halfspace
+      release_upto(n_chunks);
+      if (tid == 0 && static_cast<int>(rank) == leader) a.redo_list[atomicAdd(a.redo_count, 1)] = static_cast<int>(b);
+      mbar_wait(&sh->hdone[par], (it >> 1) & 1);   // the director is done with x1[par] / ctl[par] before we run ahead
+      continue;
+    }
+
+    // ------------------------------------------------------------------ sweep B: fp32 classification, raw copies of the rest
+    float ax = 0.f, ay = 0.f, cf = 0.f;   // "surely above": shifted coordinate sums and count
+    int n_list = 0;                       // warp-uniform
+    {
+      const float h0f = ctl->h0f, h1f = ctl->h1f, thr_keep = ctl->thr_keep, thr_above = ctl->thr_above;
+      const unsigned lt_mask = (1u << lane) - 1u;
+      auto extract = [&](unsigned mk, const float4& v0, const float4& v1, const float4& v2, const float4& v3) {
+        // mask bit 2u + e <-> sample e of row u.  Exclusive prefix of the per-lane counts (0..8) by ballot planes.
+        const int mine = __popc(mk);
+        const unsigned p0 = __ballot_sync(kFull, mine & 1), p1 = __ballot_sync(kFull, mine & 2),
+                       p2 = __ballot_sync(kFull, mine & 4), p3 = __ballot_sync(kFull, mine & 8);
+        int pos = n_list + __popc(p0 & lt_mask) + 2 * __popc(p1 & lt_mask) + 4 * __popc(p2 & lt_mask) + 8 * __popc(p3 & lt_mask);
+        n_list += __popc(p0) + 2 * __popc(p1) + 4 * __popc(p2) + 8 * __popc(p3);
+        if (mk) {
+          const float4 vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (mk & (1u << (2 * u))) {
+              if (pos < kClWarpList) wlist[pos] = make_float2(vv[u].x, vv[u].y);
+              ++pos;
+            }
+            if (mk & (2u << (2 * u))) {
+              if (pos < kClWarpList) wlist[pos] = make_float2(vv[u].z, vv[u].w);
+              ++pos;
+            }
+          }
+        }
+      };
+      auto classify4 = [&](const float4& v, unsigned& mk, unsigned bit, bool ok0, bool ok1) {
+        const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nf), d1 = __fadd2_rn(make_float2(v.z, v.w), nf);
+        float p0 = fmaf(h1f, d0.y, h0f * d0.x), p1 = fmaf(h1f, d1.y, h0f * d1.x);
+        if (!ok0) p0 = __int_as_float(0x7f800000);
+        if (!ok1) p1 = __int_as_float(0x7f800000);
+        classify_f32(p0, thr_above, thr_keep, d0.x, d0.y, ax, ay, cf, mk, bit);
+        classify_f32(p1, thr_above, thr_keep, d1.x, d1.y, ax, ay, cf, mk, bit + bit);
+      };
+      for (int k = 0; k < O; ++k) {
+        const uint32_t ob = static_cast<uint32_t>(k) * oct_b;
+        const uint32_t oe = part_b < ob + oct_b ? part_b : ob + oct_b;
+        const uint32_t len = oe > ob ? oe - ob : 0u;
+        const uint32_t n_lr = (len + kClLaneRow - 1) / kClLaneRow;
+        uint32_t lr = 0;
+        for (; (lr + 4) * kClLaneRow <= len; lr += 4) {
+          const uint32_t base = ob + lr * kClLaneRow + toff;
+          release_upto(static_cast<int>((ob + lr * kClLaneRow + woff) >> 15));
+          const float4 v0 = slot4[base >> 4], v1 = slot4[(base + kClLaneRow) >> 4], v2 = slot4[(base + 2 * kClLaneRow) >> 4],
+                       v3 = slot4[(base + 3 * kClLaneRow) >> 4];
+          unsigned mk = 0u;
+          classify4(v0, mk, 1u, true, true);
+          classify4(v1, mk, 4u, true, true);
+          classify4(v2, mk, 16u, true, true);
+          classify4(v3, mk, 64u, true, true);
+          if (__any_sync(kFull, mk != 0u)) extract(mk, v0, v1, v2, v3);
+        }
+        if (lr < n_lr) {   // last (up to 4) rows of the octant, possibly ragged
+          release_upto(static_cast<int>((ob + lr * kClLaneRow + woff) >> 15));
+          float4 vv[4];
+          unsigned mk = 0u;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t off = ob + (lr + u) * kClLaneRow + toff;
+            const bool ok0 = (lr + u < n_lr) && (off + 8 <= oe), ok1 = (lr + u < n_lr) && (off + 16 <= oe);
+            vv[u] = ok0 ? slot4[off >> 4] : make_float4(first.x, first.y, first.x, first.y);
+            classify4(vv[u], mk, 1u << (2 * u), ok0, ok1);
+          }
+          if (__any_sync(kFull, mk != 0u)) extract(mk, vv[0], vv[1], vv[2], vv[3]);
+        }
+      }
+    }
+    release_upto(n_chunks);   // the whole part is back with the producer: halfspace b+1 streams in behind us
+
+    // ------------------------------------------------------------------ phase 2b: exact loss of the listed samples
+    mbar_wait(&sh->hdone[par], (it >> 1) & 1);
+    const double h0 = ctl->h0, h1 = ctl->h1;
+    const bool nonfinite = ctl->nonfinite != 0;
+    const double t_lo = ctl->t_lo, t_hi = ctl->t_hi;
+    bool overflow = n_list > kClWarpList || nonfinite;
+    int nc = 0;   // window candidates of this warp, compacted in place at the head of its list (as doubles)
+    if (!overflow) {
+      double* wcand = reinterpret_cast<double*>(wlist);
+      for (int k0 = 0; k0 < n_list; k0 += 32) {
+        const int kk = k0 + lane;
+        const bool active = kk < n_list;
+        double L = 0.0;
+        float2 v = first;
+        if (active) {
+          v = wlist[kk];
+          L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
+        }
+        const bool up = active && (L > t_hi);
+        const bool cd = active && !up && (L >= t_lo);
+        if (up) {  // inside the fp32 uncertainty band but exactly above the window: joins the "above" set
+          cf += 1.0f;
+          ax += v.x - first.x;
+          ay += v.y - first.y;
+        }
+        const unsigned bal = __ballot_sync(kFull, cd);   // (all lanes have read their entry: the ballot orders the overwrite)
+        if (cd) wcand[nc + __popc(bal & ((1u << lane) - 1u))] = L;
+        nc += __popc(bal);
+      }
+    }
+    {
+      const int wc = __reduce_add_sync(kFull, static_cast<int>(cf));
+      const double sx = warp_sum_any(static_cast<double>(ax)), sy = warp_sum_any(static_cast<double>(ay));
+      if (lane == 0) {
+        sh->wsum[warp * 4] = static_cast<double>(wc);
+        sh->wsum[warp * 4 + 1] = sx;
+        sh->wsum[warp * 4 + 2] = sy;
+        sh->wcnt[warp * 2] = nc;
+        sh->wcnt[warp * 2 + 1] = overflow ? 1 : 0;
+      }
+    }
+    cl_team_sync();  // S3
+    // ------------------------------------------------------------------ exchange 2: everything goes to the leader CTA
+    {
+      int before = 0, total = 0, ovf = 0;
+#pragma unroll
+      for (int w = 0; w < kClTeamWarps; ++w) {
+        const int c = sh->wcnt[w * 2];
+        before += w < warp ? c : 0;
+        total += c;
+        ovf |= sh->wcnt[w * 2 + 1];
+      }
+      if (total > cap) ovf = 1;
+      if (!ovf) {
+        const double* wcand = reinterpret_cast<const double*>(wlist);
+        const uint32_t dst = mapa_u32(smem_u32(&sh->pool[rank * cap + before]), static_cast<uint32_t>(leader));
+        for (int j = lane; j < nc; j += 32) st_cluster_f64(dst + 8u * j, wcand[j]);
+      }
+      if (tid == 0) {
+        double n_above = 0.0, sdx = 0.0, sdy = 0.0;
+        for (int w = 0; w < kClTeamWarps; ++w) {
+          n_above += sh->wsum[w * 4];
+          sdx += sh->wsum[w * 4 + 1];
+          sdy += sh->wsum[w * 4 + 2];
+        }
+        const uint32_t dst = mapa_u32(smem_u32(&sh->x2[rank][0]), static_cast<uint32_t>(leader));
+        st_cluster_f64(dst, n_above);
+        st_cluster_f64(dst + 8, sdx);
+        st_cluster_f64(dst + 16, sdy);
+        st_cluster_f64(dst + 24, ovf ? -1.0 : static_cast<double>(total));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&sh->xbar2), static_cast<uint32_t>(leader)));
+    }
+
+    // ------------------------------------------------------------------ finish (leader CTA of this halfspace)
+    if (static_cast<int>(rank) == leader) {
+      mbar_wait_cluster(&sh->xbar2, x2_uses & 1u);
+      ++x2_uses;
+      double n_above = 0.0, sdx = 0.0, sdy = 0.0;
+      int ncand = 0, ovf = 0;
+      for (int s = 0; s < C; ++s) {
+        n_above += sh->x2[s][0];
+        sdx += sh->x2[s][1];
+        sdy += sh->x2[s][2];
+        const double c = sh->x2[s][3];
+        if (c < 0.0) ovf = 1; else ncand += static_cast<int>(c);
+      }
+      const int cnt_hi = static_cast<int>(n_above);
+      const bool fast = !ovf && !nonfinite && cnt_hi < a.kc && a.kc <= cnt_hi + ncand;
+      if (fast) {
+        auto each = [&](auto&& f) {
+          for (int s = 0; s < C; ++s) {
+            const int n_s = static_cast<int>(sh->x2[s][3]);
+            for (int j = tid; j < n_s; j += kClTeam) f(sh->pool[s * cap + j]);
+          }
+        };
+        const double T_thr = select_rank(each, [] { cl_team_sync(); }, warp == 0, tid, kClTeam, key_of(t_lo), key_of(t_hi),
+                                         a.kc - cnt_hi, sh->hist, sh->small, ctl);
+        int c4 = 0;
+        double s4 = 0.0;
+        each([&](double L) {
+          if (L > T_thr) {
+            ++c4;
+            s4 += L;
+          }
+        });
+        const int wc4 = __reduce_add_sync(kFull, c4);
+        const double ws4 = warp_sum_any(s4);
+        if (lane == 0) {
+          sh->wsum[warp * 4] = static_cast<double>(wc4);
+          sh->wsum[warp * 4 + 1] = ws4;
+        }
+        cl_team_sync();
+        if (tid == 0) {
+          double cc = 0.0, ss = 0.0;
+          for (int w = 0; w < kClTeamWarps; ++w) {
+            cc += sh->wsum[w * 4];
+            ss += sh->wsum[w * 4 + 1];
+          }
+          // loss sum of the "surely above" set by linearity, xi_i = f + d_i:  sum_i -(h.xi_i) = -(h0 (n f0 + sum dx) + h1 (n f1 + sum dy))
+          const double s_lin = -(h0 * (n_above * ctl->f0 + sdx) + h1 * (n_above * ctl->f1 + sdy));
+          const int status = ctl->degenerate ? kStatusDegenerate : 0;
+          write_risk_outputs(a, b, ctl, false, s_lin + ss, cnt_hi + static_cast<int>(cc), T_thr, status);
+        }
+      } else if (tid == 0) {
+        a.redo_list[atomicAdd(a.redo_count, 1)] = static_cast<int>(b);
+      }
+      cl_team_sync();   // wsum / pool / hist are free again
+    }
+  }
+  cluster_sync_all();   // nobody leaves while a peer may still write into its shared memory
+}
+
+}  // namespace drcvar

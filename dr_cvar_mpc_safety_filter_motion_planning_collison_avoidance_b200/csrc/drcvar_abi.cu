@@ -16,6 +16,7 @@
 
 #include "halfspace_kernel.cuh"
 #include "streaming_kernel.cuh"
+#include "cluster_kernel.cuh"
 
 namespace {
 
@@ -218,6 +219,75 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   a.phase_cycles = nullptr;
 #endif
   const bool tail = c.tail_idx_out != nullptr;
+  a.cl_ctas = 0;
+  a.redo_count = nullptr;
+  a.redo_list = nullptr;
+  if (streaming && !(c.flags & (DRCVAR_FLAG_FORCE_STREAMING | DRCVAR_FLAG_NO_CLUSTER | DRCVAR_FLAG_GENERAL_ONLY)) &&
+      sizeof(T) == 4 && !tail && c.gen_mean == nullptr && c.N > kOctantMinN && c.B < 0x7fffffffLL) {
+    // ---- cluster / DSMEM kernel: one cluster of 2 / 4 / 8 CTAs per halfspace, every sample read from HBM once
+    const bool bulk_ok = contiguous && (reinterpret_cast<uintptr_t>(c.samples) % 16 == 0) &&
+                         ((static_cast<size_t>(c.stride_b) * sizeof(T)) % 16 == 0 || c.B == 1) && (row_bytes % 16 == 0);
+    int ctas = 0;
+    for (int cc = 2; cc <= kClMaxCtas; cc *= 2)
+      if (cluster_smem_bytes(c.N, cc) <= static_cast<size_t>(di->max_smem_optin)) {
+        ctas = cc;
+        break;
+      }
+    double zl = 0, zh = 0;
+    if (bulk_ok && ctas && plan_window(c.N, kc, c.N, 0.6 * kClPool, &zl, &zh)) {
+      KernelArgs ca = a;
+      ca.use_window = 1;
+      ca.z_lo = zl;
+      ca.z_hi = zh;
+      ca.z_mid_f = static_cast<float>(0.5 * (zl + zh));
+      ca.z_half_f = static_cast<float>(0.5 * (zh - zl));
+      ca.z_lo_f = ca.z_mid_f - ca.z_half_f;
+      ca.z_hi_f = ca.z_mid_f + ca.z_half_f;
+      ca.bulk = 1;
+      ca.cl_ctas = ctas;
+      const size_t csmem = cluster_smem_bytes(c.N, ctas);
+      CUDA_TRY(cudaFuncSetAttribute(cluster_kernel_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(csmem)));
+      int* redo = nullptr;   // [0] = count, [1..] = halfspace indices; stream-ordered allocation
+      CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&redo), sizeof(int) * (static_cast<size_t>(c.B) + 1), stream));
+      CUDA_TRY(cudaMemsetAsync(redo, 0, sizeof(int), stream));
+      ca.redo_count = redo;
+      ca.redo_list = redo + 1;
+      cudaLaunchConfig_t cfg{};
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = static_cast<unsigned>(ctas);
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.gridDim = dim3(static_cast<unsigned>(ctas), 1, 1);
+      cfg.blockDim = dim3(kClThreads, 1, 1);
+      cfg.dynamicSmemBytes = csmem;
+      cfg.stream = stream;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int max_clusters = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, cluster_kernel_f32, &cfg));
+      if (max_clusters >= 1) {
+        const long long n_cl = std::min<long long>(c.B, max_clusters);
+        cfg.gridDim = dim3(static_cast<unsigned>(n_cl * ctas), 1, 1);
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, cluster_kernel_f32, ca));
+        g_launches.fetch_add(1);
+        // the halfspaces it handed back (window miss, overflow, non-finite data): exact general select, streaming kernel
+        KernelArgs ra = a;
+        ra.use_window = 0;
+        ra.redo_count = redo;
+        ra.redo_list = redo + 1;
+        ra.bulk = 1;
+        auto rk = streaming_kernel<T, false>;
+        const long long rgrid = std::min<long long>(c.B, di->sms);
+        rk<<<static_cast<unsigned>(rgrid), kStreamThreads, 0, stream>>>(ra);
+        CUDA_TRY(cudaGetLastError());
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaFreeAsync(redo, stream));
+        return DRCVAR_OK;
+      }
+      CUDA_TRY(cudaFreeAsync(redo, stream));
+    }
+  }
   if (streaming) {
     auto sk = tail ? streaming_kernel<T, true> : streaming_kernel<T, false>;
     if constexpr (sizeof(T) == 4) {

@@ -65,6 +65,19 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kBulkChunk = 32768;
 constexpr int kRowsPerChunk = kBulkChunk / (16 * 256);   // a row = one 16-byte load per sweep thread = 4 KB
 
+// Canonical mean for N > kOctantMinN: 8 octants of whole 4 KB rows, each with its own slot sums + tree; the octant totals
+// are combined by an adjacent-pair tree (oracle/closed_form.py).  This is the split the cluster kernel
+// distributes over its CTAs; the resident kernel never sees such N.
+constexpr int kOctantMinN = 32768;
+constexpr int kOctants = 8;
+__host__ __device__ inline long long octant_bytes(long long n, size_t elem_bytes) {
+  const long long row = n * 2 * static_cast<long long>(elem_bytes);
+  return (row + kOctants * 4096 - 1) / (kOctants * 4096) * 4096;
+}
+__host__ __device__ inline int octant_samples(long long n, size_t elem_bytes) {
+  return static_cast<int>(octant_bytes(n, elem_bytes) / (2 * static_cast<long long>(elem_bytes)));
+}
+
 constexpr int kStatusNonfinite = 1;
 constexpr int kStatusGeneral = 2;
 constexpr int kStatusDegenerate = 4;
@@ -102,6 +115,11 @@ struct KernelArgs {
   unsigned long long gen_seed;
   long long gen_index_offset;   // global index of halfspace 0 of this launch (shards reproduce the unsharded stream)
   float* gen_samples_out;    // optional [B,N,2] dump of the generated samples (parity tests)
+  // cluster kernel (cluster_kernel.cuh): CTAs per halfspace; halfspaces it could not finish (window miss, overflow,
+  // non-finite data) are appended to redo_list and processed by the streaming kernel, which then takes its work from it
+  int cl_ctas;
+  int* redo_count;
+  int* redo_list;
 };
 
 struct Ctl {                        // one per parity buffer

@@ -35,16 +35,18 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
   __shared__ double xch[kSweepThreads * 2];
   __shared__ double cand[kW * kStreamCand];
   __shared__ int iscr[4 * kW];
+  __shared__ double oct_tot[2 * kOctants];
   __shared__ Ctl ctl_s;
   Ctl* ctl = &ctl_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int half = tid >> 8, lt = tid & (kSweepThreads - 1);   // half 0: even canonical rows, half 1: odd rows
   const int N = a.N;
-  const int full_rows = N / kRowSamples;
-  const int rows_all = (N + kRowSamples - 1) / kRowSamples;
   auto sync = [] { __syncthreads(); };
 
-  for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+  // work list: the whole batch, or the halfspaces the cluster kernel handed back (redo list, filled on the device)
+  const long long n_work = a.redo_list != nullptr ? static_cast<long long>(*a.redo_count) : a.B;
+  for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    const long long b = a.redo_list != nullptr ? static_cast<long long>(a.redo_list[wi]) : wi;
     const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
     const bool vec = kGen || a.bulk != 0;   // contiguous (x, y) pairs, 16-byte aligned rows: vector loads
     // generate mode (fp32): the samples are drawn on the fly in EVERY pass (sample_gen.cuh; one Philox call per pair)
@@ -105,70 +107,113 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
     }
     // ------------------------------------------------------------------ pass 1: canonical lane sums + moments
     // Thread (half, lt) owns slot half*256 + lt: rows r = half, half+2, ... in increasing order (the canonical order).
+    // N > kOctantMinN: the contract cuts the samples into 8 octants of whole 4 KB rows, each with its own slot sums and
+    // tree (oracle/closed_form.py) — the split the cluster kernel distributes over its CTAs.
     const V2 first = load(0);
-    double s_x, s_y;                       // this thread's slot sums
+    const int n_oct = N > kOctantMinN ? kOctants : 1;
+    const int oct_len = n_oct == 1 ? N : octant_samples(N, sizeof(T));
     float q_xx = 0.f, q_yy = 0.f, q_xy = 0.f, q_dx = 0.f, q_dy = 0.f;
-    if constexpr (kF32) {
-      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f), sq = make_float2(0.f, 0.f);
-      float sxy = 0.f;
-      const float2 nf = make_float2(-first.x, -first.y);
-      auto body = [&](float2 v, float2& acc) {
-        const float2 d = __fadd2_rn(v, nf);
-        acc = __fadd2_rn(acc, d);
-        sq = __ffma2_rn(d, d, sq);
-        sxy = fmaf(d.x, d.y, sxy);
-      };
-      int r = half;
-      if (vec) {
+    int n_sub_i = 0;   // fp64 inputs: samples behind the second moments (rows 0, 4, 8, ... of every octant)
+    for (int oc = 0; oc < n_oct; ++oc) {
+      const int i_lo = oc * oct_len;
+      const int n_k = N - i_lo < oct_len ? (N - i_lo > 0 ? N - i_lo : 0) : oct_len;
+      const int full_rows = n_k / kRowSamples;
+      const int rows_all = (n_k + kRowSamples - 1) / kRowSamples;
+      double s_x, s_y;                       // this thread's slot sums
+      if constexpr (kF32) {
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f), sq = make_float2(0.f, 0.f);
+        float sxy = 0.f;
+        const float2 nf = make_float2(-first.x, -first.y);
+        auto body = [&](float2 v, float2& acc) {
+          const float2 d = __fadd2_rn(v, nf);
+          acc = __fadd2_rn(acc, d);
+          sq = __ffma2_rn(d, d, sq);
+          sxy = fmaf(d.x, d.y, sxy);
+        };
+        int r = half;
+        if (vec) {
+          const int it_lo = i_lo >> 1;   // octants start on whole rows: i_lo is even
 #pragma unroll 8
-        for (; r < full_rows; r += 2) {
-          const float4 v = load4(r * kSweepThreads + lt);
-          body(make_float2(v.x, v.y), acc0);
-          body(make_float2(v.z, v.w), acc1);
-        }
-      } else {
-        for (; r < full_rows; r += 2) {
-          const int i0 = r * kRowSamples + 2 * lt;
-          body(load(i0), acc0);
-          body(load(i0 + 1), acc1);
-        }
-      }
-      if (r == full_rows && full_rows < rows_all) {   // ragged last row (only the half with its parity)
-        const int i0 = r * kRowSamples + 2 * lt;
-        if (i0 < N) body(load(i0), acc0);
-        if (i0 + 1 < N) body(load(i0 + 1), acc1);
-      }
-      s_x = __dadd_rn(static_cast<double>(acc0.x), static_cast<double>(acc1.x));   // lanes 2 slot, 2 slot + 1
-      s_y = __dadd_rn(static_cast<double>(acc0.y), static_cast<double>(acc1.y));
-      q_xx = sq.x;
-      q_yy = sq.y;
-      q_xy = sxy;
-    } else {
-      s_x = 0.0;
-      s_y = 0.0;
-      double dxx = 0.0, dyy = 0.0, dxy = 0.0, ddx = 0.0, ddy = 0.0;
-#pragma unroll 8
-      for (int r = half; r < rows_all; r += 2) {
-        const int i = r * kRowSamples + lt;
-        if (i < N) {
-          const V2 v = load(i);
-          s_x = __dadd_rn(s_x, v.x);
-          s_y = __dadd_rn(s_y, v.y);
-          if ((r & 3) == 0) {   // second moments on every 4th row (as in the resident kernel: n_sigma on the host)
-            const double dx = v.x - first.x, dy = v.y - first.y;
-            ddx += dx;
-            ddy += dy;
-            dxx = fma(dx, dx, dxx);
-            dyy = fma(dy, dy, dyy);
-            dxy = fma(dx, dy, dxy);
+          for (; r < full_rows; r += 2) {
+            const float4 v = load4(it_lo + r * kSweepThreads + lt);
+            body(make_float2(v.x, v.y), acc0);
+            body(make_float2(v.z, v.w), acc1);
+          }
+        } else {
+          for (; r < full_rows; r += 2) {
+            const int i0 = i_lo + r * kRowSamples + 2 * lt;
+            body(load(i0), acc0);
+            body(load(i0 + 1), acc1);
           }
         }
+        if (r == full_rows && full_rows < rows_all) {   // ragged last row (only the half with its parity)
+          const int i0 = i_lo + r * kRowSamples + 2 * lt;
+          if (i0 < N) body(load(i0), acc0);
+          if (i0 + 1 < N) body(load(i0 + 1), acc1);
+        }
+        s_x = __dadd_rn(static_cast<double>(acc0.x), static_cast<double>(acc1.x));   // lanes 2 slot, 2 slot + 1
+        s_y = __dadd_rn(static_cast<double>(acc0.y), static_cast<double>(acc1.y));
+        q_xx += sq.x;
+        q_yy += sq.y;
+        q_xy += sxy;
+      } else {
+        s_x = 0.0;
+        s_y = 0.0;
+        double dxx = 0.0, dyy = 0.0, dxy = 0.0, ddx = 0.0, ddy = 0.0;
+#pragma unroll 8
+        for (int r = half; r < rows_all; r += 2) {
+          const int i = i_lo + r * kRowSamples + lt;
+          if (i < N) {
+            const V2 v = load(i);
+            s_x = __dadd_rn(s_x, v.x);
+            s_y = __dadd_rn(s_y, v.y);
+            if ((r & 3) == 0) {   // second moments on every 4th row (as in the resident kernel: n_sigma on the host)
+              const double dx = v.x - first.x, dy = v.y - first.y;
+              ddx += dx;
+              ddy += dy;
+              dxx = fma(dx, dx, dxx);
+              dyy = fma(dy, dy, dyy);
+              dxy = fma(dx, dy, dxy);
+            }
+          }
+        }
+        q_xx += static_cast<float>(dxx);
+        q_yy += static_cast<float>(dyy);
+        q_xy += static_cast<float>(dxy);
+        q_dx += static_cast<float>(ddx);
+        q_dy += static_cast<float>(ddy);
+        if (n_k > 0) {
+          const int r4 = (rows_all + 3) / 4;
+          const int last = (r4 - 1) * 4 * kRowSamples;
+          n_sub_i += (r4 - 1) * kSweepThreads + (n_k - last < kSweepThreads ? n_k - last : kSweepThreads);
+        }
       }
-      q_xx = static_cast<float>(dxx);
-      q_yy = static_cast<float>(dyy);
-      q_xy = static_cast<float>(dxy);
-      q_dx = static_cast<float>(ddx);
-      q_dy = static_cast<float>(ddy);
+      if (half == 1) {
+        xch[2 * lt] = s_x;
+        xch[2 * lt + 1] = s_y;
+      }
+      __syncthreads();
+      if (half == 0) {   // u[j] = s[j] + s[j + 256], then the canonical butterfly inside each group of 32
+        const double tx = warp_sum_canon(__dadd_rn(s_x, xch[2 * lt]));
+        const double ty = warp_sum_canon(__dadd_rn(s_y, xch[2 * lt + 1]));
+        if (lane == 0) {
+          red[warp * 8] = tx;
+          red[warp * 8 + 1] = ty;
+        }
+      }
+      __syncthreads();
+      if (tid < 2) {     // adjacent-pair tree over the 8 group totals -> total of this octant (coordinate tid)
+        double t[kSweepWarps];
+#pragma unroll
+        for (int g = 0; g < kSweepWarps; ++g) t[g] = red[g * 8 + tid];
+#pragma unroll
+        for (int n = kSweepWarps; n > 1; n >>= 1)
+#pragma unroll
+          for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);
+        oct_tot[2 * oc + tid] = t[0];
+      }
+      // (the next octant's xch / red writes are ordered behind this read by its own first __syncthreads: red is only
+      //  rewritten after that barrier, xch is not read here)
     }
     {
       const float mxx = warp_sum_any(q_xx), myy = warp_sum_any(q_yy), mxy = warp_sum_any(q_xy);
@@ -178,33 +223,24 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
         w[0] = mxx; w[1] = myy; w[2] = mxy; w[3] = mdx; w[4] = mdy;
       }
     }
-    if (half == 1) {
-      xch[2 * lt] = s_x;
-      xch[2 * lt + 1] = s_y;
-    }
-    __syncthreads();
-    if (half == 0) {   // u[j] = s[j] + s[j + 256], then the canonical butterfly inside each group of 32
-      const double tx = warp_sum_canon(__dadd_rn(s_x, xch[2 * lt]));
-      const double ty = warp_sum_canon(__dadd_rn(s_y, xch[2 * lt + 1]));
-      if (lane == 0) {
-        red[warp * 8] = tx;
-        red[warp * 8 + 1] = ty;
-      }
-    }
     __syncthreads();
     // ------------------------------------------------------------------ warp 0: canonical mean / direction, window
     if (warp == 0) {
       double w[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        double t[kSweepWarps];
+        if (n_oct == 1) {
+          w[j] = oct_tot[j];
+        } else {   // adjacent-pair tree over the 8 octant totals
+          double t[kOctants];
 #pragma unroll
-        for (int g = 0; g < kSweepWarps; ++g) t[g] = red[g * 8 + j];
+          for (int g = 0; g < kOctants; ++g) t[g] = oct_tot[2 * g + j];
 #pragma unroll
-        for (int n = kSweepWarps; n > 1; n >>= 1)
+          for (int n = kOctants; n > 1; n >>= 1)
 #pragma unroll
-          for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);
-        w[j] = t[0];
+            for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);
+          w[j] = t[0];
+        }
       }
       const double f0 = static_cast<double>(first.x), f1 = static_cast<double>(first.y);
       double m0 = __ddiv_rn(w[0], static_cast<double>(N)), m1 = __ddiv_rn(w[1], static_cast<double>(N));
@@ -244,9 +280,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
         ex = m0 - f0;
         ey = m1 - f1;
       } else {
-        const int r4 = (rows_all + 3) / 4;
-        const int last = (r4 - 1) * 4 * kRowSamples;
-        n_sub = static_cast<double>((r4 - 1) * kSweepThreads + (N - last < kSweepThreads ? N - last : kSweepThreads));
+        n_sub = static_cast<double>(n_sub_i > 0 ? n_sub_i : 1);
         ex = q[3] / n_sub;
         ey = q[4] / n_sub;
       }

@@ -55,6 +55,7 @@ extern "C" {
 #define DRCVAR_FLAG_GENERAL_ONLY 2u  /* disable the statistical candidate window (always use the general select) */
 #define DRCVAR_FLAG_NO_BULK 4u       /* disable cp.async.bulk staging (use the generic strided loader) */
 #define DRCVAR_FLAG_FORCE_STREAMING 8u /* use the two-pass streaming kernel even when one CTA could hold N samples */
+#define DRCVAR_FLAG_NO_CLUSTER 16u   /* large N: do not use the cluster / DSMEM single-read kernel (streaming kernel instead) */
 
 /* per-halfspace status bits written to status_out */
 #define DRCVAR_STATUS_NONFINITE 1   /* non-finite input: sentinel 100.0 emitted (core/risk_metrics.py:177,265,303,338) */

@@ -33,6 +33,11 @@ oracle DEFINES the arithmetic the CUDA path must reproduce bit-for-bit where ord
       then u[j] = s[j] + s[j+256] (j < 256); each group of 32 consecutive u is combined by an
       xor-butterfly (1,2,4,8,16); the 8 group totals by an adjacent-pair tree ((w0+w1)+(w2+w3))+((w4+w5)+(w6+w7));
       mean = S / N in fp64 (fp32 inputs: mean = fl64(v_0) + S / N).
+      N > 32768 (the sizes served by the cluster / DSMEM kernel, where 4 or 8 CTAs each hold a part of the samples):
+      the samples are cut into 8 OCTANTS of ceil(N * 2 * itemsize / 8 / 4096) * 4096 bytes (whole 4 KB rows; the last
+      octants may be short or empty); every octant gets the slot sums + tree above on its own sub-array (lane index
+      relative to the octant start, fp32 shift still by the GLOBAL first sample v_0), and the 8 octant totals are
+      combined by the adjacent-pair tree ((o0+o1)+(o2+o3))+((o4+o5)+(o6+o7)) = S.
   * projection  p_i = rn(rn(h0*x_i) + rn(h1*y_i))  (no FMA);  loss  L_i = -p_i.
   * tail: k_f = alpha*N (snapped to the nearest integer when within 1e-9 relative),
     kc = ceil(k_f); T = kc-th largest loss; index set = {L_i > T} U lowest-index ties, |set| = kc
@@ -49,6 +54,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 LANES = 512
+OCTANT_MIN_N = 32768   # N above this uses the 8-octant rule
+OCTANTS = 8
 SENTINEL = 100.0  # core/risk_metrics.py:177,265,303,338
 
 _XOR_IDX = {x: (np.arange(32) ^ x) for x in (1, 2, 4, 8, 16)}
@@ -87,16 +94,46 @@ def canonical_sum(v) -> float:
     return _tree512(_lane_sums(v, LANES, np.float64))
 
 
-def canonical_mean_1d(v) -> float:
-    """Canonical mean of one coordinate; the arithmetic depends on the INPUT dtype (see module docstring)."""
-    v = np.ascontiguousarray(v).ravel()
-    n = v.shape[0]
+def octant_len(n: int, itemsize: int) -> int:
+    """Samples per octant for N > OCTANT_MIN_N: whole 4 KB rows of (x, y) pairs."""
+    row_bytes = n * 2 * itemsize
+    ob = -(-row_bytes // (OCTANTS * 4096)) * 4096
+    return ob // (2 * itemsize)
+
+
+def _pair_tree(w) -> float:
+    w = np.asarray(w, dtype=np.float64)
+    while w.shape[0] > 1:
+        w = w[0::2] + w[1::2]
+    return float(w[0])
+
+
+def _slot_total(v, v0) -> float:
+    """Canonical total of one (sub-)array: fp32 -> shifted fp32 lanes, fp64 -> fp64 slots; then the 512-tree."""
+    if v.shape[0] == 0:
+        return 0.0
     if v.dtype == np.float32:
-        d = (v - v[0]).astype(np.float32)                      # fl32(v_i - v_0)
+        d = (v - v0).astype(np.float32)                        # fl32(v_i - v_0)
         s = _lane_sums(d, 2 * LANES, np.float32).astype(np.float64)
         s = s[0::2] + s[1::2]                                  # adjacent fp32 lanes, added in fp64
-        return float(np.float64(v[0]) + np.float64(_tree512(s)) / np.float64(n))
-    return float(np.float64(canonical_sum(v)) / np.float64(n))
+        return _tree512(s)
+    return _tree512(_lane_sums(v, LANES, np.float64))
+
+
+def canonical_mean_1d(v) -> float:
+    """Canonical mean of one coordinate; the arithmetic depends on the INPUT dtype and on N (see module docstring)."""
+    v = np.ascontiguousarray(v).ravel()
+    if v.dtype != np.float32:
+        v = v.astype(np.float64, copy=False)
+    n = v.shape[0]
+    if n > OCTANT_MIN_N:
+        ol = octant_len(n, v.dtype.itemsize)
+        total = _pair_tree([_slot_total(v[k * ol:(k + 1) * ol], v[0]) for k in range(OCTANTS)])
+    else:
+        total = _slot_total(v, v[0]) if n else 0.0
+    if v.dtype == np.float32:
+        return float(np.float64(v[0]) + np.float64(total) / np.float64(n))
+    return float(np.float64(total) / np.float64(n))
 
 
 def canonical_mean(samples) -> np.ndarray:

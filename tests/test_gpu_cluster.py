@@ -1,0 +1,142 @@
+"""
+GPU parity tests of the cluster / DSMEM kernel (csrc/cluster_kernel.cuh): N > 32768 fp32 — BASELINE config 5 is
+N = 100 000 — one thread-block cluster per halfspace, every sample read from HBM once.  All calls go through the C ABI.
+
+Bars: h, h_mean and the threshold T (= kc-th largest loss, which fixes the tail-index set) bit-exact against the
+oracle; offsets <= 1e-6 m against the oracle on the same fp32 samples; bit-identical T / h against the streaming kernel
+(DRCVAR_FLAG_NO_CLUSTER), whose tail-index sets are checked bit for bit in test_gpu_parity.py; run-to-run determinism.
+"""
+import numpy as np
+import pytest
+
+from oracle import closed_form as cf
+
+pytestmark = pytest.mark.gpu
+
+ABS32 = 1e-6
+P = dict(alpha=0.1, delta=0.1, epsilon=0.01, robot_radius=0.3, obstacle_radius=0.3)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 as pkg
+    return pkg
+
+
+def gaussian_batch(rng, B, n, spread=4.0):
+    mu = rng.uniform(-spread, spread, size=(B, 1, 2))
+    s = (mu + 0.1 * rng.standard_normal((B, n, 2))).astype(np.float32)
+    ego = rng.uniform(-1, 1, size=(B, 2))
+    return s, ego
+
+
+def check_against_oracle(res, s, ego, p, which, h_in=None):
+    for b in which:
+        o = cf.halfspace(s[b], ego[b], p["alpha"], p["delta"], p["epsilon"], p["robot_radius"], p["obstacle_radius"],
+                         None if h_in is None else h_in[b])
+        assert np.array_equal(res.h[b], o.h), (b, res.h[b], o.h)
+        assert np.array_equal(res.h_mean[b], o.h_mean), (b, res.h_mean[b], o.h_mean)
+        assert res.var[b] == o.var, (b, res.var[b], o.var)                       # T bit-exact -> the tail set is fixed
+        ref = np.array([o.g_mean, o.g_cvar, o.g_dr])
+        assert np.abs(res.g[b] - ref).max() <= ABS32, (b, res.g[b], ref)
+        assert abs(res.cvar[b] - o.cvar) <= ABS32 and abs(res.g_star[b] - o.g_dr_star) <= ABS32
+        assert abs(res.g[b, 0] - o.g_mean) <= 1e-9 * max(1.0, abs(o.g_mean))     # the mean halfspace has no fp32 shortcut
+
+
+def host_chunks(B, n):
+    """The host path stages ~64 MB of samples per launch (drcvar_abi.cu: run_host)."""
+    per = max(1, (64 << 20) // (n * 8))
+    return -(-B // per)
+
+
+def launches(eng, fn):
+    before = eng.launch_count()
+    r = fn()
+    return r, eng.launch_count() - before
+
+
+def test_config5_sample_count(eng):
+    """N = 100 000 (4 CTAs per halfspace), enough halfspaces for several pipelined iterations per cluster."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    rng = np.random.RandomState(101)
+    B, n = 240, 100000
+    s, ego = gaussian_batch(rng, B, n)
+    res, nl = launches(eng, lambda: eng.compute_halfspaces(s, ego, **P))
+    assert nl == 2 * host_chunks(B, n)  # per chunk: cluster kernel + the (normally empty) redo pass of the streaming kernel
+    ref, nl2 = launches(eng, lambda: eng.compute_halfspaces(s, ego, flags=_lib.FLAG_NO_CLUSTER, **P))
+    assert nl2 == host_chunks(B, n)
+    assert np.array_equal(res.h, ref.h) and np.array_equal(res.h_mean, ref.h_mean) and np.array_equal(res.var, ref.var)
+    assert np.abs(res.g - ref.g).max() <= ABS32 and np.array_equal(res.g[:, 0], ref.g[:, 0])
+    assert (res.status & _lib.STATUS_GENERAL).sum() <= 2          # window misses are 3e-5 events
+    check_against_oracle(res, s, ego, P, range(0, B, 7))
+    again = eng.compute_halfspaces(s, ego, **P)
+    for k in ("h", "h_mean", "g", "cvar", "var", "g_star", "status"):
+        assert np.array_equal(getattr(res, k), getattr(again, k)), k
+
+
+@pytest.mark.parametrize("n", [32770, 40000, 52002, 65544, 131072, 150000, 200000])
+def test_cluster_sizes_and_ragged_octants(eng, n):
+    """2, 4 and 8 CTAs per halfspace; short / empty last octants; parts that end inside a 32 KB chunk."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    rng = np.random.RandomState(n % 1000)
+    B = 40
+    s, ego = gaussian_batch(rng, B, n)
+    res, nl = launches(eng, lambda: eng.compute_halfspaces(s, ego, **P))
+    assert nl == 2 * host_chunks(B, n)
+    ref = eng.compute_halfspaces(s, ego, flags=_lib.FLAG_NO_CLUSTER, **P)
+    assert np.array_equal(res.h, ref.h) and np.array_equal(res.var, ref.var) and np.array_equal(res.h_mean, ref.h_mean)
+    assert np.abs(res.g - ref.g).max() <= ABS32
+    check_against_oracle(res, s, ego, P, (0, 17, B - 1))
+
+
+def test_other_tail_fractions_and_explicit_normals(eng):
+    rng = np.random.RandomState(7)
+    B, n = 24, 100000
+    s, ego = gaussian_batch(rng, B, n)
+    for alpha in (0.2, 0.05, 0.5):
+        p = dict(P, alpha=alpha)
+        res = eng.compute_halfspaces(s, ego, **p)
+        check_against_oracle(res, s, ego, p, (0, 11, B - 1))
+    th = rng.uniform(0, 2 * np.pi, size=B)
+    h = np.stack([np.cos(th), np.sin(th)], axis=1) * rng.uniform(0.5, 2.0, size=(B, 1))     # non-unit normals too
+    res = eng.compute_halfspaces(s, None, h=h, **P)
+    check_against_oracle(res, s, np.zeros((B, 2)), P, (0, 5, B - 1), h_in=h)
+
+
+def test_redo_list_non_gaussian_and_non_finite(eng):
+    """Samples the Gaussian window plan does not fit (uniform noise), a NaN sample and a halfspace whose mean sits on
+    the ego position: the cluster kernel hands them to the streaming kernel's exact general select."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    rng = np.random.RandomState(3)
+    B, n = 12, 100000
+    mu = rng.uniform(-4, 4, size=(B, 1, 2))
+    s = (mu + rng.uniform(-0.3, 0.3, size=(B, n, 2))).astype(np.float32)
+    ego = rng.uniform(-1, 1, size=(B, 2))
+    s[5, 77777, 1] = np.nan
+    s[9] = (mu[9] + 0.1 * rng.standard_normal((n, 2))).astype(np.float32)     # one Gaussian halfspace among them
+    res, nl = launches(eng, lambda: eng.compute_halfspaces(s, ego, **P))
+    assert nl == 2 * host_chunks(B, n)
+    assert res.status[5] & _lib.STATUS_NONFINITE and res.g[5, 1] == 100.0
+    assert not (res.status[9] & _lib.STATUS_GENERAL)
+    assert (res.status[[0, 1, 2, 3]] & _lib.STATUS_GENERAL).all()
+    check_against_oracle(res, s, ego, P, (0, 3, 9, 11))
+    # direction undefined: mean == ego -> fallback [1, 0] (core/geometry.py:49-51)
+    m = np.array([cf.canonical_mean(s[2])])
+    res2 = eng.compute_halfspaces(s[2:3], m, **P)
+    assert res2.status[0] & _lib.STATUS_DEGENERATE and np.array_equal(res2.h[0], [1.0, 0.0])
+    check_against_oracle(res2, s[2:3], m, P, (0,))
+
+
+def test_device_pointers_and_single_halfspace(eng):
+    import torch
+    rng = np.random.RandomState(11)
+    s, ego = gaussian_batch(rng, 5, 100000)
+    host = eng.compute_halfspaces(s, ego, **P)
+    dev = eng.compute_halfspaces(torch.from_numpy(s).cuda(), torch.from_numpy(ego).cuda(), **P)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.g.cpu().numpy(), host.g) and np.array_equal(dev.var.cpu().numpy(), host.var)
+    one = eng.compute_halfspaces(s[3], ego[3], **P)
+    assert np.array_equal(one.g[0], host.g[3])

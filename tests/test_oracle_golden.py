@@ -172,3 +172,34 @@ def test_tail_count_snapping():
         cf.tail_count(0.0, 10)
     with pytest.raises(ValueError):
         cf.tail_count(1.5, 10)
+
+
+def test_octant_rule_of_the_canonical_mean():
+    """N > 32768: 8 octants of whole 4 KB rows, each with its own slot sums + tree (the cluster kernel's split).
+    Checked against a direct, loop-level restatement and against the plain mean."""
+    rng = np.random.RandomState(12)
+    for dtype, n in ((np.float32, 32769), (np.float32, 100000), (np.float64, 50001), (np.float32, 40000)):
+        v = (2.5 + 0.1 * rng.standard_normal(n)).astype(dtype)
+        item = np.dtype(dtype).itemsize
+        ol = cf.octant_len(n, item)
+        assert (ol * 2 * item) % 4096 == 0 and 8 * ol >= n and 8 * (ol - 4096 // (2 * item)) < n
+        lanes = 1024 if dtype == np.float32 else 512
+        tot = []
+        for k in range(8):
+            part = v[k * ol:(k + 1) * ol]
+            acc = np.zeros(lanes, dtype=dtype)
+            d = (part - v[0]).astype(np.float32) if dtype == np.float32 else part
+            for i in range(part.shape[0]):          # lane index relative to the octant start, increasing i
+                acc[i % lanes] = dtype(acc[i % lanes] + d[i])
+            s = acc.astype(np.float64)
+            if dtype == np.float32:
+                s = s[0::2] + s[1::2]
+            tot.append(cf._tree512(s))
+        S = ((tot[0] + tot[1]) + (tot[2] + tot[3])) + ((tot[4] + tot[5]) + (tot[6] + tot[7]))
+        want = (float(v[0]) + S / n) if dtype == np.float32 else S / n
+        got = cf.canonical_mean_1d(v)
+        assert got == want
+        assert abs(got - float(np.mean(v.astype(np.float64)))) < 1e-12
+    # N <= 32768 keeps the single-chain rule (the resident kernel's sizes): unchanged goldens
+    v = (1.0 + 0.1 * rng.standard_normal(32768)).astype(np.float32)
+    assert cf.canonical_mean_1d(v) == float(np.float64(v[0]) + np.float64(cf._slot_total(v, v[0])) / np.float64(32768))
