@@ -7,8 +7,8 @@
 //             halfspace b+1, each chunk issued the moment all 16 sweep warps have released it in sweep B of halfspace b
 //   sweep A   trails the chunks as they land: canonical lane sums per octant (shifted by the first sample, packed fp32
 //             partials, fp64 tree) + second moments
-//   exchange1 every CTA sends its octant totals + moments to every CTA (st.shared::cluster + remote mbarrier arrive with
-//             release.cluster); all CTAs then compute the SAME window / fp32 thresholds (warp 0) and the SAME canonical
+//   exchange1 every CTA sends its octant totals + moments to every CTA (st.async through DSMEM, completion counted on the
+//             destination's mbarrier); all CTAs then compute the SAME window / fp32 thresholds (warp 0) and the SAME canonical
 //             direction (director warp: IEEE div / sqrt chain, off the team's path)              core/geometry.py:35-53
 //   sweep B   fp32 classification with the rigorous bound of the resident kernel: surely above the window (count +
 //             shifted coordinate sums; the loss sum follows from linearity), surely below (ignored), or "needs the exact
@@ -28,18 +28,20 @@ namespace drcvar {
 
 constexpr int kClTeamWarps = 16;
 constexpr int kClTeam = kClTeamWarps * 32;        // 512: thread t owns slot t of the canonical tree
-constexpr int kClThreads = kClTeam + 64;          // + producer warp + director warp
+constexpr int kClThreads = kClTeam + 96;          // + producer warp + director warp + finisher warp
 constexpr int kClProducerWarp = kClTeamWarps;
 constexpr int kClDirectorWarp = kClTeamWarps + 1;
+constexpr int kClFinisherWarp = kClTeamWarps + 2;
 constexpr int kClMaxCtas = 8;
 constexpr int kClMaxChunks = 8;                   // 32 KB chunks of one CTA's part (<= 227 KB)
-constexpr int kClWarpList = 48;                   // masked samples (raw copies) per sweep warp
-constexpr int kClPool = 1024;                     // candidate losses gathered at the leader (all CTAs together)
+constexpr int kClWarpList = 40;                   // masked samples (raw copies) per sweep warp
+constexpr int kClPool = 1536;                     // candidate losses gathered at the leader (all CTAs together)
 constexpr int kClX1 = 12;                         // doubles per source CTA in exchange 1
 constexpr uint32_t kClLaneRow = 8192;             // one 16-byte load per team thread
 
 struct ClShared {
-  double pool[kClPool];                           // leader: candidates [src][cap]; sweep A: tree exchange (first 4 KB)
+  double pool[kClPool];                           // leader: candidates [src][cap], read by the finisher warp
+  double xch[512];                                // sweep A: slots 256..511 on their way to threads 0..255
   double x1[2][kClMaxCtas][kClX1];                // exchange 1 [parity][src]: octant totals (x, y)..., qxx, qyy, qxy, bound2
   double x2[kClMaxCtas][4];                       // exchange 2 at the leader [src]: n_above, sum dx, sum dy, ncand (-1: overflow)
   float2 list[kClTeamWarps][kClWarpList];
@@ -51,6 +53,9 @@ struct ClShared {
   unsigned hist[kHistBuckets];
   double small[kResolveMax];
   Ctl ctl[2];
+  Ctl fin_ctl;                                    // leader: copy of ctl[par] for the finisher warp (it may lag behind)
+  long long fin_b;
+  unsigned long long fdone;                       // finisher -> team: pool / x2 / fin_ctl may be refilled
   unsigned long long full[kClMaxChunks];
   unsigned long long free_[kClMaxChunks];
   unsigned long long xbar1[2];
@@ -74,24 +79,23 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+// Remote store whose completion is counted in bytes on the DESTINATION CTA's mbarrier (like a TMA copy): the data is
+// visible to whoever observes the phase completion, and the sender needs no fence.  (A release.cluster arrive compiles
+// to MEMBAR.ALL.GPU, microseconds under full HBM load: measured 12 k cycles per halfspace in the first version.)
+__device__ __forceinline__ void st_async_f64(uint32_t addr, double v, uint32_t cluster_bar_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(addr),
+               "l"(__double_as_longlong(v)), "r"(cluster_bar_addr)
+               : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+// One arrival on a (remote) mbarrier that also announces the bytes this sender's st.async stores will complete.
+__device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint32_t cluster_bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar_addr), "r"(bytes)
+               : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
-        : "memory");
-  }
-}
+// Wait for an exchange: the payload was written into THIS CTA's shared memory by st.async, whose bytes complete on the
+// barrier exactly like a TMA copy, so the plain (acquire.cta) wait every TMA consumer uses is enough.  An
+// acquire.cluster wait adds CCTL.IVALL (L1 invalidate) per warp: 19 % of all stall samples in the first profile.
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, uint32_t parity) { mbar_wait_idle(bar, parity); }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -137,6 +141,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     mbar_init(&sh->xbar2, kClTeamWarps * C);
     mbar_init(&sh->hdone[0], 1);
     mbar_init(&sh->hdone[1], 1);
+    mbar_init(&sh->fdone, 1);
     mbar_fence_init();
   }
   if (tid < 2 * kClTeamWarps) sh->wcnt[tid] = 0;
@@ -220,13 +225,72 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     return;
   }
 
+  // ============================================================================================ finisher warp
+  // Leader CTA of halfspace it (it % C == rank): exact rank among the gathered window candidates, CVaR, offsets — off the
+  // sweep team's path, which goes straight on to the next halfspace.                         core/risk_metrics.py:84-338
+  if (warp == kClFinisherWarp) {
+    int it = 0;
+    uint32_t n_lead = 0;
+    for (long long b = q; b < a.B; b += n_clusters, ++it) {
+      if (it % C != static_cast<int>(rank)) continue;
+      mbar_wait_cluster(&sh->xbar2, n_lead & 1u);
+      ++n_lead;
+      Ctl* fc = &sh->fin_ctl;
+      bool fast = fc->window_ok != 0 && fc->nonfinite == 0;
+      double n_above = 0.0, sdx = 0.0, sdy = 0.0;
+      int ncand = 0;
+      if (fast) {
+        for (int s = 0; s < C; ++s) {
+          n_above += sh->x2[s][0];
+          sdx += sh->x2[s][1];
+          sdy += sh->x2[s][2];
+          const double c = sh->x2[s][3];
+          if (c < 0.0) fast = false; else ncand += static_cast<int>(c);
+        }
+      }
+      const int cnt_hi = static_cast<int>(n_above);
+      fast = fast && cnt_hi < a.kc && a.kc <= cnt_hi + ncand;
+      if (fast) {
+        auto each = [&](auto&& f) {
+          for (int s = 0; s < C; ++s) {
+            const int n_s = static_cast<int>(sh->x2[s][3]);
+            for (int j = lane; j < n_s; j += 32) f(sh->pool[s * cap + j]);
+          }
+        };
+        const double T_thr = select_rank(each, [] { __syncwarp(); }, true, lane, 32, key_of(fc->t_lo), key_of(fc->t_hi),
+                                         a.kc - cnt_hi, sh->hist, sh->small, fc);
+        int c4 = 0;
+        double s4 = 0.0;
+        each([&](double L) {
+          if (L > T_thr) {
+            ++c4;
+            s4 += L;
+          }
+        });
+        c4 = __reduce_add_sync(kFull, c4);
+        s4 = warp_sum_any(s4);
+        if (lane == 0) {
+          // loss sum of the "surely above" set by linearity, xi_i = f + d_i:  sum_i -(h.xi_i) = -(h0 (n f0 + sum dx) + h1 (n f1 + sum dy))
+          const double s_lin = -(fc->h0 * (n_above * fc->f0 + sdx) + fc->h1 * (n_above * fc->f1 + sdy));
+          write_risk_outputs(a, b, fc, false, s_lin + s4, cnt_hi + c4, T_thr, fc->degenerate ? kStatusDegenerate : 0);
+        }
+      } else if (lane == 0) {
+        a.redo_list[atomicAdd(a.redo_count, 1)] = static_cast<int>(b);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->fdone);
+    }
+    return;
+  }
+
   // ============================================================================================ sweep team
   const float4* slot4 = reinterpret_cast<const float4*>(smem_raw);
   const uint32_t toff = 16u * tid;
   const uint32_t woff = 16u * (tid & ~31);   // first byte of this warp inside a lane-row
   float2* wlist = sh->list[warp];
   int it = 0;
-  uint32_t x2_uses = 0;   // exchanges this CTA has received as the leader (phase of xbar2)
+  PH_DECL
+  uint32_t n_lead = 0;    // halfspaces this CTA has led so far (phase of fdone)
   for (long long b = q; b < a.B; b += n_clusters, ++it) {
     const int par = it & 1;
     const int leader = it % C;
@@ -254,6 +318,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       }
     };
 
+    PH_MARK(0)
     // ------------------------------------------------------------------ sweep A: canonical lane sums per octant + moments
     float2 sq = make_float2(0.f, 0.f);
     float sxy = 0.f;
@@ -299,7 +364,8 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       // slot tid = adjacent fp32 lanes widened and added; u[j] = s[j] + s[j + 256]; butterfly per group of 32; pair tree of 8
       const double s_x = __dadd_rn(static_cast<double>(acc0.x), static_cast<double>(acc1.x));
       const double s_y = __dadd_rn(static_cast<double>(acc0.y), static_cast<double>(acc1.y));
-      double* xch = sh->pool;
+      PH_MARK(1)
+      double* xch = sh->xch;
       if (tid >= 256) {
         xch[2 * (tid - 256)] = s_x;
         xch[2 * (tid - 256) + 1] = s_y;
@@ -319,8 +385,12 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       if (lane == 3) sh->mom[warp * 4 + 3] = __uint_as_float(bnd);
     }
     cl_team_sync();
+    PH_MARK(2)
     // ------------------------------------------------------------------ exchange 1: totals + moments to every CTA
     if (tid < C) {   // thread d serves destination CTA d
+      // leader of this halfspace: our finisher must be done with the pool / x2 / fin_ctl of the halfspace we led last,
+      // before any CTA can get past exchange 1 and send the next candidates
+      if (static_cast<int>(rank) == leader && n_lead > 0) mbar_wait(&sh->fdone, (n_lead - 1) & 1u);
       double qxx = 0.0, qxy = 0.0, qyy = 0.0;
       float b2 = 0.f;
       for (int w = 0; w < kClTeamWarps; ++w) {
@@ -330,14 +400,16 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         b2 = fmaxf(b2, sh->mom[w * 4 + 3]);
       }
       const uint32_t dst = mapa_u32(smem_u32(&sh->x1[par][rank][0]), static_cast<uint32_t>(tid));
-      for (int i = 0; i < 2 * O; ++i) st_cluster_f64(dst + 8u * i, sh->octtot[i]);
-      st_cluster_f64(dst + 64, qxx);
-      st_cluster_f64(dst + 72, qyy);
-      st_cluster_f64(dst + 80, qxy);
-      st_cluster_f64(dst + 88, static_cast<double>(b2));
-      mbar_arrive_remote(mapa_u32(smem_u32(&sh->xbar1[par]), static_cast<uint32_t>(tid)));
+      const uint32_t bar = mapa_u32(smem_u32(&sh->xbar1[par]), static_cast<uint32_t>(tid));
+      mbar_arrive_expect_tx_remote(bar, 8u * (2u * O + 4u));
+      for (int i = 0; i < 2 * O; ++i) st_async_f64(dst + 8u * i, sh->octtot[i], bar);
+      st_async_f64(dst + 64, qxx, bar);
+      st_async_f64(dst + 72, qyy, bar);
+      st_async_f64(dst + 80, qxy, bar);
+      st_async_f64(dst + 88, static_cast<double>(b2), bar);
     }
     mbar_wait_cluster(&sh->xbar1[par], (it >> 1) & 1);
+    PH_MARK(3)
 
     // ------------------------------------------------------------------ window placement (warp 0; identical in every CTA)
     if (warp == 0) {
@@ -419,6 +491,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       }
     }
     cl_team_sync();  // S2
+    PH_MARK(4)
     const bool window = ctl->window_ok != 0;
 
     int rel = 0;   // chunks this warp has handed back (warp-uniform)
@@ -433,8 +506,15 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     if (!window) {
       // no usable window (degenerate / non-finite / tiny tails): the streaming kernel redoes this halfspace
       release_upto(n_chunks);
-      if (tid == 0 && static_cast<int>(rank) == leader) a.redo_list[atomicAdd(a.redo_count, 1)] = static_cast<int>(b);
       mbar_wait(&sh->hdone[par], (it >> 1) & 1);   // the director is done with x1[par] / ctl[par] before we run ahead
+      if (lane == 0) {   // the leader's finisher puts the halfspace on the redo list (fin_ctl.window_ok == 0)
+        if (tid == 0 && static_cast<int>(rank) == leader) {
+          sh->fin_ctl = *ctl;
+          __threadfence_block();
+        }
+        mbar_arrive_expect_tx_remote(mapa_u32(smem_u32(&sh->xbar2), static_cast<uint32_t>(leader)), 0u);
+      }
+      if (static_cast<int>(rank) == leader) ++n_lead;
       continue;
     }
 
@@ -444,8 +524,20 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     {
       const float h0f = ctl->h0f, h1f = ctl->h1f, thr_keep = ctl->thr_keep, thr_above = ctl->thr_above;
       const unsigned lt_mask = (1u << lane) - 1u;
-      auto extract = [&](unsigned mk, const float4& v0, const float4& v1, const float4& v2, const float4& v3) {
-        // mask bit 2u + e <-> sample e of row u.  Exclusive prefix of the per-lane counts (0..8) by ballot planes.
+      auto extract = [&](unsigned mk, uint32_t base, const float4& v0, const float4& v1, const float4& v2, const float4& v3) {
+        // mask bit 2u + e <-> sample e of row u (this thread's 16 bytes at base + u * 8 KB).
+        const unsigned bal = __ballot_sync(kFull, mk != 0u);
+        if (__all_sync(kFull, (mk & (mk - 1u)) == 0u)) {   // usual case: no lane holds more than one masked sample
+          if (mk) {
+            const unsigned e = static_cast<unsigned>(__ffs(static_cast<int>(mk))) - 1u;
+            const int pos = n_list + __popc(bal & lt_mask);
+            if (pos < kClWarpList)
+              wlist[pos] = *reinterpret_cast<const float2*>(smem_raw + base + (e >> 1) * kClLaneRow + (e & 1u) * 8u);
+          }
+          n_list += __popc(bal);
+          return;
+        }
+        // general case: exclusive prefix of the per-lane counts (0..8) by ballot planes
         const int mine = __popc(mk);
         const unsigned p0 = __ballot_sync(kFull, mine & 1), p1 = __ballot_sync(kFull, mine & 2),
                        p2 = __ballot_sync(kFull, mine & 4), p3 = __ballot_sync(kFull, mine & 8);
@@ -490,7 +582,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
           classify4(v1, mk, 4u, true, true);
           classify4(v2, mk, 16u, true, true);
           classify4(v3, mk, 64u, true, true);
-          if (__any_sync(kFull, mk != 0u)) extract(mk, v0, v1, v2, v3);
+          if (__any_sync(kFull, mk != 0u)) extract(mk, base, v0, v1, v2, v3);
         }
         if (lr < n_lr) {   // last (up to 4) rows of the octant, possibly ragged
           release_upto(static_cast<int>((ob + lr * kClLaneRow + woff) >> 15));
@@ -498,19 +590,24 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
           unsigned mk = 0u;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const uint32_t off = ob + (lr + u) * kClLaneRow + toff;
-            const bool ok0 = (lr + u < n_lr) && (off + 8 <= oe), ok1 = (lr + u < n_lr) && (off + 16 <= oe);
-            vv[u] = ok0 ? slot4[off >> 4] : make_float4(first.x, first.y, first.x, first.y);
-            classify4(vv[u], mk, 1u << (2 * u), ok0, ok1);
+            vv[u] = make_float4(first.x, first.y, first.x, first.y);
+            if (lr + u < n_lr) {   // warp-uniform: rows beyond the octant cost nothing
+              const uint32_t off = ob + (lr + u) * kClLaneRow + toff;
+              const bool ok0 = off + 8 <= oe, ok1 = off + 16 <= oe;
+              if (ok0) vv[u] = slot4[off >> 4];
+              classify4(vv[u], mk, 1u << (2 * u), ok0, ok1);
+            }
           }
-          if (__any_sync(kFull, mk != 0u)) extract(mk, vv[0], vv[1], vv[2], vv[3]);
+          if (__any_sync(kFull, mk != 0u)) extract(mk, ob + lr * kClLaneRow + toff, vv[0], vv[1], vv[2], vv[3]);
         }
       }
     }
+    PH_MARK(5)
     release_upto(n_chunks);   // the whole part is back with the producer: halfspace b+1 streams in behind us
 
     // ------------------------------------------------------------------ phase 2b: exact loss of the listed samples
     mbar_wait(&sh->hdone[par], (it >> 1) & 1);
+    PH_MARK(6)
     const double h0 = ctl->h0, h1 = ctl->h1;
     const bool nonfinite = ctl->nonfinite != 0;
     const double t_lo = ctl->t_lo, t_hi = ctl->t_hi;
@@ -550,7 +647,9 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         sh->wcnt[warp * 2 + 1] = overflow ? 1 : 0;
       }
     }
+    PH_MARK(7)
     cl_team_sync();  // S3
+    PH_MARK(8)
     // ------------------------------------------------------------------ exchange 2: everything goes to the leader CTA
     {
       int before = 0, total = 0, ovf = 0;
@@ -562,10 +661,18 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         ovf |= sh->wcnt[w * 2 + 1];
       }
       if (total > cap) ovf = 1;
+      const uint32_t bar = mapa_u32(smem_u32(&sh->xbar2), static_cast<uint32_t>(leader));
+      if (lane == 0) {
+        if (tid == 0 && static_cast<int>(rank) == leader) {   // what our finisher needs of ctl[par], which the team reuses
+          sh->fin_ctl = *ctl;
+          __threadfence_block();
+        }
+        mbar_arrive_expect_tx_remote(bar, (ovf ? 0u : 8u * nc) + (tid == 0 ? 32u : 0u));
+      }
       if (!ovf) {
         const double* wcand = reinterpret_cast<const double*>(wlist);
         const uint32_t dst = mapa_u32(smem_u32(&sh->pool[rank * cap + before]), static_cast<uint32_t>(leader));
-        for (int j = lane; j < nc; j += 32) st_cluster_f64(dst + 8u * j, wcand[j]);
+        for (int j = lane; j < nc; j += 32) st_async_f64(dst + 8u * j, wcand[j], bar);
       }
       if (tid == 0) {
         double n_above = 0.0, sdx = 0.0, sdy = 0.0;
@@ -575,71 +682,21 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
           sdy += sh->wsum[w * 4 + 2];
         }
         const uint32_t dst = mapa_u32(smem_u32(&sh->x2[rank][0]), static_cast<uint32_t>(leader));
-        st_cluster_f64(dst, n_above);
-        st_cluster_f64(dst + 8, sdx);
-        st_cluster_f64(dst + 16, sdy);
-        st_cluster_f64(dst + 24, ovf ? -1.0 : static_cast<double>(total));
+        st_async_f64(dst, n_above, bar);
+        st_async_f64(dst + 8, sdx, bar);
+        st_async_f64(dst + 16, sdy, bar);
+        st_async_f64(dst + 24, ovf ? -1.0 : static_cast<double>(total), bar);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&sh->xbar2), static_cast<uint32_t>(leader)));
+      if (static_cast<int>(rank) == leader) ++n_lead;
     }
-
-    // ------------------------------------------------------------------ finish (leader CTA of this halfspace)
-    if (static_cast<int>(rank) == leader) {
-      mbar_wait_cluster(&sh->xbar2, x2_uses & 1u);
-      ++x2_uses;
-      double n_above = 0.0, sdx = 0.0, sdy = 0.0;
-      int ncand = 0, ovf = 0;
-      for (int s = 0; s < C; ++s) {
-        n_above += sh->x2[s][0];
-        sdx += sh->x2[s][1];
-        sdy += sh->x2[s][2];
-        const double c = sh->x2[s][3];
-        if (c < 0.0) ovf = 1; else ncand += static_cast<int>(c);
-      }
-      const int cnt_hi = static_cast<int>(n_above);
-      const bool fast = !ovf && !nonfinite && cnt_hi < a.kc && a.kc <= cnt_hi + ncand;
-      if (fast) {
-        auto each = [&](auto&& f) {
-          for (int s = 0; s < C; ++s) {
-            const int n_s = static_cast<int>(sh->x2[s][3]);
-            for (int j = tid; j < n_s; j += kClTeam) f(sh->pool[s * cap + j]);
-          }
-        };
-        const double T_thr = select_rank(each, [] { cl_team_sync(); }, warp == 0, tid, kClTeam, key_of(t_lo), key_of(t_hi),
-                                         a.kc - cnt_hi, sh->hist, sh->small, ctl);
-        int c4 = 0;
-        double s4 = 0.0;
-        each([&](double L) {
-          if (L > T_thr) {
-            ++c4;
-            s4 += L;
-          }
-        });
-        const int wc4 = __reduce_add_sync(kFull, c4);
-        const double ws4 = warp_sum_any(s4);
-        if (lane == 0) {
-          sh->wsum[warp * 4] = static_cast<double>(wc4);
-          sh->wsum[warp * 4 + 1] = ws4;
-        }
-        cl_team_sync();
-        if (tid == 0) {
-          double cc = 0.0, ss = 0.0;
-          for (int w = 0; w < kClTeamWarps; ++w) {
-            cc += sh->wsum[w * 4];
-            ss += sh->wsum[w * 4 + 1];
-          }
-          // loss sum of the "surely above" set by linearity, xi_i = f + d_i:  sum_i -(h.xi_i) = -(h0 (n f0 + sum dx) + h1 (n f1 + sum dy))
-          const double s_lin = -(h0 * (n_above * ctl->f0 + sdx) + h1 * (n_above * ctl->f1 + sdy));
-          const int status = ctl->degenerate ? kStatusDegenerate : 0;
-          write_risk_outputs(a, b, ctl, false, s_lin + ss, cnt_hi + static_cast<int>(cc), T_thr, status);
-        }
-      } else if (tid == 0) {
-        a.redo_list[atomicAdd(a.redo_count, 1)] = static_cast<int>(b);
-      }
-      cl_team_sync();   // wsum / pool / hist are free again
-    }
+    PH_MARK(9)
+    cl_team_sync();   // list / wsum / wcnt are free again (a slow warp may still have been sending from its list)
+    PH_MARK(10)
   }
+#ifdef DRCVAR_PROFILE_PHASES
+  if (tid == 64 && a.phase_cycles)
+    for (int k = 0; k < 12; ++k) a.phase_cycles[(blockIdx.x * 2 + 0) * 12 + k] = ph_t[k];
+#endif
   cluster_sync_all();   // nobody leaves while a peer may still write into its shared memory
 }
 

@@ -122,6 +122,14 @@ int device_info(int device, DeviceInfo** out) {
   if (!d.ready) {
     CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    // the cluster path takes its redo list from the stream-ordered allocator: keep freed blocks in the pool instead of
+    // handing them back to the driver at every synchronisation (a cudaMallocAsync per call would cost milliseconds)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     d.ready = true;
   }
   *out = &d;
@@ -266,6 +274,9 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
       cfg.numAttrs = 1;
       int max_clusters = 0;
       CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, cluster_kernel_f32, &cfg));
+#ifdef DRCVAR_PROFILE_PHASES
+      fprintf(stderr, "[drcvar] cluster kernel: N=%lld ctas=%d smem=%zu max_active_clusters=%d\n", c.N, ctas, csmem, max_clusters);
+#endif
       if (max_clusters >= 1) {
         const long long n_cl = std::min<long long>(c.B, max_clusters);
         cfg.gridDim = dim3(static_cast<unsigned>(n_cl * ctas), 1, 1);
