@@ -2,7 +2,7 @@
 // config 5, N = 100 000): ONE THREAD-BLOCK CLUSTER PER HALFSPACE, the samples spread over the distributed shared memory
 // of its 2 / 4 / 8 CTAs (one CTA per SM, each holding 8 / C octants of the canonical mean contract).
 //
-// Per CTA: 16 sweep warps (the team) + a producer warp + a director warp, persistent over the batch (cluster-strided).
+// Per CTA: 16 sweep warps (the team) + producer, director and finisher warps, persistent over the batch (cluster-strided).
 //   producer  1-D TMA bulk copies (cp.async.bulk, 32 KB chunks, one transaction mbarrier per chunk) of this CTA's part of
 //             halfspace b+1, each chunk issued the moment all 16 sweep warps have released it in sweep B of halfspace b
 //   sweep A   trails the chunks as they land: canonical lane sums per octant (shifted by the first sample, packed fp32
@@ -12,7 +12,7 @@
 //             direction (director warp: IEEE div / sqrt chain, off the team's path)              core/geometry.py:35-53
 //   sweep B   fp32 classification with the rigorous bound of the resident kernel: surely above the window (count +
 //             shifted coordinate sums; the loss sum follows from linearity), surely below (ignored), or "needs the exact
-//             fp64 loss" -> raw copy into a per-warp list; every chunk is handed back to the producer as soon as the warp
+//             fp64 loss" -> raw copy into a per-warp list; every chunk is handed back (and refilled by TMA) as soon as the last warp
 //             is past it
 //   phase 2b  canonical fp64 loss of the listed samples; window candidates are compacted per warp
 //   exchange2 partial counts / sums and the candidates go to the halfspace's leader CTA (rotating) through DSMEM
@@ -24,14 +24,21 @@
 
 #include "halfspace_kernel.cuh"
 
+#ifdef DRCVAR_PROFILE_PHASES
+#define CL_DBG(bit) ((a.debug & (bit)) != 0)   // ablation switches of the profiling build (wrong results, timing only)
+#else
+#define CL_DBG(bit) false
+#endif
+
 namespace drcvar {
 
 constexpr int kClTeamWarps = 16;
 constexpr int kClTeam = kClTeamWarps * 32;        // 512: thread t owns slot t of the canonical tree
-constexpr int kClThreads = kClTeam + 96;          // + producer warp + director warp + finisher warp
+constexpr int kClThreads = kClTeam + 96;          // + producer, director and finisher warps
 constexpr int kClProducerWarp = kClTeamWarps;
 constexpr int kClDirectorWarp = kClTeamWarps + 1;
 constexpr int kClFinisherWarp = kClTeamWarps + 2;
+constexpr int kClBarDirector = 2;                 // named barriers 2, 3 (one per parity): warp 0 of the team -> director
 constexpr int kClMaxCtas = 8;
 constexpr int kClMaxChunks = 8;                   // 32 KB chunks of one CTA's part (<= 227 KB)
 constexpr int kClWarpList = 40;                   // masked samples (raw copies) per sweep warp
@@ -99,6 +106,16 @@ __device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, uint3
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {   // explicit shared-space load (no generic -> shared conversion in the loops)
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void cl_team_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kClTeam) : "memory"); }
 
 __device__ __forceinline__ double pair_tree8(const double* t_in, int stride) {
@@ -148,21 +165,24 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
   __syncthreads();
   cluster_sync_all();   // every CTA's barriers exist before anybody arrives on them remotely
 
+  // this CTA's part of halfspace b, chunk j: global -> shared, completion counted on full[j]
+  auto issue_chunk = [&](long long b, int j) {
+    const unsigned char* src =
+        reinterpret_cast<const unsigned char*>(a.samples) + static_cast<size_t>(b) * a.stride_b * sizeof(float) + part_lo;
+    const uint32_t off = static_cast<uint32_t>(j) * kBulkChunk;
+    const uint32_t n = part_b - off < kBulkChunk ? part_b - off : kBulkChunk;
+    mbar_expect_tx(&sh->full[j], n);
+    bulk_g2s(smem_raw + off, src + off, n, &sh->full[j]);
+  };
   // ============================================================================================ producer warp
   if (warp == kClProducerWarp) {
     if (lane == 0) {
       int it = 0;
-      for (long long b = q; b < a.B; b += n_clusters, ++it) {
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.samples) +
-                                   static_cast<size_t>(b) * a.stride_b * sizeof(float) + part_lo;
+      for (long long b = q; b < a.B; b += n_clusters, ++it)
         for (int j = 0; j < n_chunks; ++j) {
           if (it > 0) mbar_wait(&sh->free_[j], (it - 1) & 1);
-          const uint32_t off = static_cast<uint32_t>(j) * kBulkChunk;
-          const uint32_t n = part_b - off < kBulkChunk ? part_b - off : kBulkChunk;
-          mbar_expect_tx(&sh->full[j], n);
-          bulk_g2s(smem_raw + off, src + off, n, &sh->full[j]);
+          if (!(CL_DBG(2) && it > 0)) issue_chunk(b, j);
         }
-      }
     }
     return;
   }
@@ -175,7 +195,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       Ctl* ctl = &sh->ctl[par];
       const float* fp = reinterpret_cast<const float*>(a.samples) + b * a.stride_b;
       const double f0 = static_cast<double>(__ldg(fp)), f1 = static_cast<double>(__ldg(fp + 1));
-      mbar_wait_cluster(&sh->xbar1[par], (it >> 1) & 1);
+      bar_sync(kClBarDirector + par, 64);   // warp 0 of the team has seen exchange 1 complete: x1[par] is in
       // octant o = src * O + k lives at x1[par][src][2k + j]
       double w[2];
 #pragma unroll
@@ -233,7 +253,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     uint32_t n_lead = 0;
     for (long long b = q; b < a.B; b += n_clusters, ++it) {
       if (it % C != static_cast<int>(rank)) continue;
-      mbar_wait_cluster(&sh->xbar2, n_lead & 1u);
+      while (!mbar_try_wait(&sh->xbar2, n_lead & 1u)) __nanosleep(400);   // off everybody's path: poll slowly
       ++n_lead;
       Ctl* fc = &sh->fin_ctl;
       bool fast = fc->window_ok != 0 && fc->nonfinite == 0;
@@ -284,7 +304,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
   }
 
   // ============================================================================================ sweep team
-  const float4* slot4 = reinterpret_cast<const float4*>(smem_raw);
+  const uint32_t slot_s = smem_u32(smem_raw);
   const uint32_t toff = 16u * tid;
   const uint32_t woff = 16u * (tid & ~31);   // first byte of this warp inside a lane-row
   float2* wlist = sh->list[warp];
@@ -311,6 +331,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     const uint32_t fpar = it & 1;
     int have = 0;   // chunks of halfspace b known to have landed
     auto wait_upto = [&](uint32_t byte_off) {
+      if (CL_DBG(2) && it > 0) return;
       const int c = static_cast<int>(byte_off >> 15);
       while (have <= c) {
         mbar_wait_spin(&sh->full[have], fpar);
@@ -341,8 +362,8 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       for (; (lr + 4) * kClLaneRow <= len; lr += 4) {
         const uint32_t base = ob + lr * kClLaneRow + toff;
         wait_upto(base + 3 * kClLaneRow);
-        const float4 v0 = slot4[base >> 4], v1 = slot4[(base + kClLaneRow) >> 4], v2 = slot4[(base + 2 * kClLaneRow) >> 4],
-                     v3 = slot4[(base + 3 * kClLaneRow) >> 4];
+        const float4 v0 = lds128(slot_s + base), v1 = lds128(slot_s + base + kClLaneRow),
+                     v2 = lds128(slot_s + base + 2 * kClLaneRow), v3 = lds128(slot_s + base + 3 * kClLaneRow);
         body(v0);
         body(v1);
         body(v2);
@@ -353,7 +374,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         float4 v = make_float4(first.x, first.y, first.x, first.y);
         if (off + 8 <= oe) {
           wait_upto(off);
-          v = slot4[off >> 4];
+          v = lds128(slot_s + off);
           if (off + 16 > oe) {
             v.z = first.x;
             v.w = first.y;
@@ -409,6 +430,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       st_async_f64(dst + 88, static_cast<double>(b2), bar);
     }
     mbar_wait_cluster(&sh->xbar1[par], (it >> 1) & 1);
+    if (warp == 0) bar_arrive(kClBarDirector + par, 64);   // the director starts the canonical chain
     PH_MARK(3)
 
     // ------------------------------------------------------------------ window placement (warp 0; identical in every CTA)
@@ -532,7 +554,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
             const unsigned e = static_cast<unsigned>(__ffs(static_cast<int>(mk))) - 1u;
             const int pos = n_list + __popc(bal & lt_mask);
             if (pos < kClWarpList)
-              wlist[pos] = *reinterpret_cast<const float2*>(smem_raw + base + (e >> 1) * kClLaneRow + (e & 1u) * 8u);
+              wlist[pos] = lds64(slot_s + base + (e >> 1) * kClLaneRow + (e & 1u) * 8u);
           }
           n_list += __popc(bal);
           return;
@@ -566,7 +588,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         classify_f32(p0, thr_above, thr_keep, d0.x, d0.y, ax, ay, cf, mk, bit);
         classify_f32(p1, thr_above, thr_keep, d1.x, d1.y, ax, ay, cf, mk, bit + bit);
       };
-      for (int k = 0; k < O; ++k) {
+      for (int k = 0; k < (CL_DBG(4) ? 0 : O); ++k) {
         const uint32_t ob = static_cast<uint32_t>(k) * oct_b;
         const uint32_t oe = part_b < ob + oct_b ? part_b : ob + oct_b;
         const uint32_t len = oe > ob ? oe - ob : 0u;
@@ -575,14 +597,14 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         for (; (lr + 4) * kClLaneRow <= len; lr += 4) {
           const uint32_t base = ob + lr * kClLaneRow + toff;
           release_upto(static_cast<int>((ob + lr * kClLaneRow + woff) >> 15));
-          const float4 v0 = slot4[base >> 4], v1 = slot4[(base + kClLaneRow) >> 4], v2 = slot4[(base + 2 * kClLaneRow) >> 4],
-                       v3 = slot4[(base + 3 * kClLaneRow) >> 4];
+          const float4 v0 = lds128(slot_s + base), v1 = lds128(slot_s + base + kClLaneRow),
+                       v2 = lds128(slot_s + base + 2 * kClLaneRow), v3 = lds128(slot_s + base + 3 * kClLaneRow);
           unsigned mk = 0u;
           classify4(v0, mk, 1u, true, true);
           classify4(v1, mk, 4u, true, true);
           classify4(v2, mk, 16u, true, true);
           classify4(v3, mk, 64u, true, true);
-          if (__any_sync(kFull, mk != 0u)) extract(mk, base, v0, v1, v2, v3);
+          if (!CL_DBG(1) && __any_sync(kFull, mk != 0u)) extract(mk, base, v0, v1, v2, v3);
         }
         if (lr < n_lr) {   // last (up to 4) rows of the octant, possibly ragged
           release_upto(static_cast<int>((ob + lr * kClLaneRow + woff) >> 15));
@@ -594,7 +616,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
             if (lr + u < n_lr) {   // warp-uniform: rows beyond the octant cost nothing
               const uint32_t off = ob + (lr + u) * kClLaneRow + toff;
               const bool ok0 = off + 8 <= oe, ok1 = off + 16 <= oe;
-              if (ok0) vv[u] = slot4[off >> 4];
+              if (ok0) vv[u] = lds128(slot_s + off);
               classify4(vv[u], mk, 1u << (2 * u), ok0, ok1);
             }
           }

@@ -223,6 +223,7 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
 
 #ifdef DRCVAR_PROFILE_PHASES
   a.phase_cycles = g_phase_cycles;
+  if (const char* e = getenv("DRCVAR_DEBUG_FLAGS")) a.debug = atoi(e);
 #else
   a.phase_cycles = nullptr;
 #endif

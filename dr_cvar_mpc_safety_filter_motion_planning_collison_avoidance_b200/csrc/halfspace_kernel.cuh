@@ -120,6 +120,7 @@ struct KernelArgs {
   int cl_ctas;
   int* redo_count;
   int* redo_list;
+  int debug;   // profiling builds only: ablation switches
 };
 
 struct Ctl {                        // one per parity buffer
