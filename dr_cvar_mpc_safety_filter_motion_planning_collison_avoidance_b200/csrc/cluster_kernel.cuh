@@ -54,8 +54,8 @@ struct ClShared {
   float2 list[kClTeamWarps][kClWarpList];
   double red[kClTeamWarps * 2];
   double octtot[kOctants * 2];
-  double wsum[kClTeamWarps * 4];
-  float mom[kClTeamWarps * 4];
+  alignas(16) double wsum[kClTeamWarps * 4];
+  alignas(16) float mom[kClTeamWarps * 4];
   int wcnt[kClTeamWarps * 2];
   unsigned hist[kHistBuckets];
   double small[kResolveMax];
@@ -408,26 +408,32 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     cl_team_sync();
     PH_MARK(2)
     // ------------------------------------------------------------------ exchange 1: totals + moments to every CTA
-    if (tid < C) {   // thread d serves destination CTA d
-      // leader of this halfspace: our finisher must be done with the pool / x2 / fin_ctl of the halfspace we led last,
-      // before any CTA can get past exchange 1 and send the next candidates
-      if (static_cast<int>(rank) == leader && n_lead > 0) mbar_wait(&sh->fdone, (n_lead - 1) & 1u);
-      double qxx = 0.0, qxy = 0.0, qyy = 0.0;
-      float b2 = 0.f;
-      for (int w = 0; w < kClTeamWarps; ++w) {
-        qxx += static_cast<double>(sh->mom[w * 4]);
-        qxy += static_cast<double>(sh->mom[w * 4 + 1]);
-        qyy += static_cast<double>(sh->mom[w * 4 + 2]);
-        b2 = fmaxf(b2, sh->mom[w * 4 + 3]);
+    if (warp == 0) {
+      // this CTA's moments: lane w < 16 holds sweep warp w's partials, xor-butterfly over the 16 lanes
+      float4 mm = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < kClTeamWarps) mm = *reinterpret_cast<const float4*>(&sh->mom[lane * 4]);
+      double qxx = static_cast<double>(mm.x), qxy = static_cast<double>(mm.y), qyy = static_cast<double>(mm.z);
+      float b2 = mm.w;
+#pragma unroll
+      for (int m = 8; m >= 1; m >>= 1) {
+        qxx += shfl_xor_d(qxx, m);
+        qxy += shfl_xor_d(qxy, m);
+        qyy += shfl_xor_d(qyy, m);
+        b2 = fmaxf(b2, __shfl_xor_sync(kFull, b2, m));
       }
-      const uint32_t dst = mapa_u32(smem_u32(&sh->x1[par][rank][0]), static_cast<uint32_t>(tid));
-      const uint32_t bar = mapa_u32(smem_u32(&sh->xbar1[par]), static_cast<uint32_t>(tid));
-      mbar_arrive_expect_tx_remote(bar, 8u * (2u * O + 4u));
-      for (int i = 0; i < 2 * O; ++i) st_async_f64(dst + 8u * i, sh->octtot[i], bar);
-      st_async_f64(dst + 64, qxx, bar);
-      st_async_f64(dst + 72, qyy, bar);
-      st_async_f64(dst + 80, qxy, bar);
-      st_async_f64(dst + 88, static_cast<double>(b2), bar);
+      if (lane < C) {   // lane d serves destination CTA d
+        // leader of this halfspace: our finisher must be done with the pool / x2 / fin_ctl of the halfspace we led last,
+        // before any CTA can get past exchange 1 and send the next candidates
+        if (static_cast<int>(rank) == leader && n_lead > 0) mbar_wait(&sh->fdone, (n_lead - 1) & 1u);
+        const uint32_t dst = mapa_u32(smem_u32(&sh->x1[par][rank][0]), static_cast<uint32_t>(lane));
+        const uint32_t bar = mapa_u32(smem_u32(&sh->xbar1[par]), static_cast<uint32_t>(lane));
+        mbar_arrive_expect_tx_remote(bar, 8u * (2u * O + 4u));
+        for (int i = 0; i < 2 * O; ++i) st_async_f64(dst + 8u * i, sh->octtot[i], bar);
+        st_async_f64(dst + 64, qxx, bar);
+        st_async_f64(dst + 72, qyy, bar);
+        st_async_f64(dst + 80, qxy, bar);
+        st_async_f64(dst + 88, static_cast<double>(b2), bar);
+      }
     }
     mbar_wait_cluster(&sh->xbar1[par], (it >> 1) & 1);
     if (warp == 0) bar_arrive(kClBarDirector + par, 64);   // the director starts the canonical chain
@@ -532,9 +538,10 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       if (lane == 0) {   // the leader's finisher puts the halfspace on the redo list (fin_ctl.window_ok == 0)
         if (tid == 0 && static_cast<int>(rank) == leader) {
           sh->fin_ctl = *ctl;
-          __threadfence_block();
+          mbar_arrive(&sh->xbar2);   // local arrive: release.cta orders the copy
+        } else {
+          mbar_arrive_expect_tx_remote(mapa_u32(smem_u32(&sh->xbar2), static_cast<uint32_t>(leader)), 0u);
         }
-        mbar_arrive_expect_tx_remote(mapa_u32(smem_u32(&sh->xbar2), static_cast<uint32_t>(leader)), 0u);
       }
       if (static_cast<int>(rank) == leader) ++n_lead;
       continue;
@@ -606,21 +613,26 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
           classify4(v3, mk, 64u, true, true);
           if (!CL_DBG(1) && __any_sync(kFull, mk != 0u)) extract(mk, base, v0, v1, v2, v3);
         }
-        if (lr < n_lr) {   // last (up to 4) rows of the octant, possibly ragged
+        if (lr < n_lr) {   // last (up to 3 whole + 1 ragged) rows of the octant, one at a time
           release_upto(static_cast<int>((ob + lr * kClLaneRow + woff) >> 15));
-          float4 vv[4];
+          const uint32_t base = ob + lr * kClLaneRow + toff;
+          const float4 f4 = make_float4(first.x, first.y, first.x, first.y);
+          float4 vv[4] = {f4, f4, f4, f4};
           unsigned mk = 0u;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            vv[u] = make_float4(first.x, first.y, first.x, first.y);
-            if (lr + u < n_lr) {   // warp-uniform: rows beyond the octant cost nothing
-              const uint32_t off = ob + (lr + u) * kClLaneRow + toff;
-              const bool ok0 = off + 8 <= oe, ok1 = off + 16 <= oe;
-              if (ok0) vv[u] = lds128(slot_s + off);
-              classify4(vv[u], mk, 1u << (2 * u), ok0, ok1);
+            if (lr + u < n_lr) {   // warp-uniform
+              const uint32_t off = base + u * kClLaneRow;
+              if (off + 16 <= oe) {           // whole 16 bytes inside the octant (every row but the ragged last one)
+                vv[u] = lds128(slot_s + off);
+                classify4(vv[u], mk, 1u << (2 * u), true, true);
+              } else if (off + 8 <= oe) {     // N odd: only the first sample of the pair exists
+                vv[u] = lds128(slot_s + off);
+                classify4(vv[u], mk, 1u << (2 * u), true, false);
+              }
             }
           }
-          if (__any_sync(kFull, mk != 0u)) extract(mk, ob + lr * kClLaneRow + toff, vv[0], vv[1], vv[2], vv[3]);
+          if (!CL_DBG(1) && __any_sync(kFull, mk != 0u)) extract(mk, base, vv[0], vv[1], vv[2], vv[3]);
         }
       }
     }
@@ -685,34 +697,45 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       if (total > cap) ovf = 1;
       const uint32_t bar = mapa_u32(smem_u32(&sh->xbar2), static_cast<uint32_t>(leader));
       if (lane == 0) {
-        if (tid == 0 && static_cast<int>(rank) == leader) {   // what our finisher needs of ctl[par], which the team reuses
+        const uint32_t tx = (ovf ? 0u : 8u * nc) + (tid == 0 ? 32u : 0u);
+        if (tid == 0 && static_cast<int>(rank) == leader) {
+          // what our finisher needs of ctl[par], which the team reuses; the LOCAL arrive releases the copy (release.cta)
           sh->fin_ctl = *ctl;
-          __threadfence_block();
+          mbar_expect_tx(&sh->xbar2, tx);
+        } else {
+          mbar_arrive_expect_tx_remote(bar, tx);
         }
-        mbar_arrive_expect_tx_remote(bar, (ovf ? 0u : 8u * nc) + (tid == 0 ? 32u : 0u));
       }
       if (!ovf) {
         const double* wcand = reinterpret_cast<const double*>(wlist);
         const uint32_t dst = mapa_u32(smem_u32(&sh->pool[rank * cap + before]), static_cast<uint32_t>(leader));
         for (int j = lane; j < nc; j += 32) st_async_f64(dst + 8u * j, wcand[j], bar);
       }
-      if (tid == 0) {
+      if (warp == 0) {   // CTA totals of the "surely above" set: lane w < 16 holds warp w's partials, fixed butterfly
         double n_above = 0.0, sdx = 0.0, sdy = 0.0;
-        for (int w = 0; w < kClTeamWarps; ++w) {
-          n_above += sh->wsum[w * 4];
-          sdx += sh->wsum[w * 4 + 1];
-          sdy += sh->wsum[w * 4 + 2];
+        if (lane < kClTeamWarps) {
+          n_above = sh->wsum[lane * 4];
+          sdx = sh->wsum[lane * 4 + 1];
+          sdy = sh->wsum[lane * 4 + 2];
         }
-        const uint32_t dst = mapa_u32(smem_u32(&sh->x2[rank][0]), static_cast<uint32_t>(leader));
-        st_async_f64(dst, n_above, bar);
-        st_async_f64(dst + 8, sdx, bar);
-        st_async_f64(dst + 16, sdy, bar);
-        st_async_f64(dst + 24, ovf ? -1.0 : static_cast<double>(total), bar);
+#pragma unroll
+        for (int m = 8; m >= 1; m >>= 1) {
+          n_above += shfl_xor_d(n_above, m);
+          sdx += shfl_xor_d(sdx, m);
+          sdy += shfl_xor_d(sdy, m);
+        }
+        if (lane == 0) {
+          const uint32_t dst = mapa_u32(smem_u32(&sh->x2[rank][0]), static_cast<uint32_t>(leader));
+          st_async_f64(dst, n_above, bar);
+          st_async_f64(dst + 8, sdx, bar);
+          st_async_f64(dst + 16, sdy, bar);
+          st_async_f64(dst + 24, ovf ? -1.0 : static_cast<double>(total), bar);
+        }
       }
       if (static_cast<int>(rank) == leader) ++n_lead;
     }
     PH_MARK(9)
-    cl_team_sync();   // list / wsum / wcnt are free again (a slow warp may still have been sending from its list)
+    // (list / wsum / wcnt are next written behind the team barriers of the next halfspace's octant trees)
     PH_MARK(10)
   }
 #ifdef DRCVAR_PROFILE_PHASES

@@ -114,12 +114,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
     const int oct_len = n_oct == 1 ? N : octant_samples(N, sizeof(T));
     float q_xx = 0.f, q_yy = 0.f, q_xy = 0.f, q_dx = 0.f, q_dy = 0.f;
     int n_sub_i = 0;   // fp64 inputs: samples behind the second moments (rows 0, 4, 8, ... of every octant)
-    for (int oc = 0; oc < n_oct; ++oc) {
-      const int i_lo = oc * oct_len;
-      const int n_k = N - i_lo < oct_len ? (N - i_lo > 0 ? N - i_lo : 0) : oct_len;
-      const int full_rows = n_k / kRowSamples;
-      const int rows_all = (n_k + kRowSamples - 1) / kRowSamples;
-      double s_x, s_y;                       // this thread's slot sums
+    double sx[kOctants], sy[kOctants];   // this thread's slot sums, per octant
+#pragma unroll
+    for (int oc = 0; oc < kOctants; ++oc) sx[oc] = sy[oc] = 0.0;
+    if (n_oct == 1) {
+      const int full_rows = N / kRowSamples;
+      const int rows_all = (N + kRowSamples - 1) / kRowSamples;
       if constexpr (kF32) {
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f), sq = make_float2(0.f, 0.f);
         float sxy = 0.f;
@@ -132,37 +132,35 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
         };
         int r = half;
         if (vec) {
-          const int it_lo = i_lo >> 1;   // octants start on whole rows: i_lo is even
 #pragma unroll 8
           for (; r < full_rows; r += 2) {
-            const float4 v = load4(it_lo + r * kSweepThreads + lt);
+            const float4 v = load4(r * kSweepThreads + lt);
             body(make_float2(v.x, v.y), acc0);
             body(make_float2(v.z, v.w), acc1);
           }
         } else {
           for (; r < full_rows; r += 2) {
-            const int i0 = i_lo + r * kRowSamples + 2 * lt;
+            const int i0 = r * kRowSamples + 2 * lt;
             body(load(i0), acc0);
             body(load(i0 + 1), acc1);
           }
         }
         if (r == full_rows && full_rows < rows_all) {   // ragged last row (only the half with its parity)
-          const int i0 = i_lo + r * kRowSamples + 2 * lt;
+          const int i0 = r * kRowSamples + 2 * lt;
           if (i0 < N) body(load(i0), acc0);
           if (i0 + 1 < N) body(load(i0 + 1), acc1);
         }
-        s_x = __dadd_rn(static_cast<double>(acc0.x), static_cast<double>(acc1.x));   // lanes 2 slot, 2 slot + 1
-        s_y = __dadd_rn(static_cast<double>(acc0.y), static_cast<double>(acc1.y));
-        q_xx += sq.x;
-        q_yy += sq.y;
-        q_xy += sxy;
+        sx[0] = __dadd_rn(static_cast<double>(acc0.x), static_cast<double>(acc1.x));   // lanes 2 slot, 2 slot + 1
+        sy[0] = __dadd_rn(static_cast<double>(acc0.y), static_cast<double>(acc1.y));
+        q_xx = sq.x;
+        q_yy = sq.y;
+        q_xy = sxy;
       } else {
-        s_x = 0.0;
-        s_y = 0.0;
+        double s_x = 0.0, s_y = 0.0;
         double dxx = 0.0, dyy = 0.0, dxy = 0.0, ddx = 0.0, ddy = 0.0;
 #pragma unroll 8
         for (int r = half; r < rows_all; r += 2) {
-          const int i = i_lo + r * kRowSamples + lt;
+          const int i = r * kRowSamples + lt;
           if (i < N) {
             const V2 v = load(i);
             s_x = __dadd_rn(s_x, v.x);
@@ -177,43 +175,140 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
             }
           }
         }
-        q_xx += static_cast<float>(dxx);
-        q_yy += static_cast<float>(dyy);
-        q_xy += static_cast<float>(dxy);
-        q_dx += static_cast<float>(ddx);
-        q_dy += static_cast<float>(ddy);
-        if (n_k > 0) {
-          const int r4 = (rows_all + 3) / 4;
-          const int last = (r4 - 1) * 4 * kRowSamples;
-          n_sub_i += (r4 - 1) * kSweepThreads + (n_k - last < kSweepThreads ? n_k - last : kSweepThreads);
+        sx[0] = s_x;
+        sy[0] = s_y;
+        q_xx = static_cast<float>(dxx);
+        q_yy = static_cast<float>(dyy);
+        q_xy = static_cast<float>(dxy);
+        q_dx = static_cast<float>(ddx);
+        q_dy = static_cast<float>(ddy);
+        const int r4 = (rows_all + 3) / 4;
+        const int last = (r4 - 1) * 4 * kRowSamples;
+        n_sub_i = (r4 - 1) * kSweepThreads + (N - last < kSweepThreads ? N - last : kSweepThreads);
+      }
+    } else {
+      // the 8 octants side by side: row r of every octant in one iteration (8 independent 16-byte loads in flight per
+      // thread), each octant with its own accumulators; within an octant the rows are still added in increasing order
+      const int rows_oct = oct_len / kRowSamples;   // octants are whole 4 KB rows
+      if constexpr (kF32) {
+        float2 a0[kOctants], a1[kOctants];
+#pragma unroll
+        for (int oc = 0; oc < kOctants; ++oc) a0[oc] = a1[oc] = make_float2(0.f, 0.f);
+        float2 sq = make_float2(0.f, 0.f);
+        float sxy = 0.f;
+        const float2 nf = make_float2(-first.x, -first.y);
+        auto body = [&](float2 v, float2& acc) {
+          const float2 d = __fadd2_rn(v, nf);
+          acc = __fadd2_rn(acc, d);
+          sq = __ffma2_rn(d, d, sq);
+          sxy = fmaf(d.x, d.y, sxy);
+        };
+        for (int r = half; r < rows_oct; r += 2) {
+          float4 v[kOctants];
+#pragma unroll
+          for (int oc = 0; oc < kOctants; ++oc) {
+            const int i0 = oc * oct_len + r * kRowSamples + 2 * lt;
+            v[oc] = make_float4(first.x, first.y, first.x, first.y);   // samples beyond N count as `first` (shifted value +0)
+            if (i0 + 1 < N) {
+              if (vec) {
+                v[oc] = load4(i0 >> 1);
+              } else {
+                const V2 p0 = load(i0), p1 = load(i0 + 1);
+                v[oc] = make_float4(p0.x, p0.y, p1.x, p1.y);
+              }
+            } else if (i0 < N) {
+              const V2 p0 = load(i0);
+              v[oc].x = p0.x;
+              v[oc].y = p0.y;
+            }
+          }
+#pragma unroll
+          for (int oc = 0; oc < kOctants; ++oc) {
+            body(make_float2(v[oc].x, v[oc].y), a0[oc]);
+            body(make_float2(v[oc].z, v[oc].w), a1[oc]);
+          }
+        }
+#pragma unroll
+        for (int oc = 0; oc < kOctants; ++oc) {
+          sx[oc] = __dadd_rn(static_cast<double>(a0[oc].x), static_cast<double>(a1[oc].x));
+          sy[oc] = __dadd_rn(static_cast<double>(a0[oc].y), static_cast<double>(a1[oc].y));
+        }
+        q_xx = sq.x;
+        q_yy = sq.y;
+        q_xy = sxy;
+      } else {
+        double dxx = 0.0, dyy = 0.0, dxy = 0.0, ddx = 0.0, ddy = 0.0;
+        for (int r = half; r < rows_oct; r += 2) {
+          V2 v[kOctants];
+          bool ok[kOctants];
+#pragma unroll
+          for (int oc = 0; oc < kOctants; ++oc) {
+            const int i = oc * oct_len + r * kRowSamples + lt;
+            ok[oc] = i < N;
+            v[oc] = first;
+            if (ok[oc]) v[oc] = load(i);
+          }
+#pragma unroll
+          for (int oc = 0; oc < kOctants; ++oc) {
+            if (ok[oc]) {
+              sx[oc] = __dadd_rn(sx[oc], v[oc].x);
+              sy[oc] = __dadd_rn(sy[oc], v[oc].y);
+              if ((r & 3) == 0) {   // second moments on every 4th row of every octant
+                const double dx = v[oc].x - first.x, dy = v[oc].y - first.y;
+                ddx += dx;
+                ddy += dy;
+                dxx = fma(dx, dx, dxx);
+                dyy = fma(dy, dy, dyy);
+                dxy = fma(dx, dy, dxy);
+              }
+            }
+          }
+        }
+        q_xx = static_cast<float>(dxx);
+        q_yy = static_cast<float>(dyy);
+        q_xy = static_cast<float>(dxy);
+        q_dx = static_cast<float>(ddx);
+        q_dy = static_cast<float>(ddy);
+        for (int oc = 0; oc < kOctants; ++oc) {
+          const int n_k = N - oc * oct_len < oct_len ? (N - oc * oct_len > 0 ? N - oc * oct_len : 0) : oct_len;
+          if (n_k > 0) {
+            const int rows_k = (n_k + kRowSamples - 1) / kRowSamples;
+            const int r4 = (rows_k + 3) / 4;
+            const int last = (r4 - 1) * 4 * kRowSamples;
+            n_sub_i += (r4 - 1) * kSweepThreads + (n_k - last < kSweepThreads ? n_k - last : kSweepThreads);
+          }
         }
       }
-      if (half == 1) {
-        xch[2 * lt] = s_x;
-        xch[2 * lt + 1] = s_y;
-      }
-      __syncthreads();
-      if (half == 0) {   // u[j] = s[j] + s[j + 256], then the canonical butterfly inside each group of 32
-        const double tx = warp_sum_canon(__dadd_rn(s_x, xch[2 * lt]));
-        const double ty = warp_sum_canon(__dadd_rn(s_y, xch[2 * lt + 1]));
-        if (lane == 0) {
-          red[warp * 8] = tx;
-          red[warp * 8 + 1] = ty;
+    }
+    // per octant: u[j] = s[j] + s[j + 256], canonical butterfly inside each group of 32, adjacent-pair tree over the 8 groups
+#pragma unroll
+    for (int oc = 0; oc < kOctants; ++oc) {
+      if (oc < n_oct) {
+        if (half == 1) {
+          xch[2 * lt] = sx[oc];
+          xch[2 * lt + 1] = sy[oc];
+        }
+        __syncthreads();
+        if (half == 0) {
+          const double tx = warp_sum_canon(__dadd_rn(sx[oc], xch[2 * lt]));
+          const double ty = warp_sum_canon(__dadd_rn(sy[oc], xch[2 * lt + 1]));
+          if (lane == 0) {
+            red[warp * 8] = tx;
+            red[warp * 8 + 1] = ty;
+          }
+        }
+        __syncthreads();
+        if (tid < 2) {
+          double t[kSweepWarps];
+#pragma unroll
+          for (int g = 0; g < kSweepWarps; ++g) t[g] = red[g * 8 + tid];
+#pragma unroll
+          for (int n = kSweepWarps; n > 1; n >>= 1)
+#pragma unroll
+            for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);
+          oct_tot[2 * oc + tid] = t[0];
         }
       }
-      __syncthreads();
-      if (tid < 2) {     // adjacent-pair tree over the 8 group totals -> total of this octant (coordinate tid)
-        double t[kSweepWarps];
-#pragma unroll
-        for (int g = 0; g < kSweepWarps; ++g) t[g] = red[g * 8 + tid];
-#pragma unroll
-        for (int n = kSweepWarps; n > 1; n >>= 1)
-#pragma unroll
-          for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);
-        oct_tot[2 * oc + tid] = t[0];
-      }
-      // (the next octant's xch / red writes are ordered behind this read by its own first __syncthreads: red is only
-      //  rewritten after that barrier, xch is not read here)
     }
     {
       const float mxx = warp_sum_any(q_xx), myy = warp_sum_any(q_yy), mxy = warp_sum_any(q_xy);
