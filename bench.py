@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-generated", action="store_true", help="skip the generate-mode leg (samples drawn in-kernel)")
+    ap.add_argument("--no-large-n", action="store_true", help="skip the N = 100 000 leg (cluster / DSMEM kernel)")
+    ap.add_argument("--large-n-halfspaces", type=int, default=16384, help="halfspaces of the N = 100 000 leg")
     return ap.parse_args()
 
 
@@ -386,6 +388,38 @@ def run_ours(a):
                      "note": "samples drawn in-kernel (Philox4x32-10 + fp32 Box-Muller, oracle/sample_gen.py); "
                              "per-rank numbers scaled by world size"}
 
+    # ---- BASELINE config 5 sample count (N = 100 000) on a shard that fits next to the headline batch: the cluster /
+    #      DSMEM kernel (one cluster of 4 CTAs per halfspace, every sample read once) beside the two-pass streaming kernel
+    large_n = None
+    if a.dtype == "f32" and not a.no_large_n and N <= 32768:
+        NL, BL = 100000, a.large_n_halfspaces
+        free, _t = torch.cuda.mem_get_info(device)
+        BL = int(max(0, min(BL, (free - (6 << 30)) // (NL * 8))))
+        if BL >= 1024:
+            sl, egl = make_device_batch(BL, NL, torch.float32, device, seed=777 + rank, chunk=256)
+            bytes_l = algorithmic_bytes_per_halfspace(NL, 4) * BL
+            large_n = {"samples_per_halfspace": NL, "halfspaces_per_gpu": BL, "unit": UNIT}
+            for name, fl in (("cluster_kernel", 0), ("streaming_kernel", _lib.FLAG_NO_CLUSTER)):
+                lo = None
+                for _ in range(2):
+                    lo = pkg.compute_halfspaces(sl, egl, stream=stream, out=lo, flags=fl, **RISK)
+                torch.cuda.synchronize(device)
+                ls, le = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ls.record(stream)
+                for _ in range(3):
+                    lo = pkg.compute_halfspaces(sl, egl, stream=stream, out=lo, flags=fl, **RISK)
+                le.record(stream)
+                torch.cuda.synchronize(device)
+                l_ms = ls.elapsed_time(le) / 3
+                large_n[name] = {"value": world * BL / (l_ms * 1e-3), "ms_per_launch": l_ms,
+                                 "hbm_gbs": bytes_l / (l_ms * 1e-3) / 1e9,
+                                 "general_path_halfspaces": int((lo.status & 2 != 0).sum().item())}
+                if name == "cluster_kernel":
+                    keep = (lo.h.clone(), lo.var.clone())
+                else:
+                    large_n["bit_identical_h_and_T"] = bool(torch.equal(keep[0], lo.h) and torch.equal(keep[1], lo.var))
+            del sl, egl
+
     # ---- roofline of the (single) kernel
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -405,7 +439,9 @@ def run_ours(a):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "halfspace_kernel",
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": "halfspace_kernel" if N <= pkg.max_samples(np.float32 if a.dtype == "f32" else np.float64)
+                else ("cluster_kernel_f32" if a.dtype == "f32" and N > 32768 else "streaming_kernel"),
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_avg": kern_ms_avg}
 
     # ---- CPU baseline beside it (rank 0, N = 1 GPU only) + parity spot-check of the timed results
@@ -426,7 +462,8 @@ def run_ours(a):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "metric": METRIC if N == 10000 else f"DR-CVaR halfspaces/sec at N={N} samples", "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "halfspaces_per_gpu": B, "samples_per_halfspace": N,
@@ -437,6 +474,7 @@ def run_ours(a):
                     "halfspaces_per_step": Be, "steps": e2e_steps,
                     "note": "compute_halfspaces() on pinned host numpy buffers: chunked H2D + kernel + D2H inside the timed region"},
             "gpu_launches": launches, "clocks": clocks, "hbm_gbs_aggregate": achieved * world, "generated": generated,
+            "large_n": None if large_n is None else dict(large_n, hbm_peak_gbs=peak, note="per-rank shard, scaled by world size"),
             "gather_ms": gather_ms, "parity_spot_check": parity,
             "status_fallback_halfspaces": int((out.status != 0).sum().item()),
         }
