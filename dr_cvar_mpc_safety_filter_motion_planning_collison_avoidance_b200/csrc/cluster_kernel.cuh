@@ -359,11 +359,13 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       };
       const uint32_t n_lr = (len + kClLaneRow - 1) / kClLaneRow;
       uint32_t lr = 0;
+      if (4 * kClLaneRow <= len) wait_upto(ob + toff + 3 * kClLaneRow);
       for (; (lr + 4) * kClLaneRow <= len; lr += 4) {
         const uint32_t base = ob + lr * kClLaneRow + toff;
-        wait_upto(base + 3 * kClLaneRow);
         const float4 v0 = lds128(slot_s + base), v1 = lds128(slot_s + base + kClLaneRow),
                      v2 = lds128(slot_s + base + 2 * kClLaneRow), v3 = lds128(slot_s + base + 3 * kClLaneRow);
+        // the (≈90-cycle) barrier test for the NEXT group overlaps these loads and the arithmetic below
+        if ((lr + 8) * kClLaneRow <= len) wait_upto(base + 7 * kClLaneRow);
         body(v0);
         body(v1);
         body(v2);

@@ -76,8 +76,11 @@ int drcvar_reduction_lanes(void);
  */
 int64_t drcvar_tail_count(double alpha, int64_t n_samples, double* k_f_out);
 
-/* Largest N the single-read shared-memory kernel holds for a sample dtype of `elem_bytes` (4 or 8) on `device`;
- * larger N is served by the two-pass streaming kernel (same results, two reads of the samples). */
+/* Largest N the single-CTA shared-memory kernel holds for a sample dtype of `elem_bytes` (4 or 8) on `device`.
+ * Larger N: fp32 samples with 32768 < N <= ~205000 (contiguous, 16-byte aligned rows) are served by the cluster / DSMEM
+ * kernel (one thread-block cluster per halfspace, one read of the samples; halfspaces it cannot finish — window miss,
+ * non-finite data — are redone by the streaming kernel in the same stream); everything else by the two-pass streaming
+ * kernel (same results, two reads of the samples). */
 int64_t drcvar_max_samples(int elem_bytes, int device);
 
 /*
