@@ -430,14 +430,15 @@ def run_ours(a):
     alg_bytes = algorithmic_bytes_per_halfspace(N, elem) * B
     achieved = alg_bytes / (kern_ms_avg * 1e-3) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            tj = json.load(open(tpath))
-            if tj.get("samples") == N and tj.get("dtype") == a.dtype:
-                traffic = tj["dram_bytes_per_halfspace"] * B
-        except Exception:
-            traffic = None
+    for tname in ("traffic.json", "traffic_n100k.json"):   # DRAM bytes per halfspace from the committed ncu captures
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                if tj.get("samples") == N and tj.get("dtype") == a.dtype:
+                    traffic = tj["dram_bytes_per_halfspace"] * B
+            except Exception:
+                pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "kernel": "halfspace_kernel" if N <= pkg.max_samples(np.float32 if a.dtype == "f32" else np.float64)
