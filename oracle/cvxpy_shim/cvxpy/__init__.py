@@ -10,8 +10,12 @@ programs with their own constraint loops.  The LP is then solved by HiGHS
 (scipy.optimize.linprog) in place of ECOS (ecos==2.0.14, environment.yml:33).
 
 So: LP construction = the reference's code, verbatim at run time; numerical solver = HiGHS.
-Anything non-linear (quad_form, square, ... used by the MPC QP, core/mpc_filter.py) raises
-NotImplementedError: the MPC consumer is outside this repo's scope.
+
+The CONSUMER of the halfspaces, the MPC safety filter's QP (core/mpc_filter.py:40-178: 2-D variables, `A @ x[t]`,
+equality constraints, `quad_form`, `square`, `multiply`), is supported too, so that the downstream-trajectory parity of
+BASELINE's north star can be checked: the QP is assembled from the reference's own constraint loops and solved by a
+dense primal-dual interior-point method (`solve_qp` below, tolerance 1e-10) in place of cvxpy's default OSQP
+(osqp==1.0.1, environment.yml:42).  `norm` / `sum_squares` remain unimplemented.
 """
 from __future__ import annotations
 
@@ -126,6 +130,19 @@ class Expression:
             return Expression(self.rows[i])
         return Expression([self.rows[i]])
 
+    def __rmatmul__(self, mat):          # numpy matrix @ affine vector (core/mpc_filter.py:84,96)
+        m = np.asarray(mat, dtype=np.float64)
+        if m.ndim != 2 or m.shape[1] != self.size:
+            raise ValueError("shape mismatch in cvxpy shim matmul")
+        out = []
+        for k in range(m.shape[0]):
+            acc = _Row()
+            for j in range(m.shape[1]):
+                if m[k, j] != 0.0:
+                    acc = acc.plus(self.rows[j].scaled(float(m[k, j])))
+            out.append(acc)
+        return Expression(out)
+
     # ---- constraints:  lhs <= rhs  stored as (lhs - rhs) <= 0
     def __le__(self, other):
         return Constraint(self - other)
@@ -133,25 +150,52 @@ class Expression:
     def __ge__(self, other):
         return Constraint(Expression._lift(other) - self)
 
-    def __eq__(self, other):  # pragma: no cover - not used by the LPs
-        raise NotImplementedError("cvxpy shim: equality constraints not supported")
+    def __eq__(self, other):             # equality constraints (MPC dynamics, core/mpc_filter.py:80-84)
+        return Constraint(self - other, kind="eq")
 
     __hash__ = object.__hash__
 
 
 class Variable(Expression):
     def __init__(self, shape=1, nonneg=False, name=None, **kw):
+        self.shape2 = None
         if isinstance(shape, tuple):
-            if len(shape) != 1:
-                raise NotImplementedError("cvxpy shim: only 1-D variables")
-            shape = shape[0]
+            if len(shape) == 2:              # x[t] -> row t (core/mpc_filter.py:59-60)
+                self.shape2 = (int(shape[0]), int(shape[1]))
+                shape = self.shape2[0] * self.shape2[1]
+            elif len(shape) == 1:
+                shape = shape[0]
+            elif len(shape) == 0:
+                shape = 1
+            else:
+                raise NotImplementedError("cvxpy shim: only scalar, 1-D and 2-D variables")
         if kw:
             raise NotImplementedError(f"cvxpy shim: Variable attributes {list(kw)} not supported")
         self.n = int(shape)
         self.nonneg = bool(nonneg)
         self.name = name
-        self.value = None
+        self._value = None
         super().__init__([_Row({(self, i): 1.0}) for i in range(self.n)])
+
+    @property
+    def value(self):
+        if self._value is None or self.shape2 is None:
+            return self._value
+        return self._value.reshape(self.shape2)
+
+    @value.setter
+    def value(self, v):
+        self._value = v
+
+    def __getitem__(self, i):
+        if self.shape2 is None:
+            return super().__getitem__(i)
+        if isinstance(i, (int, np.integer)):
+            t = int(i)
+            if t < 0:
+                t += self.shape2[0]
+            return Expression(self.rows[t * self.shape2[1]:(t + 1) * self.shape2[1]])
+        raise NotImplementedError("cvxpy shim: 2-D variables support row indexing only")
 
 
 class Parameter(Expression):
@@ -164,12 +208,47 @@ class Parameter(Expression):
 
 
 class Constraint:
-    def __init__(self, expr_le_zero):
-        self.expr = expr_le_zero
+    def __init__(self, expr_le_zero, kind="le"):
+        self.expr = expr_le_zero     # kind "le": expr <= 0;  kind "eq": expr == 0
+        self.kind = kind
+
+
+class QuadExpr:
+    """Scalar convex objective: sum_k coef_k * e_k^T Q_k e_k (e_k affine vectors) + an affine scalar."""
+    __array_ufunc__ = None
+
+    def __init__(self, quads=None, affine=None):
+        self.quads = quads or []                 # (coef, rows, Q)
+        self.affine = affine or _Row()
+
+    def _plus(self, other):
+        if isinstance(other, QuadExpr):
+            return QuadExpr(self.quads + other.quads, self.affine.plus(other.affine))
+        if isinstance(other, Expression):
+            if other.size != 1:
+                raise ValueError("objective terms must be scalar")
+            return QuadExpr(list(self.quads), self.affine.plus(other.rows[0]))
+        if _is_number(other):
+            return QuadExpr(list(self.quads), self.affine.plus(_Row(const=float(other))))
+        return NotImplemented
+
+    __add__ = _plus
+    __radd__ = _plus
+
+    def __mul__(self, c):
+        if not _is_number(c) or c < 0:
+            raise NotImplementedError("cvxpy shim: only nonnegative scalar * quadratic")
+        return QuadExpr([(q[0] * float(c), q[1], q[2]) for q in self.quads], self.affine.scaled(float(c)))
+
+    __rmul__ = __mul__
 
 
 class Minimize:
     def __init__(self, expr):
+        self.quad = None
+        if isinstance(expr, QuadExpr):
+            self.quad = expr
+            expr = Expression([expr.affine])
         expr = Expression._lift(expr)
         if expr.size != 1:
             raise ValueError("objective must be scalar")
@@ -189,9 +268,78 @@ def _unsupported(name):
     return f
 
 
-quad_form = _unsupported("quad_form")
-square = _unsupported("square")
-multiply = _unsupported("multiply")
+def quad_form(expr, Q):            # e^T Q e  (core/mpc_filter.py:70,73)
+    expr = Expression._lift(expr)
+    Q = np.asarray(Q, dtype=np.float64)
+    if Q.shape != (expr.size, expr.size):
+        raise ValueError("quad_form shape mismatch")
+    return QuadExpr([(1.0, list(expr.rows), 0.5 * (Q + Q.T))])
+
+
+def square(expr):                  # core/mpc_filter.py:146
+    expr = Expression._lift(expr)
+    if expr.size != 1:
+        raise NotImplementedError("cvxpy shim: square of a scalar only")
+    return QuadExpr([(1.0, list(expr.rows), np.ones((1, 1)))])
+
+
+def multiply(a, expr):             # elementwise constant * affine (core/mpc_filter.py:139)
+    expr = Expression._lift(expr)
+    arr = np.asarray(a, dtype=np.float64).ravel()
+    if arr.size != expr.size:
+        raise ValueError("multiply shape mismatch")
+    return Expression([r.scaled(float(c)) for r, c in zip(expr.rows, arr)])
+
+
+def solve_qp(P, q, G, h, A, b, tol=1e-10, max_iter=200):
+    """min 0.5 z'Pz + q'z  s.t.  Gz <= h, Az = b  — dense Mehrotra predictor-corrector interior-point method."""
+    n, m, p = q.shape[0], h.shape[0], b.shape[0]
+    z, y = np.zeros(n), np.zeros(p)
+    s, lam = np.ones(m), np.ones(m)
+    if m:
+        s = np.maximum(h - G @ z, 1.0)
+    scale = 1.0 + max(np.abs(q).max(initial=0.0), np.abs(h).max(initial=0.0), np.abs(b).max(initial=0.0))
+    for it in range(max_iter):
+        rd = P @ z + q + (G.T @ lam if m else 0.0) + (A.T @ y if p else 0.0)
+        rp = G @ z + s - h if m else np.zeros(0)
+        re = A @ z - b if p else np.zeros(0)
+        mu = float(s @ lam) / m if m else 0.0
+        if max(np.abs(rd).max(initial=0.0), np.abs(rp).max(initial=0.0), np.abs(re).max(initial=0.0)) <= tol * scale \
+                and mu <= tol:
+            return z, True, it
+        W = lam / s if m else np.zeros(0)
+        H = P + (G.T @ (W[:, None] * G) if m else 0.0) + 1e-13 * np.eye(n)
+        K = np.block([[H, A.T], [A, -1e-13 * np.eye(p)]]) if p else H
+
+        def direction(rc):
+            rhs = -rd - (G.T @ ((lam * rp - rc) / s) if m else 0.0)
+            sol = np.linalg.solve(K, np.concatenate([rhs, -re]) if p else rhs)
+            dz, dy = sol[:n], sol[n:]
+            ds = -rp - G @ dz if m else np.zeros(0)
+            dlam = (-rc - lam * ds) / s if m else np.zeros(0)
+            return dz, dy, ds, dlam
+
+        def step_len(v, dv):
+            neg = dv < 0
+            return min(1.0, float(np.min(-v[neg] / dv[neg]))) if neg.any() else 1.0
+
+        dz, dy, ds, dlam = direction(s * lam)
+        if m:
+            a_aff = min(step_len(s, ds), step_len(lam, dlam))
+            mu_aff = float((s + a_aff * ds) @ (lam + a_aff * dlam)) / m
+            sigma = (mu_aff / mu) ** 3 if mu > 0 else 0.0
+            dz, dy, ds, dlam = direction(s * lam + ds * dlam - sigma * mu)
+            a = 0.995 * min(step_len(s, ds), step_len(lam, dlam))
+            a = min(a, 1.0)
+            s = s + a * ds
+            lam = lam + a * dlam
+        else:
+            a = 1.0
+        z = z + a * dz
+        y = y + a * dy
+    return z, False, max_iter
+
+
 norm = _unsupported("norm")
 sum_squares = _unsupported("sum_squares")
 
@@ -214,6 +362,9 @@ class Problem:
                         self._vars.append(v)
 
         visit(objective.expr)
+        if objective.quad is not None:
+            for _c, qrows, _Q in objective.quad.quads:
+                visit(Expression(qrows))
         for c in self.constraints:
             visit(c.expr)
         self._offset = {}
@@ -225,8 +376,10 @@ class Problem:
         # constant (variable) part of A, built once like a DPP problem
         rows, cols, vals = [], [], []
         self._row_forms = []
+        self._row_kind = []
         for c in self.constraints:
             for r in c.expr.rows:
+                self._row_kind.append(c.kind)
                 ri = len(self._row_forms)
                 for (v, i), coef in r.vars.items():
                     if coef != 0.0:
@@ -242,7 +395,47 @@ class Problem:
         for v in self._vars:
             self._bounds += [((0.0 if v.nonneg else None), None)] * v.n
 
+    def _solve_qp(self):
+        n = self._ncols
+        P = np.zeros((n, n))
+        q = self._c.copy()
+        const = self.objective.expr.rows[0].constant_value()
+        for coef, qrows, Q in self.objective.quad.quads:      # coef * (M z + c)' Q (M z + c)
+            M = np.zeros((len(qrows), n))
+            c0 = np.zeros(len(qrows))
+            for k, r in enumerate(qrows):
+                for (v, i), cf in r.vars.items():
+                    M[k, self._offset[id(v)] + i] += cf
+                c0[k] = r.constant_value()
+            P += 2.0 * coef * (M.T @ Q @ M)
+            q += 2.0 * coef * (M.T @ (Q @ c0))
+            const += coef * float(c0 @ Q @ c0)
+        Aall = self._A.toarray()
+        rhs = np.array([-r.constant_value() for r in self._row_forms], dtype=np.float64)
+        eq = np.array([k == "eq" for k in self._row_kind], dtype=bool)
+        G, h, A, b = Aall[~eq], rhs[~eq], Aall[eq], rhs[eq]
+        nn = [self._offset[id(v)] + i for v in self._vars if v.nonneg for i in range(v.n)]
+        if nn:
+            E = np.zeros((len(nn), n))
+            E[np.arange(len(nn)), nn] = -1.0
+            G, h = np.vstack([G, E]), np.concatenate([h, np.zeros(len(nn))])
+        z, ok, _it = solve_qp(P, q, G, h, A, b)
+        if ok:
+            self.status = OPTIMAL
+            for v in self._vars:
+                o = self._offset[id(v)]
+                v.value = np.array(z[o:o + v.n], dtype=np.float64)
+            self.value = float(0.5 * z @ P @ z + q @ z + const)
+        else:
+            self.status = "solver_error"
+            self.value = None
+        return self.value
+
     def solve(self, solver=None, **kw):
+        if self.objective.quad is not None and self.objective.quad.quads:
+            return self._solve_qp()
+        if any(k == "eq" for k in self._row_kind):
+            raise NotImplementedError("cvxpy shim: equality constraints are only supported on the QP path")
         b = np.array([-r.constant_value() for r in self._row_forms], dtype=np.float64)
         res = linprog(self._c, A_ub=self._A, b_ub=b, bounds=self._bounds, method="highs")
         if res.status == 0:

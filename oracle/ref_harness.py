@@ -66,6 +66,7 @@ def reference_modules(quiet: bool = True):
             ns.obstacles = importlib.import_module("simulation.obstacles")
             ns.planner = importlib.import_module("simulation.planner")
             ns.dynamics = importlib.import_module("core.dynamics")
+            ns.mpc_filter = importlib.import_module("core.mpc_filter")   # QP solved by the shim's interior-point method
             ns.parameters = importlib.import_module("config.parameters")
             ns.scenarios = importlib.import_module("config.scenarios")
             ns.scratch = scratch

@@ -11,6 +11,10 @@ Cases
   timing_sweep.npz      evaluation/timing_analysis.py:51-104 inputs (N = 10..1500), create() outputs
   explicit_h.npz        core/risk_metrics.py:267,305 entry points with non-unit h, fractional alpha*N, alpha*N<1
   n10k.npz              one N = 10 000, alpha = 0.1, eps = 0.01 halfspace (BASELINE config 4 parameters)
+  mpc_head_on_seed42.npz / mpc_multi_obstacle_seed42.npz
+                        the CONSUMER: MPCSafetyFilter.filter_trajectory (core/mpc_filter.py:40-178, called as in
+                        main.py:101-113) fed with the reference's halfspaces of the same run; the QP is assembled by the
+                        reference's own loops and solved by the shim's interior-point method instead of cvxpy/OSQP
 """
 from __future__ import annotations
 
@@ -59,6 +63,36 @@ def scenario_case(ref, name):
     out["sample_trajectories"] = np.stack([tr[:, : P.HORIZON + 1, :] for tr in traj])  # [n_obs, N, H+1, 2]
     out["x_ref"] = x_ref
     out["params"] = np.array([P.ALPHA, P.DELTA, P.EPSILON, P.ROBOT_RADIUS, P.OBSTACLE_RADIUS, P.HORIZON], dtype=np.float64)
+    return out
+
+
+def mpc_case(ref, name):
+    """main.py:37-113 — halfspaces of the reference's path into the reference's MPC filter, all three metrics."""
+    P = ref.parameters
+    np.random.seed(42)  # main.py:191
+    cfg = ref.scenarios.get_scenario_config(name)
+    data = ref.obstacles.generate_obstacle_scenarios(cfg, P.SIM_TIME, P.DT, P.NUM_SAMPLES)
+    A, B, C = ref.dynamics.create_double_integrator_matrices(P.DT)
+    Q = P.Q_WEIGHT * np.eye(4)
+    R = P.R_WEIGHT * np.eye(2)
+    planner = ref.planner.ReferenceTrajectoryPlanner(A, B, C, Q, R, P.HORIZON, P.DT)
+    x_ref, u_ref, _ = planner.straight_line_trajectory(cfg["ego_start"], cfg["ego_goal"])
+    env = ref.environment.SafetyFilteringEnvironment(P.ROBOT_RADIUS, P.OBSTACLE_RADIUS, P.HORIZON, P.DT,
+                                                     P.ALPHA, P.DELTA, P.EPSILON)
+    hs = env.compute_safe_halfspaces_for_trajectory(data["sample_trajectories"], x_ref)
+    state_bounds = (np.array([-10, -10, -5, -5]), np.array([10, 10, 5, 5]))   # main.py:54-55
+    input_bounds = (np.array([-5, -5]), np.array([5, 5]))
+    x0 = np.zeros(4)
+    x0[:2] = cfg["ego_start"]
+    mpc = ref.mpc_filter.MPCSafetyFilter(A, B, C, Q, R, P.HORIZON, P.DT)
+    out = dict(A=A, B=B, C=C, Q=Q, R=R, horizon=P.HORIZON, dt=P.DT, x0=x0, x_ref=x_ref, u_ref=u_ref,
+               u_min=input_bounds[0], u_max=input_bounds[1], pos_min=state_bounds[0], pos_max=state_bounds[1])
+    for metric in ("mean", "cvar", "dr_cvar"):
+        x_f, u_f, info = mpc.filter_trajectory(x0, x_ref, u_ref, hs[metric], input_bounds, state_bounds[:2])
+        assert info["status"] == "optimal" and not info.get("used_fallback"), (name, metric, info)
+        out[f"x_{metric}"] = x_f
+        out[f"u_{metric}"] = u_f
+        out[f"objective_{metric}"] = info["objective"]
     return out
 
 
@@ -147,6 +181,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, "timing_sweep.npz"), **timing_sweep_case(ref))
         np.savez_compressed(os.path.join(HERE, "explicit_h.npz"), **explicit_h_case(ref))
         np.savez_compressed(os.path.join(HERE, "n10k.npz"), **n10k_case(ref))
+        np.savez_compressed(os.path.join(HERE, "mpc_head_on_seed42.npz"), **mpc_case(ref, "head_on"))
+        np.savez_compressed(os.path.join(HERE, "mpc_multi_obstacle_seed42.npz"), **mpc_case(ref, "multi_obstacle"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes", file=sys.stderr)

@@ -50,6 +50,11 @@ EXPECTED = {
         "SafetyFilteringEnvironment.compute_safe_halfspaces_for_trajectory": "(self, obstacle_sample_trajectories, ego_ref_trajectory)",
         "SafetyFilteringEnvironment.compute_distance_to_collision": "(self, ego_trajectory, obstacle_trajectories)",
     },
+    "core.mpc_filter": {
+        "MPCSafetyFilter.__init__": "(self, A, B, C, Q, R, horizon, dt)",
+        "MPCSafetyFilter.filter_trajectory":
+            "(self, x0, x_ref, u_ref, safe_halfspaces, input_constraints=None, position_constraints=None)",
+    },
     "utils.timing": {
         "Timer.__init__": "(self, name=None)", "Timer.start": "(self)", "Timer.stop": "(self)", "timeit": "(func)",
         "TimingStats.add": "(self, name, time_value)", "TimingStats.get_stats": "(self, name)",
@@ -101,7 +106,8 @@ def test_frozen_table_matches_the_reference_itself():
     _purge()
     with ref_harness.reference_modules() as ref:
         mods = {"core.risk_metrics": ref.risk_metrics, "core.halfspaces": ref.halfspaces, "core.geometry": ref.geometry,
-                "simulation.environment": ref.environment, "utils.timing": importlib.import_module("utils.timing")}
+                "simulation.environment": ref.environment, "utils.timing": importlib.import_module("utils.timing"),
+                "core.mpc_filter": ref.mpc_filter}
         for modname, table in EXPECTED.items():
             for dotted, sig in table.items():
                 assert _sig(mods[modname], dotted) == sig, (modname, dotted)
