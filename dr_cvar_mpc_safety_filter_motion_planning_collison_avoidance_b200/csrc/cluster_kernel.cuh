@@ -18,8 +18,9 @@
 //   exchange2 partial counts / sums and the candidates go to the halfspace's leader CTA (rotating) through DSMEM
 //   finish    leader: exact rank among the candidates (radix narrowing), CVaR, offsets          core/risk_metrics.py:84-338
 // A window miss (3e-5 of Gaussian halfspaces), an overflow or non-finite data put the halfspace on a redo list that the
-// streaming kernel processes right after (exact general select, same arithmetic contract).  Tail indices and the
-// generate mode stay on the streaming kernel.  fp32 inputs only.
+// streaming kernel processes right after (exact general select, same arithmetic contract).  Generate mode (samples ==
+// nullptr): the team draws this CTA's part into the slot (sample_gen.cuh, once per halfspace — the streaming kernel re-draws
+// it in each of its passes) instead of waiting for TMA.  Tail indices stay on the streaming kernel.  fp32 inputs only.
 #pragma once
 
 #include "halfspace_kernel.cuh"
@@ -60,6 +61,7 @@ struct ClShared {
   unsigned hist[kHistBuckets];
   double small[kResolveMax];
   Ctl ctl[2];
+  float2 gfirst;                                  // generate mode: sample 0 of the current halfspace
   Ctl fin_ctl;                                    // leader: copy of ctl[par] for the finisher warp (it may lag behind)
   long long fin_b;
   unsigned long long fdone;                       // finisher -> team: pool / x2 / fin_ctl may be refilled
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
   const size_t slot_bytes = (static_cast<size_t>(part_cap) + 127) & ~static_cast<size_t>(127);
   ClShared* sh = reinterpret_cast<ClShared*>(smem_raw + slot_bytes);
   const int cap = kClPool / C;   // candidates per source CTA in the leader's pool
+  const bool gen = a.gen_mean != nullptr;
 
   if (tid == 0) {
     for (int j = 0; j < kClMaxChunks; ++j) {
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
   };
   // ============================================================================================ producer warp
   if (warp == kClProducerWarp) {
-    if (lane == 0) {
+    if (lane == 0 && !gen) {
       int it = 0;
       for (long long b = q; b < a.B; b += n_clusters, ++it)
         for (int j = 0; j < n_chunks; ++j) {
@@ -193,9 +196,8 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     for (long long b = q; b < a.B; b += n_clusters, ++it) {
       const int par = it & 1;
       Ctl* ctl = &sh->ctl[par];
-      const float* fp = reinterpret_cast<const float*>(a.samples) + b * a.stride_b;
-      const double f0 = static_cast<double>(__ldg(fp)), f1 = static_cast<double>(__ldg(fp + 1));
       bar_sync(kClBarDirector + par, 64);   // warp 0 of the team has seen exchange 1 complete: x1[par] is in
+      const double f0 = ctl->f0, f1 = ctl->f1;   // first sample (shift origin), left by warp 0 before the hand-off
       // octant o = src * O + k lives at x1[par][src][2k + j]
       double w[2];
 #pragma unroll
@@ -315,8 +317,46 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     const int par = it & 1;
     const int leader = it % C;
     Ctl* ctl = &sh->ctl[par];
-    const float* fp = reinterpret_cast<const float*>(a.samples) + b * a.stride_b;
-    const float2 first = make_float2(__ldg(fp), __ldg(fp + 1));
+    float2 first;
+    if (gen) {
+      // generate mode: draw this CTA's part of halfspace b into the slot — nominal position + L z, z from Philox4x32-10 +
+      // Box-Muller, one Philox call per pair of samples (sample_gen.cuh; same stream as the other kernels)
+      const float gmx = static_cast<float>(a.gen_mean[2 * b]), gmy = static_cast<float>(a.gen_mean[2 * b + 1]);
+      const float gl00 = static_cast<float>(a.gen_chol[3 * b]), gl10 = static_cast<float>(a.gen_chol[3 * b + 1]),
+                  gl11 = static_cast<float>(a.gen_chol[3 * b + 2]);
+      const unsigned long long gb = static_cast<unsigned long long>(b + a.gen_index_offset);
+      const uint32_t k0 = static_cast<uint32_t>(a.gen_seed), k1 = static_cast<uint32_t>(a.gen_seed >> 32);
+      auto gen_pair = [&](uint32_t j) {   // samples 2j, 2j+1 of the halfspace
+        const Philox4 r = philox4x32_10(j, static_cast<uint32_t>(gb), static_cast<uint32_t>(gb >> 32), kGenStreamTag, k0, k1);
+        const float2 s0 = gen_sample(r.x, r.y, gmx, gmy, gl00, gl10, gl11);
+        const float2 s1 = gen_sample(r.z, r.w, gmx, gmy, gl00, gl10, gl11);
+        return make_float4(s0.x, s0.y, s1.x, s1.y);
+      };
+      const uint32_t pair_lo = part_lo >> 4, n_pairs = (part_b + 15u) >> 4;
+      float* dump = a.gen_samples_out ? a.gen_samples_out + static_cast<size_t>(b) * N * 2 : nullptr;
+      for (uint32_t j = tid; j < n_pairs; j += kClTeam) {
+        const float4 p = gen_pair(pair_lo + j);
+        *reinterpret_cast<float4*>(smem_raw + 16u * j) = p;
+        if (dump) {
+          const size_t i0 = 2 * static_cast<size_t>(pair_lo + j);
+          dump[2 * i0] = p.x;
+          dump[2 * i0 + 1] = p.y;
+          if (i0 + 1 < static_cast<size_t>(N)) {
+            dump[2 * i0 + 2] = p.z;
+            dump[2 * i0 + 3] = p.w;
+          }
+        }
+      }
+      if (tid == kClTeam - 1) {   // sample 0 for everybody (every CTA needs the shift origin)
+        const float4 p = gen_pair(0);
+        sh->gfirst = make_float2(p.x, p.y);
+      }
+      cl_team_sync();
+      first = sh->gfirst;
+    } else {
+      const float* fp = reinterpret_cast<const float*>(a.samples) + b * a.stride_b;
+      first = make_float2(__ldg(fp), __ldg(fp + 1));
+    }
     double pre0 = 0.0, pre1 = 0.0;   // warp 0: ego (or the explicit normal), fetched early
     if (warp == 0) {
       if (a.h_in != nullptr) {
@@ -331,7 +371,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     const uint32_t fpar = it & 1;
     int have = 0;   // chunks of halfspace b known to have landed
     auto wait_upto = [&](uint32_t byte_off) {
-      if (CL_DBG(2) && it > 0) return;
+      if (gen || (CL_DBG(2) && it > 0)) return;
       const int c = static_cast<int>(byte_off >> 15);
       while (have <= c) {
         mbar_wait_spin(&sh->full[have], fpar);
@@ -438,7 +478,14 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       }
     }
     mbar_wait_cluster(&sh->xbar1[par], (it >> 1) & 1);
-    if (warp == 0) bar_arrive(kClBarDirector + par, 64);   // the director starts the canonical chain
+    if (warp == 0) {
+      if (lane == 0) {
+        ctl->f0 = static_cast<double>(first.x);
+        ctl->f1 = static_cast<double>(first.y);
+      }
+      __syncwarp();
+      bar_arrive(kClBarDirector + par, 64);   // the director starts the canonical chain
+    }
     PH_MARK(3)
 
     // ------------------------------------------------------------------ window placement (warp 0; identical in every CTA)
@@ -512,7 +559,6 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       window_ok = window_ok && isfinite(thr_keep) && isfinite(thr_above) && (khi >= klo) && (thr_above <= thr_keep) &&
                   isfinite(t_lo) && isfinite(t_hi);
       if (lane == 0) {
-        ctl->f0 = f0; ctl->f1 = f1;
         ctl->t_lo = t_lo;
         ctl->t_hi = t_hi;
         ctl->h0f = h0f; ctl->h1f = h1f; ctl->thr_keep = thr_keep; ctl->thr_above = thr_above;

@@ -232,10 +232,13 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   a.redo_count = nullptr;
   a.redo_list = nullptr;
   if (streaming && !(c.flags & (DRCVAR_FLAG_FORCE_STREAMING | DRCVAR_FLAG_NO_CLUSTER | DRCVAR_FLAG_GENERAL_ONLY)) &&
-      sizeof(T) == 4 && !tail && c.gen_mean == nullptr && c.N > kOctantMinN && c.B < 0x7fffffffLL) {
+      sizeof(T) == 4 && !tail && c.N > kOctantMinN && c.B < 0x7fffffffLL) {
     // ---- cluster / DSMEM kernel: one cluster of 2 / 4 / 8 CTAs per halfspace, every sample read from HBM once
-    const bool bulk_ok = contiguous && (reinterpret_cast<uintptr_t>(c.samples) % 16 == 0) &&
-                         ((static_cast<size_t>(c.stride_b) * sizeof(T)) % 16 == 0 || c.B == 1) && (row_bytes % 16 == 0);
+    const bool gen_mode = c.gen_mean != nullptr;   // samples drawn by the kernel: no TMA, no alignment to ask for
+    const bool bulk_ok = gen_mode ? (c.N % 2 == 0)
+                                  : (contiguous && (reinterpret_cast<uintptr_t>(c.samples) % 16 == 0) &&
+                                     ((static_cast<size_t>(c.stride_b) * sizeof(T)) % 16 == 0 || c.B == 1) &&
+                                     (row_bytes % 16 == 0));
     int ctas = 0;
     for (int cc = 2; cc <= kClMaxCtas; cc *= 2)
       if (cluster_smem_bytes(c.N, cc) <= static_cast<size_t>(di->max_smem_optin)) {
@@ -252,7 +255,7 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
       ca.z_half_f = static_cast<float>(0.5 * (zh - zl));
       ca.z_lo_f = ca.z_mid_f - ca.z_half_f;
       ca.z_hi_f = ca.z_mid_f + ca.z_half_f;
-      ca.bulk = 1;
+      ca.bulk = gen_mode ? 0 : 1;
       ca.cl_ctas = ctas;
       const size_t csmem = cluster_smem_bytes(c.N, ctas);
       CUDA_TRY(cudaFuncSetAttribute(cluster_kernel_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(csmem)));
@@ -290,6 +293,9 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
         ra.redo_list = redo + 1;
         ra.bulk = 1;
         auto rk = streaming_kernel<T, false>;
+        if constexpr (sizeof(T) == 4) {
+          if (gen_mode) rk = streaming_kernel<float, false, true>;
+        }
         const long long rgrid = std::min<long long>(c.B, di->sms);
         rk<<<static_cast<unsigned>(rgrid), kStreamThreads, 0, stream>>>(ra);
         CUDA_TRY(cudaGetLastError());

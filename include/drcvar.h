@@ -147,8 +147,10 @@ int drcvar_trajectory_f64(const double* const* traj, int64_t n_obs, int64_t N, i
  *   mean [B,2] double nominal positions (nominal_trajectory[t], obstacles.py:75; rounded to fp32 by the kernel)
  *   chol [B,3] double (l00, l10, l11): lower Cholesky factor of noise_cov (obstacles.py:68-72); zeros = no noise (t = 0)
  *   samples_out [B,N,2] float or NULL: dump of the generated samples (parity tests; costs the HBM write)
- * Other arguments and outputs as drcvar_halfspaces_f32.  N > drcvar_max_samples(4, device) goes through the streaming
- * kernel, which re-draws the samples in each of its passes (same values: the generator is counter-based).
+ * Other arguments and outputs as drcvar_halfspaces_f32.  32768 < N <= ~205000 (even N, no tail indices) runs the cluster
+ * kernel, every CTA drawing its part of the samples into shared memory once; other N > drcvar_max_samples(4, device) go
+ * through the streaming kernel, which re-draws the samples in each of its passes (same values: the generator is
+ * counter-based).
  */
 int drcvar_halfspaces_generated_f32(const double* mean, const double* chol, uint64_t seed, int64_t index_offset,
                                     int64_t B, int64_t N, const double* ego, const double* h_in,

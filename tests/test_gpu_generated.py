@@ -105,3 +105,27 @@ def test_generated_large_n_streaming(eng):
         assert np.array_equal(res.h[b], o.h) and res.var[b] == o.var and np.array_equal(res.tail_idx[b], o.tail_idx)
         assert abs(res.cvar[b] - o.cvar) <= ABS32 and abs(fast.cvar[b] - o.cvar) <= ABS32
     assert np.array_equal(fast.var, res.var)
+
+
+def test_generated_large_n_cluster_kernel(eng):
+    """Generate mode on the cluster / DSMEM kernel (N = 100 000, no tail indices): every CTA draws its part of the samples
+    into its shared memory once; same Philox stream, so the samples, h and T are bit-identical to the streaming kernel's
+    (which re-draws them in each pass) and to the oracle's restatement."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    n, B = 100000, 70
+    mean, ego = scenario(B, 91)
+    cov = np.array([[0.012, 0.003], [0.003, 0.009]])
+    before = eng.launch_count()
+    res = eng.compute_halfspaces_generated(mean, cov, n, seed=11, ego=ego, want_samples=True, **P)
+    assert eng.launch_count() - before == 2          # cluster kernel + its (empty) redo pass
+    ref = eng.compute_halfspaces_generated(mean, cov, n, seed=11, ego=ego, flags=_lib.FLAG_NO_CLUSTER, **P)
+    assert np.array_equal(res.h, ref.h) and np.array_equal(res.h_mean, ref.h_mean) and np.array_equal(res.var, ref.var)
+    assert np.abs(res.g - ref.g).max() <= ABS32
+    want = sg.generate(mean, sg.cholesky2(cov), n, seed=11)
+    assert np.array_equal(res.samples.view(np.uint32), want.view(np.uint32))
+    for b in (0, 33, B - 1):
+        o = cf.halfspace(want[b], ego[b], P["alpha"], P["delta"], P["epsilon"], P["robot_radius"], P["obstacle_radius"])
+        assert np.array_equal(res.h[b], o.h) and res.var[b] == o.var and abs(res.cvar[b] - o.cvar) <= ABS32
+    # shards reproduce their slice of the unsharded stream (index_offset)
+    part = eng.compute_halfspaces_generated(mean[40:], cov, n, seed=11, ego=ego[40:], index_offset=40, **P)
+    assert np.array_equal(part.var, res.var[40:]) and np.array_equal(part.g, res.g[40:])
