@@ -287,8 +287,7 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
         CUDA_TRY(cudaLaunchKernelEx(&cfg, cluster_kernel_f32, ca));
         g_launches.fetch_add(1);
         // the halfspaces it handed back (window miss, overflow, non-finite data): exact general select, streaming kernel
-        KernelArgs ra = a;
-        ra.use_window = 0;
+        KernelArgs ra = a;   // (the streaming kernel's own window plan: after two misses in a row a CTA learns the centre)
         ra.redo_count = redo;
         ra.redo_list = redo + 1;
         ra.bulk = 1;

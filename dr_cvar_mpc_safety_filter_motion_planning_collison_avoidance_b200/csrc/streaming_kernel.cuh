@@ -38,6 +38,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
   __shared__ double oct_tot[2 * kOctants];
   __shared__ Ctl ctl_s;
   Ctl* ctl = &ctl_s;
+  // Window centre learned from this CTA's earlier halfspaces (as in the resident kernel): after two CONSECUTIVE window
+  // misses — samples that are evidently not Gaussian — the exact threshold of the general select, in sigma units around
+  // the loss mean, becomes the centre of a 2.5 x wider window and is tracked from then on.  Isolated misses (3e-5 of
+  // Gaussian halfspaces) change nothing.  Speed only: T, the tail set and the status of the others never depend on it.
+  if (threadIdx.x == 0) {
+    ctl_s.z_learned = 0;
+    ctl_s.z_missrun = 0;
+    ctl_s.z_est = 0.f;
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int half = tid >> 8, lt = tid & (kSweepThreads - 1);   // half 0: even canonical rows, half 1: odd rows
   const int N = a.N;
@@ -383,8 +392,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
       const double var_l = h0 * h0 * cxx + 2.0 * h0 * h1 * cxy + h1 * h1 * cyy;
       const double sigma = sqrt(var_l);
       const double mu_l = -(h0 * m0 + h1 * m1);
-      const double t_lo = __dadd_rn(mu_l + a.z_lo * sigma, 0.0);   // +0.0: never -0.0 (canonical losses are +0)
-      const double t_hi = __dadd_rn(mu_l + a.z_hi * sigma, 0.0);
+      double z_lo = a.z_lo, z_hi = a.z_hi;
+      if (ctl->z_learned) {   // written two barriers ago by thread 0: CTA-uniform
+        z_lo = static_cast<double>(ctl->z_est) - static_cast<double>(a.z_half_adapt_f);
+        z_hi = static_cast<double>(ctl->z_est) + static_cast<double>(a.z_half_adapt_f);
+      }
+      const double t_lo = __dadd_rn(mu_l + z_lo * sigma, 0.0);   // +0.0: never -0.0 (canonical losses are +0)
+      const double t_hi = __dadd_rn(mu_l + z_hi * sigma, 0.0);
       const int window_ok = a.use_window && !nonfinite && n_sub >= 256.0 && var_l > 0.0 && isfinite(t_lo) &&
                             isfinite(t_hi) && t_lo <= t_hi;
       if (lane == 0) {
@@ -394,6 +408,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
         ctl->t_lo = t_lo;
         ctl->t_hi = t_hi;
         ctl->window_ok = window_ok;
+        ctl->pl = Ctl::Place{static_cast<float>(mu_l), static_cast<float>(sigma), 0.0};
         write_mean_outputs(a, b, m0, m1);
       }
     }
@@ -582,7 +597,19 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
         s_tot += red[w];
       }
     }
-    if (tid == 0) write_risk_outputs(a, b, ctl, nonfinite, s_tot, c_tot, T_thr, status);
+    if (tid == 0) {
+      write_risk_outputs(a, b, ctl, nonfinite, s_tot, c_tot, T_thr, status);
+      if (ctl->window_ok && !nonfinite) {   // where the threshold really sits, in sigma units around the loss mean
+        const float zT = (static_cast<float>(T_thr) - ctl->pl.pm) / ctl->pl.sigma;
+        if (fast) {
+          ctl->z_missrun = 0;
+          if (ctl->z_learned && isfinite(zT)) ctl->z_est = 0.5f * (ctl->z_est + zT);
+        } else if (isfinite(zT)) {
+          ctl->z_est = zT;
+          if (++ctl->z_missrun >= 2) ctl->z_learned = 1;
+        }
+      }
+    }
 
     if (kTail && a.tail_idx_out != nullptr) {
       int* out = a.tail_idx_out + b * static_cast<long long>(a.kc);
