@@ -44,7 +44,7 @@ constexpr int kClMaxCtas = 8;
 constexpr int kClMaxChunks = 8;                   // 32 KB chunks of one CTA's part (<= 227 KB)
 constexpr int kClWarpList = 40;                   // masked samples (raw copies) per sweep warp
 constexpr int kClPool = 1536;                     // candidate losses gathered at the leader (all CTAs together)
-constexpr int kClX1 = 12;                         // doubles per source CTA in exchange 1
+constexpr int kClX1 = 14;                         // doubles per source CTA in exchange 1
 constexpr uint32_t kClLaneRow = 8192;             // one 16-byte load per team thread
 
 struct ClShared {
@@ -57,13 +57,13 @@ struct ClShared {
   double octtot[kOctants * 2];
   alignas(16) double wsum[kClTeamWarps * 4];
   alignas(16) float mom[kClTeamWarps * 4];
+  double dmom[kClTeamWarps * 6];                  // fp64 kernel: per-warp qxx, qyy, qxy, qdx, qdy, n_sub
   int wcnt[kClTeamWarps * 2];
   unsigned hist[kHistBuckets];
   double small[kResolveMax];
   Ctl ctl[2];
   float2 gfirst;                                  // generate mode: sample 0 of the current halfspace
   Ctl fin_ctl;                                    // leader: copy of ctl[par] for the finisher warp (it may lag behind)
-  long long fin_b;
   unsigned long long fdone;                       // finisher -> team: pool / x2 / fin_ctl may be refilled
   unsigned long long full[kClMaxChunks];
   unsigned long long free_[kClMaxChunks];
@@ -72,8 +72,8 @@ struct ClShared {
   unsigned long long hdone[2];
 };
 
-__host__ __device__ inline size_t cluster_smem_bytes(long long n, int ctas) {
-  const size_t part = static_cast<size_t>(kOctants / ctas) * static_cast<size_t>(octant_bytes(n, 4));
+__host__ __device__ inline size_t cluster_smem_bytes(long long n, int ctas, size_t elem_bytes = 4) {
+  const size_t part = static_cast<size_t>(kOctants / ctas) * static_cast<size_t>(octant_bytes(n, elem_bytes));
   return ((part + 127) & ~static_cast<size_t>(127)) + sizeof(ClShared) + 128;
 }
 

@@ -17,6 +17,7 @@
 #include "halfspace_kernel.cuh"
 #include "streaming_kernel.cuh"
 #include "cluster_kernel.cuh"
+#include "cluster_kernel_f64.cuh"
 
 namespace {
 
@@ -232,7 +233,10 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   a.redo_count = nullptr;
   a.redo_list = nullptr;
   if (streaming && !(c.flags & (DRCVAR_FLAG_FORCE_STREAMING | DRCVAR_FLAG_NO_CLUSTER | DRCVAR_FLAG_GENERAL_ONLY)) &&
-      sizeof(T) == 4 && !tail && c.N > kOctantMinN && c.B < 0x7fffffffLL) {
+      !tail && c.N > kOctantMinN && c.B < 0x7fffffffLL &&
+      (sizeof(T) == 4 || (c.gen_mean == nullptr && (c.flags & DRCVAR_FLAG_FORCE_CLUSTER)))) {
+    // (fp64 samples: the two-pass streaming kernel is faster — 1.96 vs 1.73 M halfspaces/s at N = 100 000: 1.6 MB per
+    //  halfspace leaves no room for a second halfspace in flight per cluster — so the fp64 cluster kernel is opt-in)
     // ---- cluster / DSMEM kernel: one cluster of 2 / 4 / 8 CTAs per halfspace, every sample read from HBM once
     const bool gen_mode = c.gen_mean != nullptr;   // samples drawn by the kernel: no TMA, no alignment to ask for
     const bool bulk_ok = gen_mode ? (c.N % 2 == 0)
@@ -241,12 +245,14 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
                                      (row_bytes % 16 == 0));
     int ctas = 0;
     for (int cc = 2; cc <= kClMaxCtas; cc *= 2)
-      if (cluster_smem_bytes(c.N, cc) <= static_cast<size_t>(di->max_smem_optin)) {
+      if (cluster_smem_bytes(c.N, cc, sizeof(T)) <= static_cast<size_t>(di->max_smem_optin)) {
         ctas = cc;
         break;
       }
     double zl = 0, zh = 0;
-    if (bulk_ok && ctas && plan_window(c.N, kc, c.N, 0.6 * kClPool, &zl, &zh)) {
+    void (*ck)(const KernelArgs) = sizeof(T) == 4 ? cluster_kernel_f32 : cluster_kernel_f64;
+    const long long cl_n_sigma = sizeof(T) == 4 ? c.N : std::max<long long>(1, c.N / 4);   // fp64: moments on every 4th row
+    if (bulk_ok && ctas && plan_window(c.N, kc, cl_n_sigma, 0.6 * kClPool, &zl, &zh)) {
       KernelArgs ca = a;
       ca.use_window = 1;
       ca.z_lo = zl;
@@ -257,8 +263,8 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
       ca.z_hi_f = ca.z_mid_f + ca.z_half_f;
       ca.bulk = gen_mode ? 0 : 1;
       ca.cl_ctas = ctas;
-      const size_t csmem = cluster_smem_bytes(c.N, ctas);
-      CUDA_TRY(cudaFuncSetAttribute(cluster_kernel_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(csmem)));
+      const size_t csmem = cluster_smem_bytes(c.N, ctas, sizeof(T));
+      CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(csmem)));
       int* redo = nullptr;   // [0] = count, [1..] = halfspace indices; stream-ordered allocation
       CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&redo), sizeof(int) * (static_cast<size_t>(c.B) + 1), stream));
       CUDA_TRY(cudaMemsetAsync(redo, 0, sizeof(int), stream));
@@ -277,14 +283,14 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       int max_clusters = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, cluster_kernel_f32, &cfg));
+      CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, ck, &cfg));
 #ifdef DRCVAR_PROFILE_PHASES
       fprintf(stderr, "[drcvar] cluster kernel: N=%lld ctas=%d smem=%zu max_active_clusters=%d\n", c.N, ctas, csmem, max_clusters);
 #endif
       if (max_clusters >= 1) {
         const long long n_cl = std::min<long long>(c.B, max_clusters);
         cfg.gridDim = dim3(static_cast<unsigned>(n_cl * ctas), 1, 1);
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, cluster_kernel_f32, ca));
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, ck, ca));
         g_launches.fetch_add(1);
         // the halfspaces it handed back (window miss, overflow, non-finite data): exact general select, streaming kernel
         KernelArgs ra = a;   // (the streaming kernel's own window plan: after two misses in a row a CTA learns the centre)

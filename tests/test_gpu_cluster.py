@@ -140,3 +140,62 @@ def test_device_pointers_and_single_halfspace(eng):
     assert np.array_equal(dev.g.cpu().numpy(), host.g) and np.array_equal(dev.var.cpu().numpy(), host.var)
     one = eng.compute_halfspaces(s[3], ego[3], **P)
     assert np.array_equal(one.g[0], host.g[3])
+
+
+# ---------------------------------------------------------------------------------------------- fp64 samples
+def gaussian_batch64(rng, B, n, spread=4.0):
+    mu = rng.uniform(-spread, spread, size=(B, 1, 2))
+    return mu + 0.1 * rng.standard_normal((B, n, 2)), rng.uniform(-1, 1, size=(B, 2))
+
+
+def check_against_oracle64(res, s, ego, p, which, h_in=None):
+    for b in which:
+        o = cf.halfspace(s[b], ego[b], p["alpha"], p["delta"], p["epsilon"], p["robot_radius"], p["obstacle_radius"],
+                         None if h_in is None else h_in[b])
+        assert np.array_equal(res.h[b], o.h) and np.array_equal(res.h_mean[b], o.h_mean), b
+        assert res.var[b] == o.var, (b, res.var[b], o.var)
+        ref = np.array([o.g_mean, o.g_cvar, o.g_dr])
+        assert np.all(np.abs(res.g[b] - ref) <= 1e-9 * np.maximum(1.0, np.abs(ref))), (b, res.g[b], ref)
+        assert abs(res.cvar[b] - o.cvar) <= 1e-9 * max(1.0, abs(o.cvar))
+
+
+@pytest.mark.parametrize("n", [32770, 50001, 100000, 100352])
+def test_fp64_cluster_kernel(eng, n):
+    """fp64 samples (the reference's dtype) on the opt-in fp64 cluster kernel (DRCVAR_FLAG_FORCE_CLUSTER): N = 100 000 is
+    1.6 MB per halfspace = 8 CTAs x 200 KB; bit-exact h / T against the oracle and the streaming kernel (the default for
+    fp64: it is faster there), offsets within 1e-9 relative."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    rng = np.random.RandomState(n % 997)
+    B = 45
+    s, ego = gaussian_batch64(rng, B, n)
+    per = max(1, (64 << 20) // (n * 16))
+    res, nl = launches(eng, lambda: eng.compute_halfspaces(s, ego, flags=_lib.FLAG_FORCE_CLUSTER, **P))
+    assert nl == 2 * -(-B // per)                 # per host chunk: cluster kernel + its redo pass
+    ref, nl2 = launches(eng, lambda: eng.compute_halfspaces(s, ego, **P))
+    assert nl2 == -(-B // per)                    # default for fp64: the (faster) two-pass streaming kernel
+    assert np.array_equal(res.h, ref.h) and np.array_equal(res.h_mean, ref.h_mean) and np.array_equal(res.var, ref.var)
+    assert np.all(np.abs(res.g - ref.g) <= 1e-9 * np.maximum(1.0, np.abs(ref.g)))
+    assert (res.status & _lib.STATUS_GENERAL).sum() <= 1
+    check_against_oracle64(res, s, ego, P, (0, 21, B - 1))
+    again = eng.compute_halfspaces(s, ego, flags=_lib.FLAG_FORCE_CLUSTER, **P)
+    assert np.array_equal(again.g, res.g) and np.array_equal(again.cvar, res.cvar)
+
+
+def test_fp64_cluster_redo_and_explicit_normals(eng):
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    rng = np.random.RandomState(19)
+    B, n = 10, 60000
+    mu = rng.uniform(-4, 4, size=(B, 1, 2))
+    s = mu + rng.uniform(-0.3, 0.3, size=(B, n, 2))                 # uniform noise: the Gaussian window misses
+    s[7] = mu[7] + 0.1 * rng.standard_normal((n, 2))
+    s[3, 12345, 0] = np.inf
+    ego = rng.uniform(-1, 1, size=(B, 2))
+    res = eng.compute_halfspaces(s, ego, flags=_lib.FLAG_FORCE_CLUSTER, **P)
+    assert res.status[3] & _lib.STATUS_NONFINITE and res.g[3, 1] == 100.0
+    assert not (res.status[7] & _lib.STATUS_GENERAL) and (res.status[[0, 1, 2]] & _lib.STATUS_GENERAL).all()
+    check_against_oracle64(res, s, ego, P, (0, 7, 9))
+    th = rng.uniform(0, 2 * np.pi, size=B)
+    h = np.stack([np.cos(th), np.sin(th)], axis=1) * rng.uniform(0.5, 2.0, size=(B, 1))
+    s2, _ = gaussian_batch64(rng, B, n)
+    res2 = eng.compute_halfspaces(s2, None, h=h, flags=_lib.FLAG_FORCE_CLUSTER, **P)
+    check_against_oracle64(res2, s2, np.zeros((B, 2)), P, (0, 4, 9), h_in=h)
