@@ -43,7 +43,7 @@ constexpr int kClBarDirector = 2;                 // named barriers 2, 3 (one pe
 constexpr int kClMaxCtas = 8;
 constexpr int kClMaxChunks = 8;                   // 32 KB chunks of one CTA's part (<= 227 KB)
 constexpr int kClWarpList = 40;                   // masked samples (raw copies) per sweep warp
-constexpr int kClPool = 1536;                     // candidate losses gathered at the leader (all CTAs together)
+constexpr int kClPool = 1408;                     // candidate losses gathered at the leader (all CTAs together)
 constexpr int kClX1 = 14;                         // doubles per source CTA in exchange 1
 constexpr uint32_t kClLaneRow = 8192;             // one 16-byte load per team thread
 
@@ -132,6 +132,7 @@ __device__ __forceinline__ double pair_tree8(const double* t_in, int stride) {
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
+template <bool kGen>
 __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const KernelArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
   const size_t slot_bytes = (static_cast<size_t>(part_cap) + 127) & ~static_cast<size_t>(127);
   ClShared* sh = reinterpret_cast<ClShared*>(smem_raw + slot_bytes);
   const int cap = kClPool / C;   // candidates per source CTA in the leader's pool
-  const bool gen = a.gen_mean != nullptr;
+  constexpr bool gen = kGen;   // generate mode is a separate instantiation: the stored-sample kernel's code is untouched
 
   if (tid == 0) {
     for (int j = 0; j < kClMaxChunks; ++j) {
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     const int leader = it % C;
     Ctl* ctl = &sh->ctl[par];
     float2 first;
-    if (gen) {
+    if constexpr (gen) {
       // generate mode: draw this CTA's part of halfspace b into the slot — nominal position + L z, z from Philox4x32-10 +
       // Box-Muller, one Philox call per pair of samples (sample_gen.cuh; same stream as the other kernels)
       const float gmx = static_cast<float>(a.gen_mean[2 * b]), gmy = static_cast<float>(a.gen_mean[2 * b + 1]);

@@ -104,6 +104,13 @@ bool plan_window(long long n, long long kc, long long n_sigma, double cand_capac
   return true;
 }
 
+// CTAs per halfspace of the cluster kernels: the smallest cluster whose per-CTA part + scratch fits one SM (0: none does)
+int cluster_ctas_for(long long n, size_t elem_bytes, size_t smem_optin) {
+  for (int cc = 2; cc <= drcvar::kClMaxCtas; cc *= 2)
+    if (drcvar::cluster_smem_bytes(n, cc, elem_bytes) <= smem_optin) return cc;
+  return 0;
+}
+
 #ifdef DRCVAR_PROFILE_PHASES
 long long* g_phase_cycles = nullptr;  // device buffer [4096][2][12], set by drcvar_debug_phase_buffer()
 #endif
@@ -243,16 +250,11 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
                                   : (contiguous && (reinterpret_cast<uintptr_t>(c.samples) % 16 == 0) &&
                                      ((static_cast<size_t>(c.stride_b) * sizeof(T)) % 16 == 0 || c.B == 1) &&
                                      (row_bytes % 16 == 0));
-    int ctas = 0;
-    for (int cc = 2; cc <= kClMaxCtas; cc *= 2)
-      if (cluster_smem_bytes(c.N, cc, sizeof(T)) <= static_cast<size_t>(di->max_smem_optin)) {
-        ctas = cc;
-        break;
-      }
+    const int ctas = cluster_ctas_for(c.N, sizeof(T), static_cast<size_t>(di->max_smem_optin));
     double zl = 0, zh = 0;
-    void (*ck)(const KernelArgs) = sizeof(T) == 4 ? cluster_kernel_f32 : cluster_kernel_f64;
+    void (*ck)(const KernelArgs) = sizeof(T) == 4 ? (gen_mode ? cluster_kernel_f32<true> : cluster_kernel_f32<false>) : cluster_kernel_f64;
     const long long cl_n_sigma = sizeof(T) == 4 ? c.N : std::max<long long>(1, c.N / 4);   // fp64: moments on every 4th row
-    if (bulk_ok && ctas && plan_window(c.N, kc, cl_n_sigma, 0.6 * kClPool, &zl, &zh)) {
+    if (bulk_ok && ctas && plan_window(c.N, kc, cl_n_sigma, 0.7 * kClPool, &zl, &zh)) {
       KernelArgs ca = a;
       ca.use_window = 1;
       ca.z_lo = zl;
@@ -791,6 +793,11 @@ void* drcvar_host_alloc(size_t bytes) {
 }
 void drcvar_host_free(void* p) {
   if (p) cudaFreeHost(p);
+}
+
+int drcvar_cluster_ctas(int64_t n_samples, int elem_bytes, int64_t smem_optin_bytes) {
+  if (n_samples <= drcvar::kOctantMinN || (elem_bytes != 4 && elem_bytes != 8) || smem_optin_bytes <= 0) return 0;
+  return cluster_ctas_for(n_samples, static_cast<size_t>(elem_bytes), static_cast<size_t>(smem_optin_bytes));
 }
 
 int64_t drcvar_launch_count(void) { return g_launches.load(); }

@@ -166,6 +166,11 @@ int drcvar_halfspaces_generated_f32(const double* mean, const double* chol, uint
 void* drcvar_host_alloc(size_t bytes);
 void drcvar_host_free(void* p);
 
+/* CTAs per halfspace (2, 4 or 8; 0 = not served) the cluster / DSMEM kernel uses for N samples of `elem_bytes` each when
+ * an SM offers `smem_optin_bytes` of opt-in shared memory (232448 on B200).  N = 100 000: 4 (fp32), 8 (fp64).  Diagnostic;
+ * also what the tests pin so that a grown scratch area cannot silently push config 5 onto clusters of 8. */
+int drcvar_cluster_ctas(int64_t n_samples, int elem_bytes, int64_t smem_optin_bytes);
+
 /* Telemetry of this process: kernels launched so far; timings (ms) and bytes of the LAST DRCVAR_HOST call. */
 int64_t drcvar_launch_count(void);
 int drcvar_last_host_call_stats(double* stage_ms, double* kernel_ms, int64_t* h2d_bytes, int64_t* d2h_bytes);

@@ -48,6 +48,20 @@ def test_host_logic_without_gpu(lib):
     assert L.drcvar_tail_count(0.5, 0, None) == lib.ERR_INVALID
 
 
+def test_cluster_sizes_are_pinned(lib):
+    """BASELINE config 5 (N = 100 000 fp32) must run on clusters of 4 CTAs (33 clusters = 132 SMs on B200); a grown scratch
+    area once pushed it silently onto clusters of 8 (15 clusters, 40 % slower).  232448 = B200's opt-in shared memory per SM."""
+    L = lib.load()
+    smem = 232448
+    assert L.drcvar_cluster_ctas(100000, 4, smem) == 4
+    assert L.drcvar_cluster_ctas(100000, 8, smem) == 8
+    assert L.drcvar_cluster_ctas(40000, 4, smem) == 2
+    assert L.drcvar_cluster_ctas(200000, 4, smem) == 8
+    assert L.drcvar_cluster_ctas(32768, 4, smem) == 0          # single-chain contract: resident / streaming kernels
+    assert L.drcvar_cluster_ctas(400000, 4, smem) == 0         # beyond 8 CTAs: streaming kernel
+    assert L.drcvar_cluster_ctas(100000, 2, smem) == 0
+
+
 def test_tail_count_matches_oracle(lib):
     from oracle import closed_form as cf
     import numpy as np
