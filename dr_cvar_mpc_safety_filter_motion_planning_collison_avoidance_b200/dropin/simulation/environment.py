@@ -67,6 +67,33 @@ class SafetyFilteringEnvironment:
             return out
         return self._wrap(h, hm, g, n_steps, len(trajs), time.time() - t0)
 
+    def compute_safe_halfspaces_for_runs(self, runs_sample_trajectories, ego_ref_trajectory):
+        """
+        EXTENSION (not in the reference): compute_safe_halfspaces_for_trajectory for MANY Monte-Carlo runs
+        that share one reference trajectory, in ONE launch — run r contributes its obstacles as extra columns of the
+        (step, obstacle) grid.  `runs_sample_trajectories[r]` is what the per-run method takes (a list of [N, T+1, 2]
+        arrays); returns one {'mean'|'cvar'|'dr_cvar': [t][obstacle]} dict per run, identical to calling the per-run
+        method run by run.  This is where the scenario-batch axis of BASELINE config 4 comes from (NUM_MC_RUNS = 300,
+        config/parameters.py:33).
+        """
+        runs = [[np.asarray(tr, dtype=np.float64) for tr in run] for run in runs_sample_trajectories]
+        n_steps = min(len(ego_ref_trajectory), self.HORIZON)
+        flat = [tr for run in runs for tr in run]
+        uniform = len(flat) > 0 and all(tr.shape == flat[0].shape for tr in flat) and flat[0].shape[1] >= n_steps
+        if n_steps == 0 or not uniform:
+            return [self.compute_safe_halfspaces_for_trajectory(run, ego_ref_trajectory) for run in runs]
+        ego_steps = np.stack([self.C @ np.asarray(ego_ref_trajectory[t]) for t in range(n_steps)])
+        t0 = time.time()
+        h, hm, g, _ = _engine.compute_trajectory(flat, ego_steps, alpha=self.ALPHA, delta=self.DELTA, epsilon=self.EPSILON,
+                                                 robot_radius=self.ROBOT_RADIUS, obstacle_radius=self.OBSTACLE_RADIUS)
+        elapsed = (time.time() - t0) / max(len(runs), 1)
+        out, col = [], 0
+        for run in runs:
+            k = len(run)
+            out.append(self._wrap(h[:, col:col + k], hm[:, col:col + k], g[:, col:col + k], n_steps, k, elapsed))
+            col += k
+        return out
+
     def _wrap(self, h, hm, g, n_steps, n_obs, elapsed):
         out = {'mean': [[] for _ in range(n_steps)], 'cvar': [[] for _ in range(n_steps)],
                'dr_cvar': [[] for _ in range(n_steps)]}
