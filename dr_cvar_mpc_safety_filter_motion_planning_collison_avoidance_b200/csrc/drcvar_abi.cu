@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "halfspace_kernel.cuh"
@@ -761,23 +762,49 @@ int drcvar_trajectory_f64(const double* const* traj, int64_t n_obs, int64_t N, i
                           int32_t* status_out) {
   if (!traj || n_obs < 1 || N < 1 || T1 < 1 || n_steps < 0 || n_steps > T1 || !ego_steps || !h_out || !g_out)
     return fail(DRCVAR_ERR_INVALID, "bad trajectory arguments");
-  // pack halfspace (t, i) = traj[i][:, t, :] into one [n_steps*n_obs, N, 2] batch, ego repeated per obstacle
+  // pack halfspace (t, i) = traj[i][:, t, :] into one [n_steps*n_obs, N, 2] batch, ego repeated per obstacle.
+  // The batch lives in a pinned buffer that is kept between calls (no page faults, full-speed H2D from the host path) and
+  // is filled obstacle-major by a few threads: every source array is read once, front to back (with many obstacles — all
+  // the runs of a Monte-Carlo batch — a step-major gather would stream the whole input through the cache once per step).
   const int64_t B = n_steps * n_obs;
   if (B == 0) return DRCVAR_OK;
-  std::vector<double> pack(static_cast<size_t>(B) * N * 2), ego(static_cast<size_t>(B) * 2);
+  for (int64_t i = 0; i < n_obs; ++i)
+    if (!traj[i]) return fail(DRCVAR_ERR_INVALID, "null trajectory pointer");
+  static std::mutex pack_mu;
+  static void* pack_buf = nullptr;
+  static size_t pack_cap = 0;
+  std::lock_guard<std::mutex> lk(pack_mu);
+  const size_t pack_bytes = static_cast<size_t>(B) * N * 2 * sizeof(double);
+  int rc = grow_pinned(&pack_buf, &pack_cap, pack_bytes);
+  if (rc) return rc;
+  double* pack = static_cast<double*>(pack_buf);
+  std::vector<double> ego(static_cast<size_t>(B) * 2);
+  auto pack_range = [&](int64_t i_lo, int64_t i_hi) {
+    for (int64_t i = i_lo; i < i_hi; ++i)
+      for (int64_t s = 0; s < N; ++s) {
+        const double* src = traj[i] + s * T1 * 2;
+        for (int64_t t = 0; t < n_steps; ++t) {
+          double* dst = pack + (static_cast<size_t>(t * n_obs + i) * N + s) * 2;
+          dst[0] = src[2 * t];
+          dst[1] = src[2 * t + 1];
+        }
+      }
+  };
+  const int64_t n_thr = std::max<int64_t>(1, std::min<int64_t>({8, static_cast<int64_t>(std::thread::hardware_concurrency()),
+                                                                n_obs, static_cast<int64_t>(pack_bytes >> 22)}));
+  if (n_thr <= 1) {
+    pack_range(0, n_obs);
+  } else {
+    std::vector<std::thread> pool;
+    for (int64_t k = 0; k < n_thr; ++k) pool.emplace_back(pack_range, k * n_obs / n_thr, (k + 1) * n_obs / n_thr);
+    for (auto& th : pool) th.join();
+  }
   for (int64_t t = 0; t < n_steps; ++t)
     for (int64_t i = 0; i < n_obs; ++i) {
-      if (!traj[i]) return fail(DRCVAR_ERR_INVALID, "null trajectory pointer");
-      double* dst = pack.data() + static_cast<size_t>(t * n_obs + i) * N * 2;
-      const double* src = traj[i] + t * 2;
-      for (int64_t s = 0; s < N; ++s) {
-        dst[2 * s] = src[s * T1 * 2];
-        dst[2 * s + 1] = src[s * T1 * 2 + 1];
-      }
       ego[static_cast<size_t>(t * n_obs + i) * 2] = ego_steps[2 * t];
       ego[static_cast<size_t>(t * n_obs + i) * 2 + 1] = ego_steps[2 * t + 1];
     }
-  return drcvar_halfspaces_f64(pack.data(), B, N, N * 2, 2, 1, ego.data(), nullptr, alpha, delta, epsilon, r_robot,
+  return drcvar_halfspaces_f64(pack, B, N, N * 2, 2, 1, ego.data(), nullptr, alpha, delta, epsilon, r_robot,
                                r_obs, flags, h_out, h_mean_out, g_out, nullptr, nullptr, nullptr, status_out, nullptr,
                                DRCVAR_HOST, nullptr);
 }
