@@ -9,7 +9,9 @@
 //           candidate lists in shared memory                (read 2: HBM or L2)
 //   select  exact rank among the candidates (range-narrowing radix select in shared memory), CVaR, offsets
 // If the window misses (or GENERAL_ONLY): the exact multi-pass radix select over all samples (2-4 more reads).
-// The single-read cluster / DSMEM kernel for large N is the planned replacement.
+// fp32 samples with 32768 < N <~ 205000 normally run the single-read cluster / DSMEM kernel (cluster_kernel.cuh); this kernel
+// serves everything else — fp64, tail indices, strided or unaligned views, 24000 < N <= 32768 — and the halfspaces the
+// cluster kernel hands back (work list `redo_list`).  After two consecutive window misses a CTA learns the window centre.
 #pragma once
 
 #include "halfspace_kernel.cuh"
