@@ -63,6 +63,8 @@ struct ClShared {
   double small[kResolveMax];
   Ctl ctl[2];
   float2 gfirst;                                  // generate mode: sample 0 of the current halfspace
+  unsigned long long zpub;                        // learned window state of this CTA's finisher: {(tag << 1 | learned), z_est bits}
+  int fin_missrun;                                // finisher: consecutive window misses it has seen
   Ctl fin_ctl;                                    // leader: copy of ctl[par] for the finisher warp (it may lag behind)
   unsigned long long fdone;                       // finisher -> team: pool / x2 / fin_ctl may be refilled
   unsigned long long full[kClMaxChunks];
@@ -164,6 +166,8 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     mbar_init(&sh->hdone[1], 1);
     mbar_init(&sh->fdone, 1);
     mbar_fence_init();
+    sh->zpub = 0ull;
+    sh->fin_missrun = 0;
   }
   if (tid < 2 * kClTeamWarps) sh->wcnt[tid] = 0;
   __syncthreads();
@@ -297,8 +301,30 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
           const double s_lin = -(fc->h0 * (n_above * fc->f0 + sdx) + fc->h1 * (n_above * fc->f1 + sdy));
           write_risk_outputs(a, b, fc, false, s_lin + s4, cnt_hi + c4, T_thr, fc->degenerate ? kStatusDegenerate : 0);
         }
+        if (lane == 0) {   // where the threshold sits, in sigma units around the loss mean (as in the resident kernel)
+          const float zT = (fc->pl.pm + static_cast<float>(T_thr + fc->pl.c_shift)) / fc->pl.sigma;
+          sh->fin_missrun = 0;
+          const float z_new = fc->z_learned ? 0.5f * (fc->z_est + zT) : zT;
+          if (isfinite(z_new) && fabsf(z_new) < 8.f)
+            sh->zpub = (static_cast<unsigned long long>((static_cast<unsigned>(it + 1) << 1) | (fc->z_learned ? 1u : 0u)) << 32) |
+                       __float_as_uint(z_new);
+        }
       } else if (lane == 0) {
         a.redo_list[atomicAdd(a.redo_count, 1)] = static_cast<int>(b);
+        // a placed window that missed: after two in a row (or already in learned mode) move a learned centre past the
+        // window, towards the side the threshold is on
+        bool clean = fc->window_ok != 0 && fc->nonfinite == 0;
+        for (int s = 0; s < C && clean; ++s) clean = sh->x2[s][3] >= 0.0;
+        if (clean) {
+          const int run = ++sh->fin_missrun;
+          if (run >= 2 || fc->z_learned) {
+            const float z_used = fc->z_learned ? fc->z_est : a.z_mid_f;
+            const float half_used = fc->z_learned ? a.z_half_adapt_f : a.z_half_f;
+            const float z_new = z_used + (a.kc <= cnt_hi ? 2.0f : -2.0f) * half_used;
+            if (isfinite(z_new) && fabsf(z_new) < 8.f)
+              sh->zpub = (static_cast<unsigned long long>((static_cast<unsigned>(it + 1) << 1) | 1u) << 32) | __float_as_uint(z_new);
+          }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->fdone);
@@ -464,18 +490,22 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         qyy += shfl_xor_d(qyy, m);
         b2 = fmaxf(b2, __shfl_xor_sync(kFull, b2, m));
       }
+      // learned-window state of our finisher: ONE read, the same bits to every destination
+      unsigned long long zp = lane == 0 ? *reinterpret_cast<volatile unsigned long long*>(&sh->zpub) : 0ull;
+      zp = __shfl_sync(kFull, zp, 0);
       if (lane < C) {   // lane d serves destination CTA d
         // leader of this halfspace: our finisher must be done with the pool / x2 / fin_ctl of the halfspace we led last,
         // before any CTA can get past exchange 1 and send the next candidates
         if (static_cast<int>(rank) == leader && n_lead > 0) mbar_wait(&sh->fdone, (n_lead - 1) & 1u);
         const uint32_t dst = mapa_u32(smem_u32(&sh->x1[par][rank][0]), static_cast<uint32_t>(lane));
         const uint32_t bar = mapa_u32(smem_u32(&sh->xbar1[par]), static_cast<uint32_t>(lane));
-        mbar_arrive_expect_tx_remote(bar, 8u * (2u * O + 4u));
+        mbar_arrive_expect_tx_remote(bar, 8u * (2u * O + 5u));
         for (int i = 0; i < 2 * O; ++i) st_async_f64(dst + 8u * i, sh->octtot[i], bar);
         st_async_f64(dst + 64, qxx, bar);
         st_async_f64(dst + 72, qyy, bar);
         st_async_f64(dst + 80, qxy, bar);
         st_async_f64(dst + 88, static_cast<double>(b2), bar);
+        st_async_f64(dst + 96, __longlong_as_double(static_cast<long long>(zp)), bar);
       }
     }
     mbar_wait_cluster(&sh->xbar1[par], (it >> 1) & 1);
@@ -544,7 +574,23 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       int window_ok = a.use_window && usable && (var_l > 0.f) && isfinite(sigma);
       // thresholds in shifted coordinates, p = h_a.(xi - first):  a_lo <-> t_lo,  a_hi <-> t_hi  (a_hi <= a_lo)
       const float pm = fmaf(h1f, mr1f, h0f * mr0f);
-      const float a_lo = pm - a.z_lo_f * sigma, a_hi = pm - a.z_hi_f * sigma;
+      // Window bounds in z units: the Gaussian plan of the host, or — once a finisher of this cluster has seen two window
+      // misses in a row (samples that are evidently not Gaussian) — the LEARNED centre with a wider window.  Every CTA
+      // received the same C states in exchange 1 and takes the newest one, so all CTAs place the same window.  Speed
+      // only: a wrong window is detected and the halfspace redone.
+      const unsigned long long zs =
+          lane < C ? static_cast<unsigned long long>(__double_as_longlong(sh->x1[par][lane][12])) : 0ull;
+      const unsigned my_hi = static_cast<unsigned>(zs >> 32);            // (tag << 1) | learned: tags are unique
+      const unsigned best_hi = __reduce_max_sync(kFull, my_hi);
+      const unsigned owner = __ballot_sync(kFull, my_hi == best_hi);
+      const float z_state = __uint_as_float(__shfl_sync(kFull, static_cast<unsigned>(zs), __ffs(owner) - 1));
+      const int z_learned = static_cast<int>(best_hi & 1u);
+      float zlo = a.z_lo_f, zhi = a.z_hi_f;
+      if (z_learned) {
+        zlo = z_state - a.z_half_adapt_f;
+        zhi = z_state + a.z_half_adapt_f;
+      }
+      const float a_lo = pm - zlo * sigma, a_hi = pm - zhi * sigma;
       const double c = static_cast<double>(h0f) * f0 + static_cast<double>(h1f) * f1;   // h_a . first
       const double t_lo = __dadd_rn(-static_cast<double>(a_lo) - c, 0.0);  // +0.0: never -0.0 (canonical losses are +0)
       const double t_hi = __dadd_rn(-static_cast<double>(a_hi) - c, 0.0);
@@ -565,6 +611,9 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         ctl->h0f = h0f; ctl->h1f = h1f; ctl->thr_keep = thr_keep; ctl->thr_above = thr_above;
         ctl->key_lo = klo;
         ctl->window_ok = window_ok;
+        ctl->z_learned = z_learned;
+        ctl->z_est = z_state;
+        ctl->pl = Ctl::Place{pm, sigma, c};
       }
     }
     cl_team_sync();  // S2

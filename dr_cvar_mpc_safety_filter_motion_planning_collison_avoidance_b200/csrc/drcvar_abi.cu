@@ -264,6 +264,7 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
       ca.z_half_f = static_cast<float>(0.5 * (zh - zl));
       ca.z_lo_f = ca.z_mid_f - ca.z_half_f;
       ca.z_hi_f = ca.z_mid_f + ca.z_half_f;
+      ca.z_half_adapt_f = 1.6f * ca.z_half_f;   // learned-centre mode: what the leader's candidate pool still holds
       ca.bulk = gen_mode ? 0 : 1;
       ca.cl_ctas = ctas;
       const size_t csmem = cluster_smem_bytes(c.N, ctas, sizeof(T));

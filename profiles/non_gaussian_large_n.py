@@ -4,7 +4,7 @@ sys.path.insert(0, '/root/repo')
 import dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 as pkg
 from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
 P = dict(alpha=0.1, delta=0.1, epsilon=0.01, robot_radius=0.3, obstacle_radius=0.3)
-B, N = 4096, 100000
+B, N = (int(sys.argv[1]) if len(sys.argv) > 1 else 4096), 100000
 g = torch.Generator(device="cuda").manual_seed(3)
 mu = torch.rand(B, 1, 2, generator=g, device="cuda") * 8 - 4
 ego = torch.zeros(B, 2, device="cuda", dtype=torch.float64)
