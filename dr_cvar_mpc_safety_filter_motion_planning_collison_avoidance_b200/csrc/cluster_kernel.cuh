@@ -18,7 +18,9 @@
 //   exchange2 partial counts / sums and the candidates go to the halfspace's leader CTA (rotating) through DSMEM
 //   finish    leader: exact rank among the candidates (radix narrowing), CVaR, offsets          core/risk_metrics.py:84-338
 // A window miss (3e-5 of Gaussian halfspaces), an overflow or non-finite data put the halfspace on a redo list that the
-// streaming kernel processes right after (exact general select, same arithmetic contract).  Generate mode (samples ==
+// streaming kernel processes right after (exact general select, same arithmetic contract).  Samples that are not
+// Gaussian: the finishers publish where the threshold really sits ({tag, learned, z} in one word, shared through
+// exchange 1, newest wins in every CTA alike) and the cluster switches to a learned, wider window.  Generate mode (samples ==
 // nullptr): the team draws this CTA's part into the slot (sample_gen.cuh, once per halfspace — the streaming kernel re-draws
 // it in each of its passes) instead of waiting for TMA.  Tail indices stay on the streaming kernel.  fp32 inputs only.
 #pragma once
