@@ -9,10 +9,10 @@ flow it repeats n_runs times.  PARITY IS UNPINNED: there is no reference source 
 What changes against a run-by-run loop: the obstacle data of all runs is generated first (same order of random draws),
 the safe halfspaces of ALL runs are computed in ONE launch (SafetyFilteringEnvironment.compute_safe_halfspaces_for_runs,
 falling back to the per-run method of an environment that lacks it), and the MPC QPs — independent per (run, metric) —
-can be fanned out over host processes (`n_workers`).  This is the real source of BASELINE config 4's scenario axis
+can be fanned out over host threads (`n_workers`; the QP time is in LAPACK, which releases the GIL).  This is the real source of BASELINE config 4's scenario axis
 (NUM_MC_RUNS = 300, config/parameters.py:33).
 """
-import multiprocessing as mp
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -37,7 +37,7 @@ def run_monte_carlo_simulation(env, scenario_config, n_runs, params, n_workers=1
 
     env: Safety filtering environment; scenario_config: Scenario configuration (config/scenarios.py);
     n_runs: Number of Monte Carlo runs; params: Configuration parameters (config/parameters.py: HORIZON, DT, SIM_TIME,
-    NUM_SAMPLES, Q_WEIGHT, R_WEIGHT); n_workers (extension): host processes for the MPC QPs.
+    NUM_SAMPLES, Q_WEIGHT, R_WEIGHT); n_workers (extension): host threads for the MPC QPs.
     Returns: results: Dictionary of results — 'min_distances' {method: [n_runs]}, 'collision_counts', 'collision_probs'
     {method: value}, 'timing_stats' (TimingStats), for the methods reference (unfiltered), mean, cvar, dr_cvar.
     """
@@ -87,8 +87,10 @@ def run_monte_carlo_simulation(env, scenario_config, n_runs, params, n_workers=1
     jobs = [(r, m) for r in range(n_runs) for m in METHODS[1:]]
     filtered = {}
     if n_workers > 1 and len(jobs) > 1:
-        with mp.get_context("fork").Pool(n_workers) as pool:       # workers inherit _WORK
-            done = pool.map(_filter_one, jobs)
+        # threads, not processes: the QP time is in LAPACK (GIL released), and forking a process that holds a CUDA context
+        # is not safe
+        with ThreadPoolExecutor(n_workers) as pool:
+            done = list(pool.map(_filter_one, jobs))
     else:
         done = [_filter_one(j) for j in jobs]
     for run, metric, x_f, info in done:

@@ -7,7 +7,7 @@ against a plain run-by-run loop of the single-scenario flow (main.py:37-147).
     run-by-run loop with the REFERENCE's MPC filter (through the cvxpy shim) on the same seed: same minimum distances;
   * GPU: compute_safe_halfspaces_for_runs (one launch for all runs) == the per-run method, bit for bit; the driver runs
     end to end with stand-ins for the reference's obstacle generator / planner (absent on the GPU box), and fanning the
-    MPC QPs out over processes changes nothing.
+    MPC QPs out over threads changes nothing.
 """
 import importlib
 import os
@@ -182,7 +182,7 @@ def test_all_runs_in_one_launch_and_driver_end_to_end(tmp_path, monkeypatch):
                         h1, g1 = single[metric][t][i].get_constraint_params()
                         h2, g2 = batched[r][metric][t][i].get_constraint_params()
                         assert np.array_equal(h1, h2) and g1 == g2
-        # the driver end to end; MPC QPs fanned out over two processes give the same numbers
+        # the driver end to end; MPC QPs fanned out over two threads give the same numbers
         np.random.seed(11)
         a = mc.run_monte_carlo_simulation(env, cfg, 4, params)
         np.random.seed(11)
