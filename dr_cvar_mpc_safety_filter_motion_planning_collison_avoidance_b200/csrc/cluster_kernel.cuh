@@ -492,13 +492,15 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         qyy += shfl_xor_d(qyy, m);
         b2 = fmaxf(b2, __shfl_xor_sync(kFull, b2, m));
       }
-      // learned-window state of our finisher: ONE read, the same bits to every destination
+      // leader of this halfspace: our finisher must be done with the pool / x2 / fin_ctl of the halfspace we led last,
+      // before any CTA can get past exchange 1 and send the next candidates
+      if (static_cast<int>(rank) == leader && n_lead > 0) mbar_wait(&sh->fdone, (n_lead - 1) & 1u);
+      // learned-window state of our finisher (ONE read, the same bits to every destination).  Only the LEADER's word is
+      // used, and the leader has just waited for its finisher: the state is a deterministic function of the halfspaces
+      // this CTA led before (it - C, it - 2C, ...), so results do not depend on how far the finishers lag.
       unsigned long long zp = lane == 0 ? *reinterpret_cast<volatile unsigned long long*>(&sh->zpub) : 0ull;
       zp = __shfl_sync(kFull, zp, 0);
       if (lane < C) {   // lane d serves destination CTA d
-        // leader of this halfspace: our finisher must be done with the pool / x2 / fin_ctl of the halfspace we led last,
-        // before any CTA can get past exchange 1 and send the next candidates
-        if (static_cast<int>(rank) == leader && n_lead > 0) mbar_wait(&sh->fdone, (n_lead - 1) & 1u);
         const uint32_t dst = mapa_u32(smem_u32(&sh->x1[par][rank][0]), static_cast<uint32_t>(lane));
         const uint32_t bar = mapa_u32(smem_u32(&sh->xbar1[par]), static_cast<uint32_t>(lane));
         mbar_arrive_expect_tx_remote(bar, 8u * (2u * O + 5u));
@@ -576,17 +578,14 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       int window_ok = a.use_window && usable && (var_l > 0.f) && isfinite(sigma);
       // thresholds in shifted coordinates, p = h_a.(xi - first):  a_lo <-> t_lo,  a_hi <-> t_hi  (a_hi <= a_lo)
       const float pm = fmaf(h1f, mr1f, h0f * mr0f);
-      // Window bounds in z units: the Gaussian plan of the host, or — once a finisher of this cluster has seen two window
-      // misses in a row (samples that are evidently not Gaussian) — the LEARNED centre with a wider window.  Every CTA
-      // received the same C states in exchange 1 and takes the newest one, so all CTAs place the same window.  Speed
-      // only: a wrong window is detected and the halfspace redone.
-      const unsigned long long zs =
-          lane < C ? static_cast<unsigned long long>(__double_as_longlong(sh->x1[par][lane][12])) : 0ull;
-      const unsigned my_hi = static_cast<unsigned>(zs >> 32);            // (tag << 1) | learned: tags are unique
-      const unsigned best_hi = __reduce_max_sync(kFull, my_hi);
-      const unsigned owner = __ballot_sync(kFull, my_hi == best_hi);
-      const float z_state = __uint_as_float(__shfl_sync(kFull, static_cast<unsigned>(zs), __ffs(owner) - 1));
-      const int z_learned = static_cast<int>(best_hi & 1u);
+      // Window bounds in z units: the Gaussian plan of the host, or — once the finisher of this halfspace's LEADER has seen
+      // two window misses in a row on the halfspaces it led (samples that are evidently not Gaussian) — its LEARNED centre
+      // with a wider window.  Every CTA received the leader's word in exchange 1, so all CTAs place the same window, and
+      // the word is a deterministic function of earlier halfspaces (one chain per leader, like the resident kernel's
+      // parity chains).  Speed only: a wrong window is detected and the halfspace redone.
+      const unsigned long long zs = static_cast<unsigned long long>(__double_as_longlong(sh->x1[par][leader][12]));
+      const float z_state = __uint_as_float(static_cast<unsigned>(zs));
+      const int z_learned = static_cast<int>((zs >> 32) & 1ull);
       float zlo = a.z_lo_f, zhi = a.z_hi_f;
       if (z_learned) {
         zlo = z_state - a.z_half_adapt_f;

@@ -297,7 +297,8 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
         CUDA_TRY(cudaLaunchKernelEx(&cfg, ck, ca));
         g_launches.fetch_add(1);
         // the halfspaces it handed back (window miss, overflow, non-finite data): exact general select, streaming kernel
-        KernelArgs ra = a;   // (the streaming kernel's own window plan: after two misses in a row a CTA learns the centre)
+        KernelArgs ra = a;
+        ra.use_window = 0;   // the redo list is filled in no particular order: the exact general select does not depend on it
         ra.redo_count = redo;
         ra.redo_list = redo + 1;
         ra.bulk = 1;

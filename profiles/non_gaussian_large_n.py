@@ -17,7 +17,7 @@ for dist in ("gauss", "uniform", "laplace"):
         elif dist == "uniform":
             z = 0.3464 * (torch.rand(nb, N, 2, generator=g, device="cuda") - 0.5)
         else:
-            u = torch.rand(nb, N, 2, generator=g, device="cuda") - 0.5
+            u = (torch.rand(nb, N, 2, generator=g, device="cuda") - 0.5).clamp(-0.4999999, 0.4999999)
             z = -0.0707 * torch.sign(u) * torch.log1p(-2 * u.abs())
         s[b0:b0 + nb] = mu[b0:b0 + nb] + z
     for name, fl in (("cluster+redo", 0), ("streaming", _lib.FLAG_NO_CLUSTER)):
