@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
                        __float_as_uint(z_new);
         }
       } else if (lane == 0) {
-        a.redo_list[atomicAdd(a.redo_count, 1)] = static_cast<int>(b);
+        a.redo_list[b] = 1;   // redo flag of halfspace b
         // a placed window that missed: after two in a row (or already in learned mode) move a learned centre past the
         // window, towards the side the threshold is on
         bool clean = fc->window_ok != 0 && fc->nonfinite == 0;

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f64(const Kernel
         if (lane == 0)
           write_risk_outputs(a, b, fc, false, s_hi + s4, cnt_hi + c4, T_thr, fc->degenerate ? kStatusDegenerate : 0);
       } else if (lane == 0) {
-        a.redo_list[atomicAdd(a.redo_count, 1)] = static_cast<int>(b);
+        a.redo_list[b] = 1;   // redo flag of halfspace b
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->fdone);

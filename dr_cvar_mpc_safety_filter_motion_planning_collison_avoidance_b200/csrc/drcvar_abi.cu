@@ -269,9 +269,9 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
       ca.cl_ctas = ctas;
       const size_t csmem = cluster_smem_bytes(c.N, ctas, sizeof(T));
       CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(csmem)));
-      int* redo = nullptr;   // [0] = count, [1..] = halfspace indices; stream-ordered allocation
+      int* redo = nullptr;   // [0] unused, [1 + b] = redo flag of halfspace b; stream-ordered allocation
       CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&redo), sizeof(int) * (static_cast<size_t>(c.B) + 1), stream));
-      CUDA_TRY(cudaMemsetAsync(redo, 0, sizeof(int), stream));
+      CUDA_TRY(cudaMemsetAsync(redo, 0, sizeof(int) * (static_cast<size_t>(c.B) + 1), stream));
       ca.redo_count = redo;
       ca.redo_list = redo + 1;
       cudaLaunchConfig_t cfg{};
@@ -297,8 +297,7 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
         CUDA_TRY(cudaLaunchKernelEx(&cfg, ck, ca));
         g_launches.fetch_add(1);
         // the halfspaces it handed back (window miss, overflow, non-finite data): exact general select, streaming kernel
-        KernelArgs ra = a;
-        ra.use_window = 0;   // the redo list is filled in no particular order: the exact general select does not depend on it
+        KernelArgs ra = a;   // the streaming kernel's own window plan; a CTA that misses twice in a row learns the centre
         ra.redo_count = redo;
         ra.redo_list = redo + 1;
         ra.bulk = 1;

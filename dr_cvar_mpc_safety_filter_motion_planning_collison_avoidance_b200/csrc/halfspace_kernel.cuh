@@ -116,9 +116,11 @@ struct KernelArgs {
   long long gen_index_offset;   // global index of halfspace 0 of this launch (shards reproduce the unsharded stream)
   float* gen_samples_out;    // optional [B,N,2] dump of the generated samples (parity tests)
   // cluster kernel (cluster_kernel.cuh): CTAs per halfspace; halfspaces it could not finish (window miss, overflow,
-  // non-finite data) are appended to redo_list and processed by the streaming kernel, which then takes its work from it
+  // non-finite data) get redo_list[b] = 1 (one flag per halfspace) and are processed by the streaming kernel, which then
+  // skips every halfspace whose flag is 0 — a static assignment of halfspaces to CTAs, so its learned windows (and the
+  // last bits of the sums) do not depend on the order in which the cluster kernel found the misses
   int cl_ctas;
-  int* redo_count;
+  int* redo_count;   // unused (kept for layout stability)
   int* redo_list;
   int debug;   // profiling builds only: ablation switches
 };

@@ -11,7 +11,7 @@
 // If the window misses (or GENERAL_ONLY): the exact multi-pass radix select over all samples (2-4 more reads).
 // fp32 samples with 32768 < N <~ 205000 normally run the single-read cluster / DSMEM kernel (cluster_kernel.cuh); this kernel
 // serves everything else — fp64, tail indices, strided or unaligned views, 24000 < N <= 32768 — and the halfspaces the
-// cluster kernel hands back (work list `redo_list`).  After two consecutive window misses a CTA learns the window centre.
+// cluster kernel hands back (flags `redo_list[b]`).  After two consecutive window misses a CTA learns the window centre.
 #pragma once
 
 #include "halfspace_kernel.cuh"
@@ -54,10 +54,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
   const int N = a.N;
   auto sync = [] { __syncthreads(); };
 
-  // work list: the whole batch, or the halfspaces the cluster kernel handed back (redo list, filled on the device)
-  const long long n_work = a.redo_list != nullptr ? static_cast<long long>(*a.redo_count) : a.B;
-  for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-    const long long b = a.redo_list != nullptr ? static_cast<long long>(a.redo_list[wi]) : wi;
+  // work: the whole batch, or — redo pass of the cluster kernel — the halfspaces whose redo flag is set
+  for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+    if (a.redo_list != nullptr && a.redo_list[b] == 0) continue;
     const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
     const bool vec = kGen || a.bulk != 0;   // contiguous (x, y) pairs, 16-byte aligned rows: vector loads
     // generate mode (fp32): the samples are drawn on the fly in EVERY pass (sample_gen.cuh; one Philox call per pair)
