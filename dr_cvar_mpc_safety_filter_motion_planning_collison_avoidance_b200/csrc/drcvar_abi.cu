@@ -19,6 +19,7 @@
 #include "streaming_kernel.cuh"
 #include "cluster_kernel.cuh"
 #include "cluster_kernel_f64.cuh"
+#include "ring_kernel.cuh"
 
 namespace {
 
@@ -330,6 +331,55 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
     return DRCVAR_OK;
+  }
+  if constexpr (sizeof(T) == 4) {
+    // ---- ring kernel (ring_kernel.cuh): fp32 samples, 4096 < N <= 10 240, contiguous 16-byte aligned rows.  One CTA per
+    // SM streams the batch through a shared-memory ring; window misses and unusual data come back as redo flags and go
+    // through the exact general path of the streaming kernel.
+    if (a.bulk && a.use_window && !tail && c.gen_mean == nullptr && c.N >= kRgMinN && c.N <= kRgMaxN && (c.N % 2 == 0) &&
+        c.B < 0x7fffffffLL && !(c.flags & (DRCVAR_FLAG_NO_RING | DRCVAR_FLAG_GENERAL_ONLY | DRCVAR_FLAG_NO_BULK))) {
+      double zl = 0, zh = 0;
+      if (plan_window(c.N, kc, c.N, 0.6 * kRgCandCap * kRgWarps, &zl, &zh)) {
+        KernelArgs ra = a;
+        ra.z_lo = zl;
+        ra.z_hi = zh;
+        ra.z_mid_f = static_cast<float>(0.5 * (zl + zh));
+        ra.z_half_f = static_cast<float>(0.5 * (zh - zl));
+        ra.z_lo_f = ra.z_mid_f - ra.z_half_f;
+        ra.z_hi_f = ra.z_mid_f + ra.z_half_f;
+        ra.z_half_adapt_f = 2.0f * ra.z_half_f;   // learned-centre mode: what the per-thread and per-warp lists still hold
+        const size_t rsmem = rg_smem_bytes();
+        if (rsmem <= static_cast<size_t>(di->max_smem_optin)) {
+          CUDA_TRY(cudaFuncSetAttribute(halfspace_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem)));
+          int* redo = nullptr;   // [0] unused, [1 + b] = redo flag of halfspace b; stream-ordered allocation
+          CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&redo), sizeof(int) * (static_cast<size_t>(c.B) + 1), stream));
+          cudaError_t e = cudaMemsetAsync(redo, 0, sizeof(int) * (static_cast<size_t>(c.B) + 1), stream);
+          if (e == cudaSuccess) {
+            ra.redo_count = redo;
+            ra.redo_list = redo + 1;
+            long long rgrid = std::min<long long>(c.B, di->sms);
+#ifdef DRCVAR_PROFILE_PHASES
+            if (const char* eg = getenv("DRCVAR_DEBUG_GRID")) rgrid = std::min<long long>(rgrid, atoll(eg));
+#endif
+            halfspace_ring_kernel<<<static_cast<unsigned>(rgrid), kRgThreads, rsmem, stream>>>(ra);
+            e = cudaGetLastError();
+          }
+          if (e == cudaSuccess) {
+            g_launches.fetch_add(1);
+            KernelArgs sa = a;   // redo pass: the streaming kernel's own plan, exact general select on a miss
+            sa.redo_count = redo;
+            sa.redo_list = redo + 1;
+            const long long sgrid = std::min<long long>(c.B, di->sms);
+            streaming_kernel<T, false><<<static_cast<unsigned>(sgrid), kStreamThreads, 0, stream>>>(sa);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) g_launches.fetch_add(1);
+          }
+          cudaFreeAsync(redo, stream);   // (also on the error paths)
+          if (e != cudaSuccess) return fail(DRCVAR_ERR_CUDA, "ring kernel launch failed: %s", cudaGetErrorString(e));
+          return DRCVAR_OK;
+        }
+      }
+    }
   }
   auto kern = tail ? halfspace_kernel<T, true> : halfspace_kernel<T, false>;
   if constexpr (sizeof(T) == 4) {

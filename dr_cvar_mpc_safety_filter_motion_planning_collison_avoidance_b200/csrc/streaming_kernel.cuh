@@ -21,6 +21,7 @@ namespace drcvar {
 constexpr int kStreamThreads = 512;
 constexpr int kStreamWarps = kStreamThreads / 32;
 constexpr int kStreamCand = 256;    // window candidates per warp (doubles)
+constexpr int kStreamRedoCap = 512;   // flagged halfspaces a CTA lists up front in a redo pass
 constexpr int kStreamUnroll = 8;    // 16-byte loads in flight per thread in pass 2
 
 template <typename T, bool kTail, bool kGen = false>
@@ -54,9 +55,40 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
   const int N = a.N;
   auto sync = [] { __syncthreads(); };
 
-  // work: the whole batch, or — redo pass of the cluster kernel — the halfspaces whose redo flag is set
-  for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
-    if (a.redo_list != nullptr && a.redo_list[b] == 0) continue;
+  // work: the whole batch, or — redo pass of the cluster / register-file kernels — the halfspaces whose redo flag is set.
+  // The assignment of halfspaces to CTAs stays the static one (b = blockIdx.x + i gridDim.x, increasing i); a redo pass
+  // first gathers the flagged i of this CTA with all threads (a dependent flag load per halfspace would cost more than
+  // the few flagged halfspaces themselves at B = 655 360) and sorts the short list.
+  __shared__ int redo_i[kStreamRedoCap];
+  __shared__ int redo_n;
+  const long long n_mine = blockIdx.x < a.B ? (a.B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  long long n_work = n_mine;
+  bool listed = false;
+  if (a.redo_list != nullptr) {
+    if (threadIdx.x == 0) redo_n = 0;
+    __syncthreads();
+    for (long long i = threadIdx.x; i < n_mine; i += kStreamThreads)
+      if (a.redo_list[blockIdx.x + i * gridDim.x] != 0) {
+        const int pos = atomicAdd(&redo_n, 1);
+        if (pos < kStreamRedoCap) redo_i[pos] = static_cast<int>(i);
+      }
+    __syncthreads();
+    if (redo_n <= kStreamRedoCap) {   // (more than that: nearly everything is flagged, the plain scan below costs nothing extra)
+      listed = true;
+      n_work = redo_n;
+      if (threadIdx.x == 0)   // insertion sort: the list is short, its order must not depend on the atomics
+        for (int i = 1; i < redo_n; ++i) {
+          const int key = redo_i[i];
+          int j = i - 1;
+          for (; j >= 0 && redo_i[j] > key; --j) redo_i[j + 1] = redo_i[j];
+          redo_i[j + 1] = key;
+        }
+      __syncthreads();
+    }
+  }
+  for (long long wi = 0; wi < n_work; ++wi) {
+    const long long b = blockIdx.x + (listed ? static_cast<long long>(redo_i[wi]) : wi) * gridDim.x;
+    if (!listed && a.redo_list != nullptr && a.redo_list[b] == 0) continue;
     const T* base = reinterpret_cast<const T*>(a.samples) + b * a.stride_b;
     const bool vec = kGen || a.bulk != 0;   // contiguous (x, y) pairs, 16-byte aligned rows: vector loads
     // generate mode (fp32): the samples are drawn on the fly in EVERY pass (sample_gen.cuh; one Philox call per pair)
