@@ -19,7 +19,6 @@
 #include "streaming_kernel.cuh"
 #include "cluster_kernel.cuh"
 #include "cluster_kernel_f64.cuh"
-#include "ring_kernel.cuh"
 
 namespace {
 
@@ -239,7 +238,6 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
 #endif
   const bool tail = c.tail_idx_out != nullptr;
   a.cl_ctas = 0;
-  a.redo_count = nullptr;
   a.redo_list = nullptr;
   if (streaming && !(c.flags & (DRCVAR_FLAG_FORCE_STREAMING | DRCVAR_FLAG_NO_CLUSTER | DRCVAR_FLAG_GENERAL_ONLY)) &&
       !tail && c.N > kOctantMinN && c.B < 0x7fffffffLL &&
@@ -270,37 +268,39 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
       ca.cl_ctas = ctas;
       const size_t csmem = cluster_smem_bytes(c.N, ctas, sizeof(T));
       CUDA_TRY(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(csmem)));
-      int* redo = nullptr;   // [0] unused, [1 + b] = redo flag of halfspace b; stream-ordered allocation
-      CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&redo), sizeof(int) * (static_cast<size_t>(c.B) + 1), stream));
-      CUDA_TRY(cudaMemsetAsync(redo, 0, sizeof(int) * (static_cast<size_t>(c.B) + 1), stream));
-      ca.redo_count = redo;
-      ca.redo_list = redo + 1;
-      cudaLaunchConfig_t cfg{};
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = static_cast<unsigned>(ctas);
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.gridDim = dim3(static_cast<unsigned>(ctas), 1, 1);
-      cfg.blockDim = dim3(kClThreads, 1, 1);
-      cfg.dynamicSmemBytes = csmem;
-      cfg.stream = stream;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      int max_clusters = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, ck, &cfg));
+      int* redo = nullptr;   // redo flag of halfspace b at redo[b]; stream-ordered allocation, freed on every path below
+      CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&redo), sizeof(int) * static_cast<size_t>(c.B), stream));
+      auto cluster_pass = [&]() -> cudaError_t {   // returns cudaErrorNotReady when no cluster fits (fall through to streaming)
+        cudaError_t e = cudaMemsetAsync(redo, 0, sizeof(int) * static_cast<size_t>(c.B), stream);
+        if (e != cudaSuccess) return e;
+        ca.redo_list = redo;
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = static_cast<unsigned>(ctas);
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(static_cast<unsigned>(ctas), 1, 1);
+        cfg.blockDim = dim3(kClThreads, 1, 1);
+        cfg.dynamicSmemBytes = csmem;
+        cfg.stream = stream;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int max_clusters = 0;
+        e = cudaOccupancyMaxActiveClusters(&max_clusters, ck, &cfg);
+        if (e != cudaSuccess) return e;
 #ifdef DRCVAR_PROFILE_PHASES
-      fprintf(stderr, "[drcvar] cluster kernel: N=%lld ctas=%d smem=%zu max_active_clusters=%d\n", c.N, ctas, csmem, max_clusters);
+        fprintf(stderr, "[drcvar] cluster kernel: N=%lld ctas=%d smem=%zu max_active_clusters=%d\n", c.N, ctas, csmem, max_clusters);
 #endif
-      if (max_clusters >= 1) {
+        if (max_clusters < 1) return cudaErrorNotReady;
         const long long n_cl = std::min<long long>(c.B, max_clusters);
         cfg.gridDim = dim3(static_cast<unsigned>(n_cl * ctas), 1, 1);
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, ck, ca));
+        e = cudaLaunchKernelEx(&cfg, ck, ca);
+        if (e != cudaSuccess) return e;
         g_launches.fetch_add(1);
         // the halfspaces it handed back (window miss, overflow, non-finite data): exact general select, streaming kernel
         KernelArgs ra = a;   // the streaming kernel's own window plan; a CTA that misses twice in a row learns the centre
-        ra.redo_count = redo;
-        ra.redo_list = redo + 1;
+        ra.redo_list = redo;
         ra.bulk = 1;
         auto rk = streaming_kernel<T, false>;
         if constexpr (sizeof(T) == 4) {
@@ -308,12 +308,16 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
         }
         const long long rgrid = std::min<long long>(c.B, di->sms);
         rk<<<static_cast<unsigned>(rgrid), kStreamThreads, 0, stream>>>(ra);
-        CUDA_TRY(cudaGetLastError());
-        g_launches.fetch_add(1);
-        CUDA_TRY(cudaFreeAsync(redo, stream));
-        return DRCVAR_OK;
-      }
-      CUDA_TRY(cudaFreeAsync(redo, stream));
+        e = cudaGetLastError();
+        if (e == cudaSuccess) g_launches.fetch_add(1);
+        return e;
+      };
+      const cudaError_t ce = cluster_pass();
+      const cudaError_t fe = cudaFreeAsync(redo, stream);
+      if (ce == cudaSuccess && fe == cudaSuccess) return DRCVAR_OK;
+      if (ce != cudaErrorNotReady)
+        return fail(DRCVAR_ERR_CUDA, "cluster kernel path failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : fe));
+      cudaGetLastError();
     }
   }
   if (streaming) {
@@ -331,55 +335,6 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
     return DRCVAR_OK;
-  }
-  if constexpr (sizeof(T) == 4) {
-    // ---- ring kernel (ring_kernel.cuh): fp32 samples, 4096 < N <= 10 240, contiguous 16-byte aligned rows.  One CTA per
-    // SM streams the batch through a shared-memory ring; window misses and unusual data come back as redo flags and go
-    // through the exact general path of the streaming kernel.
-    if (a.bulk && a.use_window && !tail && c.gen_mean == nullptr && c.N >= kRgMinN && c.N <= kRgMaxN && (c.N % 2 == 0) &&
-        c.B < 0x7fffffffLL && !(c.flags & (DRCVAR_FLAG_NO_RING | DRCVAR_FLAG_GENERAL_ONLY | DRCVAR_FLAG_NO_BULK))) {
-      double zl = 0, zh = 0;
-      if (plan_window(c.N, kc, c.N, 0.6 * kRgCandCap * kRgWarps, &zl, &zh)) {
-        KernelArgs ra = a;
-        ra.z_lo = zl;
-        ra.z_hi = zh;
-        ra.z_mid_f = static_cast<float>(0.5 * (zl + zh));
-        ra.z_half_f = static_cast<float>(0.5 * (zh - zl));
-        ra.z_lo_f = ra.z_mid_f - ra.z_half_f;
-        ra.z_hi_f = ra.z_mid_f + ra.z_half_f;
-        ra.z_half_adapt_f = 2.0f * ra.z_half_f;   // learned-centre mode: what the per-thread and per-warp lists still hold
-        const size_t rsmem = rg_smem_bytes();
-        if (rsmem <= static_cast<size_t>(di->max_smem_optin)) {
-          CUDA_TRY(cudaFuncSetAttribute(halfspace_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem)));
-          int* redo = nullptr;   // [0] unused, [1 + b] = redo flag of halfspace b; stream-ordered allocation
-          CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&redo), sizeof(int) * (static_cast<size_t>(c.B) + 1), stream));
-          cudaError_t e = cudaMemsetAsync(redo, 0, sizeof(int) * (static_cast<size_t>(c.B) + 1), stream);
-          if (e == cudaSuccess) {
-            ra.redo_count = redo;
-            ra.redo_list = redo + 1;
-            long long rgrid = std::min<long long>(c.B, di->sms);
-#ifdef DRCVAR_PROFILE_PHASES
-            if (const char* eg = getenv("DRCVAR_DEBUG_GRID")) rgrid = std::min<long long>(rgrid, atoll(eg));
-#endif
-            halfspace_ring_kernel<<<static_cast<unsigned>(rgrid), kRgThreads, rsmem, stream>>>(ra);
-            e = cudaGetLastError();
-          }
-          if (e == cudaSuccess) {
-            g_launches.fetch_add(1);
-            KernelArgs sa = a;   // redo pass: the streaming kernel's own plan, exact general select on a miss
-            sa.redo_count = redo;
-            sa.redo_list = redo + 1;
-            const long long sgrid = std::min<long long>(c.B, di->sms);
-            streaming_kernel<T, false><<<static_cast<unsigned>(sgrid), kStreamThreads, 0, stream>>>(sa);
-            e = cudaGetLastError();
-            if (e == cudaSuccess) g_launches.fetch_add(1);
-          }
-          cudaFreeAsync(redo, stream);   // (also on the error paths)
-          if (e != cudaSuccess) return fail(DRCVAR_ERR_CUDA, "ring kernel launch failed: %s", cudaGetErrorString(e));
-          return DRCVAR_OK;
-        }
-      }
-    }
   }
   auto kern = tail ? halfspace_kernel<T, true> : halfspace_kernel<T, false>;
   if constexpr (sizeof(T) == 4) {
@@ -429,29 +384,27 @@ struct HostCtx {
   double last_stage_ms = 0, last_kernel_ms = 0;
   long long last_h2d = 0, last_d2h = 0;
 };
-HostCtx g_host;
+// One context per device: a process that drives several GPUs through DRCVAR_HOST (cudaSetDevice between calls, or one
+// thread per GPU) keeps every device's streams, events and staging buffers; nothing is torn down on a device switch and
+// calls on different devices do not serialise on each other.
+HostCtx g_host[64];
 
-int ensure_host_ctx(HostCtx& hc) {
+int host_ctx(HostCtx** out) {
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
-  if (hc.device != dev) {
-    // (re)create per-device resources; old buffers are released
-    for (int i = 0; i < 2; ++i) {
-      if (hc.d_samples[i]) cudaFree(hc.d_samples[i]);
-      if (hc.d_io[i]) cudaFree(hc.d_io[i]);
-      if (hc.h_pack[i]) cudaFreeHost(hc.h_pack[i]);
-      if (hc.h_out_stage[i]) cudaFreeHost(hc.h_out_stage[i]);
-      hc.h_out_stage[i] = nullptr; hc.h_out_cap[i] = 0;
-      hc.d_samples[i] = nullptr; hc.d_samples_cap[i] = 0;
-      hc.d_io[i] = nullptr; hc.d_io_cap[i] = 0;
-      hc.h_pack[i] = nullptr; hc.h_pack_cap[i] = 0;
-      if (hc.streams[i]) cudaStreamDestroy(hc.streams[i]);
-      CUDA_TRY(cudaStreamCreateWithFlags(&hc.streams[i], cudaStreamNonBlocking));
-    }
-    if (!hc.ev_start) {
-      CUDA_TRY(cudaEventCreate(&hc.ev_start));
-      CUDA_TRY(cudaEventCreate(&hc.ev_stop));
-    }
+  if (dev < 0 || dev >= 64) return fail(DRCVAR_ERR_INVALID, "device index %d out of range", dev);
+  *out = &g_host[dev];
+  return DRCVAR_OK;
+}
+
+// (called with hc.mu held, on the device the context belongs to)
+int ensure_host_ctx(HostCtx& hc) {
+  if (hc.device < 0) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&hc.streams[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&hc.ev_start));
+    CUDA_TRY(cudaEventCreate(&hc.ev_stop));
     hc.device = dev;
   }
   return DRCVAR_OK;
@@ -482,9 +435,12 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 template <typename T>
 int run_host(const Call& c) {
-  HostCtx& hc = g_host;
+  HostCtx* hcp = nullptr;
+  int rc = host_ctx(&hcp);
+  if (rc) return rc;
+  HostCtx& hc = *hcp;
   std::lock_guard<std::mutex> lk(hc.mu);
-  int rc = ensure_host_ctx(hc);
+  rc = ensure_host_ctx(hc);
   if (rc) return rc;
   double k_f;
   long long kc;
@@ -619,9 +575,12 @@ int run_host(const Call& c) {
 
 // DRCVAR_HOST path of the generate mode: the inputs are tiny (mean, chol, ego per halfspace), one stream, no chunking.
 int run_host_generated(const Call& c) {
-  HostCtx& hc = g_host;
+  HostCtx* hcp = nullptr;
+  int rc = host_ctx(&hcp);
+  if (rc) return rc;
+  HostCtx& hc = *hcp;
   std::lock_guard<std::mutex> lk(hc.mu);
-  int rc = ensure_host_ctx(hc);
+  rc = ensure_host_ctx(hc);
   if (rc) return rc;
   double k_f;
   long long kc;
@@ -886,10 +845,14 @@ void drcvar_debug_phase_buffer(long long* dev_buf) { g_phase_cycles = dev_buf; }
 #endif
 
 int drcvar_last_host_call_stats(double* stage_ms, double* kernel_ms, int64_t* h2d_bytes, int64_t* d2h_bytes) {
-  if (stage_ms) *stage_ms = g_host.last_stage_ms;
-  if (kernel_ms) *kernel_ms = g_host.last_kernel_ms;
-  if (h2d_bytes) *h2d_bytes = g_host.last_h2d;
-  if (d2h_bytes) *d2h_bytes = g_host.last_d2h;
+  HostCtx* hc = nullptr;   // the context of the CURRENT device (the one the last DRCVAR_HOST call of this thread ran on)
+  const int rc = host_ctx(&hc);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(hc->mu);
+  if (stage_ms) *stage_ms = hc->last_stage_ms;
+  if (kernel_ms) *kernel_ms = hc->last_kernel_ms;
+  if (h2d_bytes) *h2d_bytes = hc->last_h2d;
+  if (d2h_bytes) *d2h_bytes = hc->last_d2h;
   return DRCVAR_OK;
 }
 

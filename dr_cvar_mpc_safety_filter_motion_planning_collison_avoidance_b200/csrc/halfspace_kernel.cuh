@@ -120,7 +120,6 @@ struct KernelArgs {
   // skips every halfspace whose flag is 0 — a static assignment of halfspaces to CTAs, so its learned windows (and the
   // last bits of the sums) do not depend on the order in which the cluster kernel found the misses
   int cl_ctas;
-  int* redo_count;   // unused (kept for layout stability)
   int* redo_list;
   int debug;   // profiling builds only: ablation switches
 };

@@ -11,7 +11,10 @@ import time
 
 import numpy as np
 
-from utils.timing import timeit, Timer
+try:   # the reference's own helpers when this overlay sits on a reference checkout
+    from utils.timing import timeit, Timer
+except ImportError:   # standalone: dropin/_stopwatch.py
+    from _stopwatch import timeit, Timer
 from core.geometry import compute_separating_vector  # noqa: F401  (re-exported like the reference module)
 from core import risk_metrics as _rm
 from core.risk_metrics import dr_cvar_halfspace, cvar_halfspace  # noqa: F401

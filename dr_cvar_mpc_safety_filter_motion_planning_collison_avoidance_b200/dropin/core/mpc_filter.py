@@ -17,7 +17,10 @@ import time
 
 import numpy as np
 
-from utils.timing import timeit, Timer
+try:   # the reference's own helpers when this overlay sits on a reference checkout
+    from utils.timing import timeit, Timer
+except ImportError:   # standalone: dropin/_stopwatch.py
+    from _stopwatch import timeit, Timer
 
 OPTIMAL = "optimal"
 

@@ -17,7 +17,10 @@ import time
 
 import numpy as np
 
-from utils.timing import timeit
+try:   # the reference's own helpers when this overlay sits on a reference checkout
+    from utils.timing import timeit
+except ImportError:   # standalone: dropin/_stopwatch.py
+    from _stopwatch import timeit
 
 from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib as _abi
 from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import engine as _engine

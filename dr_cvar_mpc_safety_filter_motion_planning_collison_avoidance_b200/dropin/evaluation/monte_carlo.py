@@ -12,23 +12,30 @@ falling back to the per-run method of an environment that lacks it), and the MPC
 can be fanned out over host threads (`n_workers`; the QP time is in LAPACK, which releases the GIL).  This is the real source of BASELINE config 4's scenario axis
 (NUM_MC_RUNS = 300, config/parameters.py:33).
 """
+import functools
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
-from utils.timing import Timer, TimingStats
+try:   # the reference's own helpers when this overlay sits on a reference checkout
+    from utils.timing import Timer, TimingStats
+except ImportError:   # standalone: dropin/_stopwatch.py
+    from _stopwatch import Timer, TimingStats
 
 METHODS = ('reference', 'mean', 'cvar', 'dr_cvar')
-_WORK = {}
 
 
-def _filter_one(job):
-    run, metric = job
-    w = _WORK
+def _filter_run(w, run):
+    """One Monte-Carlo run: ONE filter object serves the three metrics in order, like main.py:19-147 (its
+    last_optimal_u fallback then carries over from metric to metric exactly as there).  `w` is this call's work
+    description (no module state: concurrent run_monte_carlo_simulation calls do not see each other)."""
     mpc = w['mpc_cls'](w['A'], w['B'], w['C'], w['Q'], w['R'], w['horizon'], w['dt'])
-    x_f, u_f, info = mpc.filter_trajectory(w['x0'], w['x_ref'], w['u_ref'], w['halfspaces'][run][metric],
-                                           w['input_bounds'], w['state_bounds'][:2])
-    return run, metric, x_f, info
+    out = []
+    for metric in METHODS[1:]:
+        x_f, u_f, info = mpc.filter_trajectory(w['x0'], w['x_ref'], w['u_ref'], w['halfspaces'][run][metric],
+                                               w['input_bounds'], w['state_bounds'][:2])
+        out.append((run, metric, x_f, info))
+    return out
 
 
 def run_monte_carlo_simulation(env, scenario_config, n_runs, params, n_workers=1):
@@ -81,18 +88,17 @@ def run_monte_carlo_simulation(env, scenario_config, n_runs, params, n_workers=1
     for _ in range(n_runs):
         timing_stats.add("Computing Safe Halfspaces", timer.elapsed / max(n_runs, 1))
 
-    _WORK.clear()
-    _WORK.update(mpc_cls=MPCSafetyFilter, A=A, B=B, C=C, Q=Q, R=R, horizon=params.HORIZON, dt=params.DT, x0=x0, x_ref=x_ref,
-                 u_ref=u_ref, halfspaces=halfspaces, input_bounds=input_bounds, state_bounds=state_bounds)
-    jobs = [(r, m) for r in range(n_runs) for m in METHODS[1:]]
+    work = dict(mpc_cls=MPCSafetyFilter, A=A, B=B, C=C, Q=Q, R=R, horizon=params.HORIZON, dt=params.DT, x0=x0, x_ref=x_ref,
+                u_ref=u_ref, halfspaces=halfspaces, input_bounds=input_bounds, state_bounds=state_bounds)
+    one_run = functools.partial(_filter_run, work)
     filtered = {}
-    if n_workers > 1 and len(jobs) > 1:
+    if n_workers > 1 and n_runs > 1:
         # threads, not processes: the QP time is in LAPACK (GIL released), and forking a process that holds a CUDA context
         # is not safe
         with ThreadPoolExecutor(n_workers) as pool:
-            done = list(pool.map(_filter_one, jobs))
+            done = [item for per_run in pool.map(one_run, range(n_runs)) for item in per_run]
     else:
-        done = [_filter_one(j) for j in jobs]
+        done = [item for r in range(n_runs) for item in one_run(r)]
     for run, metric, x_f, info in done:
         filtered[(run, metric)] = x_f
         timing_stats.add(f"MPC Filtering ({metric})", info.get('solve_time', 0.0))

@@ -137,24 +137,31 @@ def _compute_device(lib, s, ego, alpha, delta, epsilon, rr, ro, h, want_tail, fl
         t = x if _is_torch_cuda(x) else torch.as_tensor(np.asarray(x, dtype=np.float64), device=dev)
         return t.to(**f64).expand(B, 2).contiguous()
 
-    ego_t, h_t = prep(ego), prep(h)
-    _, kc = tail_count(alpha, N)
-    if out is None:
-        out = HalfspaceBatch(
-            h=torch.empty((B, 2), **f64), h_mean=torch.empty((B, 2), **f64), g=torch.empty((B, 3), **f64),
-            cvar=torch.empty(B, **f64), var=torch.empty(B, **f64), g_star=torch.empty(B, **f64),
-            status=torch.zeros(B, dtype=torch.int32, device=dev),
-            tail_idx=torch.empty((B, kc), dtype=torch.int32, device=dev) if want_tail else None)
+    # Temporaries and outputs are made on the stream the kernel runs on: with an explicit `stream=` the conversions of ego / h
+    # are ordered before the launch and the caching allocator cannot hand their memory to another stream while the kernel
+    # still reads it.  The batch keeps them alive until the caller drops it.
     if stream is None:
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        tstream = torch.cuda.current_stream(dev)
     elif hasattr(stream, "cuda_stream"):
-        stream = stream.cuda_stream
+        tstream = stream
+    else:
+        tstream = torch.cuda.ExternalStream(int(stream), device=dev)
+    _, kc = tail_count(alpha, N)
+    with torch.cuda.stream(tstream):
+        ego_t, h_t = prep(ego), prep(h)
+        if out is None:
+            out = HalfspaceBatch(
+                h=torch.empty((B, 2), **f64), h_mean=torch.empty((B, 2), **f64), g=torch.empty((B, 3), **f64),
+                cvar=torch.empty(B, **f64), var=torch.empty(B, **f64), g_star=torch.empty(B, **f64),
+                status=torch.zeros(B, dtype=torch.int32, device=dev),
+                tail_idx=torch.empty((B, kc), dtype=torch.int32, device=dev) if want_tail else None)
+    out._keepalive = (s, ego_t, h_t)
     p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
     fn = lib.drcvar_halfspaces_f32 if s.dtype == torch.float32 else lib.drcvar_halfspaces_f64
     rc = fn(s.data_ptr(), B, N, sb, sn, sc, p(ego_t), p(h_t), float(alpha), float(delta), float(epsilon), float(rr),
             float(ro), int(flags), p(out.h), p(out.h_mean), p(out.g), p(out.cvar), p(out.var), p(out.g_star),
             p(out.status), p(out.tail_idx), dev.index if dev.index is not None else torch.cuda.current_device(),
-            C.c_void_p(stream))
+            C.c_void_p(tstream.cuda_stream))
     _lib.check(rc)
     return out
 

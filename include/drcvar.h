@@ -56,7 +56,6 @@ extern "C" {
 #define DRCVAR_FLAG_NO_BULK 4u       /* disable cp.async.bulk staging (use the generic strided loader) */
 #define DRCVAR_FLAG_FORCE_STREAMING 8u /* use the two-pass streaming kernel even when one CTA could hold N samples */
 #define DRCVAR_FLAG_NO_CLUSTER 16u   /* large N: do not use the cluster / DSMEM single-read kernel (streaming kernel instead) */
-#define DRCVAR_FLAG_NO_RING 64u     /* fp32, 4096 < N <= 10 240: do not use the ring kernel (one-slot resident kernel instead) */
 #define DRCVAR_FLAG_FORCE_CLUSTER 32u /* fp64 samples, large N: use the fp64 cluster kernel (opt-in: the streaming kernel is faster there) */
 
 /* per-halfspace status bits written to status_out */
