@@ -280,8 +280,14 @@ __device__ __forceinline__ double value_of(unsigned long long k) {
 __device__ __forceinline__ double loss_of(double h0, double h1, double x, double y) {
   return __dsub_rn(0.0, __dadd_rn(__dmul_rn(h0, x), __dmul_rn(h1, y)));
 }
+// IEEE fp64 division / square root are ~25-instruction software sequences.  The per-halfspace scalar code uses eleven of
+// them (mean, direction, mean halfspace, offsets); inlined they were ~270 instructions of a per-halfspace code footprint
+// that has to stay inside the 32 KB instruction cache next to the sweeps (profiles/README.md, round 2), so they are
+// shared, never inlined.  Same instructions, same bits.
+__device__ __noinline__ double ddiv_canon(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __noinline__ double dsqrt_canon(double a) { return __dsqrt_rn(a); }
 __device__ __forceinline__ double norm2_canon(double a, double b) {
-  return __dsqrt_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+  return dsqrt_canon(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
 }
 __device__ __forceinline__ float sqrt_approx(float x) {   // one MUFU.SQRT (<= 2 ulp), no fix-up / slow path
   float r;
@@ -329,7 +335,7 @@ __device__ __forceinline__ float warp_sum_any4(float a, float b, float c, float 
 // Histogram scan by ONE warp: finds the bucket (from the top) that holds rank r (1-based).
 __device__ __forceinline__ void scan_hist_warp(const unsigned* hist, int r, int lane, int& bstar, int& rprime, int& cnt_in) {
   int run = 0, row = -1, r_row = 0;
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < kHistBuckets / 32; ++i) {
     const int tot = __reduce_add_sync(kFull, static_cast<int>(hist[kHistBuckets - 1 - (32 * i + lane)]));
     if (row < 0 && run + tot >= r) {
@@ -425,8 +431,8 @@ __device__ __forceinline__ void write_mean_outputs(const KernelArgs& a, long lon
     hm0 = 1.0;
     hm1 = 0.0;
   } else {
-    hm0 = __ddiv_rn(m0, mn);
-    hm1 = __ddiv_rn(m1, mn);
+    hm0 = ddiv_canon(m0, mn);
+    hm1 = ddiv_canon(m1, mn);
   }
   const double hmn = norm2_canon(hm0, hm1);
   const double g_mean = -__dsub_rn(__dadd_rn(__dmul_rn(hm0, m0), __dmul_rn(hm1, m1)), __dmul_rn(a.R, hmn));
@@ -452,7 +458,7 @@ __device__ __forceinline__ void write_risk_outputs(const KernelArgs& a, long lon
     g_dr = __dsub_rn(100.0, r);
   } else {
     const double S = __dadd_rn(s_tot, __dmul_rn(__dsub_rn(a.k_f, static_cast<double>(c_tot)), T_thr));
-    cvar = __ddiv_rn(S, a.k_f);
+    cvar = ddiv_canon(S, a.k_f);
     var_t = T_thr;
     const double cr = __dadd_rn(cvar, r);
     g_cvar = __dsub_rn(cr, a.delta);
@@ -521,6 +527,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     bulk_g2s(smem_raw, src, n0, &bars->data0);
     if (copy_bytes > n0) {
       mbar_expect_tx(&bars->data, copy_bytes - n0);
+#pragma unroll 1
       for (uint32_t off = n0; off < copy_bytes; off += kBulkChunk) {
         const uint32_t n = copy_bytes - off < kBulkChunk ? copy_bytes - off : kBulkChunk;
         bulk_g2s(smem_raw + off, src + off, n, &bars->data);
@@ -551,9 +558,13 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         // pass over all candidates: above bucket b* -> counted/summed; bucket b* -> gathered for exact ranking
         double s3 = 0.0;
         int c3 = 0, n_small = 0;
+        // (rolled on purpose, here and below: the finisher is off the team's path, but its code shares the 32 KB
+        //  instruction cache with the sweeps — the per-halfspace footprint of the kernel was 35 KB)
+#pragma unroll 1
         for (int w = 0; w < kSweepWarps; ++w) {
           const int nc = ired[w * 2 + 1];
           const double* wc = cand + w * kWarpCand;
+#pragma unroll 1
           for (int j0 = 0; j0 < nc; j0 += 32) {
             const int j = j0 + lane;
             bool in_b = false;
@@ -622,7 +633,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         const double s3t = warp_sum_any(s3);
         double lx = 0.0, ly = 0.0;   // "surely above" coordinate sums: lane partials of the 8 sweep warps, fixed order
         if constexpr (kF32) {
-#pragma unroll
+#pragma unroll 1
           for (int w = 0; w < kSweepWarps; ++w) {
             const float2 p = reinterpret_cast<const float2*>(cand + w * kWarpCand + kCandCap)[lane];
             lx += static_cast<double>(p.x);
@@ -632,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         const double s_x = warp_sum_any(lx), s_y = warp_sum_any(ly);
         if (lane == 0) {
           double s_e = 0.0, n_lin = 0.0;
-#pragma unroll
+#pragma unroll 1
           for (int w = 0; w < kSweepWarps; ++w) {
             s_e += fin[w * 4 + 2];
             n_lin += fin[w * 4 + 3];
@@ -696,8 +707,8 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);  // adjacent-pair tree
         w[j] = t[0];
       }
-      double m0 = __ddiv_rn(w[0], static_cast<double>(N));
-      double m1 = __ddiv_rn(w[1], static_cast<double>(N));
+      double m0 = ddiv_canon(w[0], static_cast<double>(N));
+      double m1 = ddiv_canon(w[1], static_cast<double>(N));
       if constexpr (kF32) {  // fp32 inputs: the lane sums were taken relative to the first sample
         m0 = __dadd_rn(red[6], m0);
         m1 = __dadd_rn(red[7], m1);
@@ -717,8 +728,8 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           h1 = 0.0;
           degenerate = 1;
         } else {
-          h0 = __ddiv_rn(d0, nrm);
-          h1 = __ddiv_rn(d1, nrm);
+          h0 = ddiv_canon(d0, nrm);
+          h1 = ddiv_canon(d1, nrm);
         }
       }
       nonfinite |= !(isfinite(h0) && isfinite(h1));
@@ -995,7 +1006,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       const float* redf = reinterpret_cast<const float*>(red);   // warp g: floats 4..9 of its 16 = qxx,qyy,qxy,bound,mdx,mdy
       float q[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       float b2 = 0.f;
-#pragma unroll
+#pragma unroll   // (warp 0's window placement is the one serial section on the team's path: rolling this loop costs 3 %)
       for (int g = 0; g < kSweepWarps; ++g) {
         q[0] += redf[g * 16 + 4];
         q[1] += redf[g * 16 + 5];
