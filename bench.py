@@ -46,7 +46,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-generated", action="store_true", help="skip the generate-mode leg (samples drawn in-kernel)")
     ap.add_argument("--no-large-n", action="store_true", help="skip the N = 100 000 leg (cluster / DSMEM kernel)")
-    ap.add_argument("--large-n-halfspaces", type=int, default=16384, help="halfspaces of the N = 100 000 leg")
+    ap.add_argument("--large-n-halfspaces", type=int, default=65536, help="halfspaces per GPU of the config-5 (N = 100 000) chunk")
+    ap.add_argument("--no-f64", action="store_true", help="skip the fp64-input leg")
+    ap.add_argument("--no-small-n", action="store_true", help="skip the small-N drop-in latency leg (BASELINE configs 1-3)")
     return ap.parse_args()
 
 
@@ -225,7 +227,7 @@ def run_reference_arm(a):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32-in/f64-acc" if a.dtype == "f32" else "f64-in/f64-acc", "data": "synthetic",
         "config": {"workload": workload_name(a), "halfspaces_per_step": per_step, "samples_per_halfspace": N},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -236,23 +238,216 @@ def run_reference_arm(a):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+KERNEL_SOURCES = ("halfspace_kernel.cuh", "streaming_kernel.cuh", "cluster_kernel.cuh", "cluster_kernel_f64.cuh", "sample_gen.cuh",
+                  "drcvar_abi.cu")
+PARITY_BAR = {"f32": 1e-6, "f64": 1e-9}   # vs the oracle on the same samples: metres (fp32 inputs) / relative (fp64 inputs)
+
+
+def kernel_source_hash():
+    """sha256 over the CUDA sources: profiles/traffic*.json are only trusted when they carry the same stamp."""
+    import hashlib
+    h = hashlib.sha256()
+    base = os.path.join(ROOT, "dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200", "csrc")
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(base, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(n, dtype, halfspaces):
+    """DRAM bytes per launch from the committed ncu capture of THIS kernel build (profiles/traffic*.json), else None."""
+    stamp = kernel_source_hash()
+    for tname in ("traffic.json", "traffic_n100k.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if not os.path.exists(tpath):
+            continue
+        try:
+            tj = json.load(open(tpath))
+        except Exception:
+            continue
+        if tj.get("samples") == n and tj.get("dtype") == dtype:
+            if tj.get("kernel_source_sha16") == stamp:
+                return tj["dram_bytes_per_halfspace"] * halfspaces, f"profiles/{tname} (ncu capture of this build)"
+            return None, f"profiles/{tname} is from another kernel build (stamp {tj.get('kernel_source_sha16')} != {stamp}): not used"
+    return None, "no ncu capture for this size"
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class Ctx:
+    """torch / torch.distributed plumbing shared by the legs."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py (impl ours) needs a CUDA device; there is no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.device)
+        self.stream = torch.cuda.current_stream(self.device)
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.device)
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def timed(self, fn, steps, warmup):
+        """Device time of `steps` calls of fn on the launching stream: barrier + synchronize on both sides, CUDA events,
+        MAX over ranks.  Returns (total ms, mean per-call ms), both max-reduced."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(self.stream)
+        for k in range(steps):
+            ev[k][0].record(self.stream)
+            fn()
+            ev[k][1].record(self.stream)
+        stop.record(self.stream)
+        self.barrier()
+        total = start.elapsed_time(stop)
+        per = statistics.mean(e0.elapsed_time(e1) for e0, e1 in ev)
+        return self.max_over_ranks(total, per)
+
+
+def e2e_leg(cx, pkg, samples_dev, B, N, elem, steps):
+    """End to end through the public API with HOST buffers: H2D + kernel + D2H inside the timed region.  Pinned source
+    buffers (the fast way to call it), pageable ones (what simulation/environment.py:88 hands over), and the plain
+    pinned H2D copy rate measured the same way at the same moment on every rank: the roofline of this leg."""
+    import numpy as np
+    torch = cx.torch
+    host = torch.empty((B, N, 2), dtype=samples_dev.dtype, pin_memory=True)
+    host.copy_(samples_dev[:B])
+    ego_h = np.zeros((B, 2))
+    pinned_np = host.numpy()
+    h2d = B * N * 2 * elem + B * 16
+    d2h = B * (16 + 16 + 24 + 8 + 8 + 8 + 4)
+
+    def wall(fn, reps):
+        for _ in range(2):
+            fn()
+        cx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        dt = time.perf_counter() - t0
+        return cx.max_over_ranks(dt)[0], r
+
+    dt_pin, res = wall(lambda: pkg.compute_halfspaces(pinned_np, ego_h, **RISK), steps)
+    pageable = np.array(pinned_np, copy=True)           # plain malloc'ed numpy array
+    dt_page, res_p = wall(lambda: pkg.compute_halfspaces(pageable, ego_h, **RISK), max(2, steps // 2))
+    assert np.array_equal(res.g, res_p.g)
+    # bare copy: the same bytes, same 64 MB chunking, one stream, nothing else
+    dst = torch.empty_like(samples_dev[:B])
+    chunk = max(1, (64 << 20) // (N * 2 * elem))
+
+    def copy_only():
+        for lo in range(0, B, chunk):
+            dst[lo:lo + chunk].copy_(host[lo:lo + chunk], non_blocking=True)
+        torch.cuda.synchronize(cx.device)
+
+    dt_copy, _ = wall(copy_only, steps)
+    per_rank_peak = B * N * 2 * elem / (dt_copy / steps) / 1e9
+    e2e_gbs = h2d / (dt_pin / steps) / 1e9
+    out = {"value": cx.world * B * steps / dt_pin, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "halfspaces_per_step": B, "steps": steps,
+           "h2d_gbs_per_gpu": e2e_gbs,
+           "h2d_copy_only_gbs_per_gpu": per_rank_peak,
+           "frac_of_copy_only": e2e_gbs / per_rank_peak,
+           "pageable_inputs": {"value": cx.world * B * max(2, steps // 2) / dt_page, "unit": UNIT,
+                               "note": "same call on a pageable numpy array (what simulation/environment.py:88 hands over)"},
+           "note": "compute_halfspaces() on pinned host numpy buffers: chunked H2D + kernel + D2H inside the timed region, every "
+                   "rank at the same time (max over ranks); copy-only = the same bytes with bare pinned cudaMemcpyAsync, measured "
+                   "the same way: the PCIe / host-memory roofline of this leg at this rank count"}
+    return out, res
+
+
+def small_n_leg():
+    """BASELINE configs 1-3 through the drop-in API (rank 0): per-call latency of the reference's timing sweep
+    (evaluation/timing_analysis.py:51-119), one launch per trajectory for head_on / multi_obstacle
+    (simulation/environment.py:60-106), the CPU oracle beside it."""
+    import contextlib
+    import io
+    import numpy as np
+    from oracle import closed_form as cf
+    dropin = os.path.join(ROOT, "dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200", "dropin")
+    sys.path.insert(0, dropin)
+    cwd = os.getcwd()
+    os.chdir(os.environ.get("TMPDIR", "/tmp"))
+    try:
+        from core.halfspaces import CVaRSafeHalfspace, DRCVaRSafeHalfspace, MeanSafeHalfspace
+        from simulation.environment import SafetyFilteringEnvironment
+        published = {10: 2.205, 50: 4.220, 100: 6.947, 500: 31.546, 1000: 69.011, 1500: 148.878}   # DR-CVaR call, BASELINE.md
+        rng = np.random.RandomState(0)
+        sink = io.StringIO()
+        create, oracle_ms = {}, {}
+        for n in (10, 50, 100, 500, 1000, 1500):
+            s = np.array([0.5, 0.0]) + 0.1 * rng.standard_normal((n, 2))
+            ego = np.zeros(2)
+            td, tc, tall, to = [], [], [], []
+            with contextlib.redirect_stdout(sink):
+                for _ in range(120):
+                    t0 = time.perf_counter(); DRCVaRSafeHalfspace.create(s, ego, 0.2, 0.1, 0.15, 0.3, 0.3); t1 = time.perf_counter()
+                    CVaRSafeHalfspace.create(s, ego, 0.2, 0.1, 0.3, 0.3); t2 = time.perf_counter()
+                    MeanSafeHalfspace.create(s, 0.3, 0.3); t3 = time.perf_counter()
+                    td.append(t1 - t0); tc.append(t2 - t1); tall.append(t3 - t0)
+            for _ in range(60):
+                t0 = time.perf_counter(); cf.halfspace(s, ego, 0.2, 0.1, 0.15, 0.3, 0.3); to.append(time.perf_counter() - t0)
+            create[str(n)] = {"dr_cvar_ms": float(np.median(td[20:]) * 1e3), "cvar_ms": float(np.median(tc[20:]) * 1e3),
+                              "all_three_metrics_ms": float(np.median(tall[20:]) * 1e3),
+                              "reference_published_dr_cvar_ms": published[n]}
+            oracle_ms[str(n)] = float(np.median(to[10:]) * 1e3)
+        traj_ms = {}
+        for name in ("head_on_seed42.npz", "multi_obstacle_seed42.npz"):
+            z = np.load(os.path.join(ROOT, "tests", "golden", name))
+            alpha, delta, eps, rr, ro, horizon = (float(v) for v in z["params"])
+            env = SafetyFilteringEnvironment(rr, ro, int(horizon), 0.2, alpha, delta, eps)
+            traj = [z["sample_trajectories"][i] for i in range(z["sample_trajectories"].shape[0])]
+            ts = []
+            with contextlib.redirect_stdout(sink):
+                for _ in range(40):
+                    t0 = time.perf_counter(); env.compute_safe_halfspaces_for_trajectory(traj, z["x_ref"]); ts.append(time.perf_counter() - t0)
+            traj_ms[name.split("_seed")[0]] = {"ms_per_trajectory": float(np.median(ts[10:]) * 1e3),
+                                               "halfspaces_x_metrics": int(z["g_mean"].size) * 3}
+        return {"create_ms": create, "cpu_oracle_all_three_metrics_ms": oracle_ms, "trajectory": traj_ms,
+                "note": "drop-in core.halfspaces.*.create per call (host numpy in, Python objects out; BASELINE configs 1-2) and "
+                        "SafetyFilteringEnvironment.compute_safe_halfspaces_for_trajectory, one launch (configs 1, 3); medians; the "
+                        "CPU oracle evaluates all three metrics of one halfspace"}
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(dropin)
+
+
 def run_ours(a):
     import numpy as np
     import torch
-    import torch.distributed as dist
     import dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 as pkg
     from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib, sharding
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (impl ours) needs a CUDA device; there is no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-
+    cx = Ctx()
+    world, rank, device, stream = cx.world, cx.rank, cx.device, cx.stream
+    dist = cx.dist
+    peak, peak_src = hbm_peak()
     tdtype = torch.float32 if a.dtype == "f32" else torch.float64
     elem = 4 if a.dtype == "f32" else 8
     N = a.samples
@@ -265,79 +460,89 @@ def run_ours(a):
         scn = max(1, int((free - (8 << 30)) // (per_scn * N * 2 * elem)))
         a.scenarios = scn
         B = scn * per_scn
+        need = B * N * 2 * elem
     samples, ego = make_device_batch(B, N, tdtype, device, seed=42 + rank)
     out = None
-    stream = torch.cuda.current_stream(device)
 
     def step():
         nonlocal out
         out = pkg.compute_halfspaces(samples, ego, stream=stream, out=out, **RISK)
 
-    for _ in range(max(a.warmup, 3)):
+    warm = max(a.warmup, 3)
+    for _ in range(warm):
         step()
-    torch.cuda.synchronize(device)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(device)
-
-    sampler = ClockSampler(local_rank)
+    cx.barrier()
+    sampler = ClockSampler(cx.local_rank)
     launches0 = pkg.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
-    start.record(stream)
-    for k in range(a.steps):
-        ev[k][0].record(stream)
-        step()
-        ev[k][1].record(stream)
-    stop.record(stream)
-    torch.cuda.synchronize(device)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(device)
+    total_ms, kern_ms_avg = cx.timed(step, a.steps, 0)
     clocks = sampler.stop()
     launches = pkg.launch_count() - launches0
-    total_ms = start.elapsed_time(stop)
-    kern_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
-    t = torch.tensor([total_ms, statistics.mean(kern_ms)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms_avg = float(t[0]), float(t[1])
     value = world * B * a.steps / (total_ms * 1e-3)
+    kernel_name = ("halfspace_kernel" if N <= pkg.max_samples(np.float32 if a.dtype == "f32" else np.float64)
+                   else ("cluster_kernel_f32" if a.dtype == "f32" and N > 32768 else "streaming_kernel"))
+    alg_bytes = algorithmic_bytes_per_halfspace(N, elem) * B
+    achieved = alg_bytes / (kern_ms_avg * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(N, a.dtype, B)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel_name,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_avg": kern_ms_avg}
 
-    # ---- final gather of the halfspaces (the only exchange; not on the hot path)
+    # ---- strong scaling: BASELINE config 4's scenarios split over the ranks, final gather of (h, g) included
+    strong = None
     gather_ms = 0.0
     if world > 1:
-        torch.cuda.synchronize(device)
-        t0 = time.perf_counter()
-        gh, gg = sharding.gather_results(out.h, out.g, a.scenarios * world, per_scn)
-        torch.cuda.synchronize(device)
-        gather_ms = (time.perf_counter() - t0) * 1e3
-        assert gh.shape[0] == world * B
+        lo_s, hi_s = sharding.shard_of(a.scenarios, world, rank)
+        lo, hi = lo_s * per_scn, hi_s * per_scn
+        sub_s, sub_e = samples[lo:hi], ego[lo:hi]
+        sub_out = None
 
-    # ---- end-to-end through the public API with HOST (pinned) buffers
-    Be = min(a.e2e_halfspaces, B)
-    host = torch.empty((Be, N, 2), dtype=tdtype, pin_memory=True)
-    host.copy_(samples[:Be])
-    ego_h = np.zeros((Be, 2))
-    host_np = host.numpy()
+        def strong_step():
+            nonlocal sub_out
+            sub_out = pkg.compute_halfspaces(sub_s, sub_e, stream=stream, out=sub_out, **RISK)
+
+        s_total, s_per = cx.timed(strong_step, a.steps, 2)
+        cx.barrier()
+        t0 = time.perf_counter()
+        gh, gg = sharding.gather_results(sub_out.h, sub_out.g, a.scenarios, per_scn)
+        torch.cuda.synchronize(device)
+        gather_ms = cx.max_over_ranks((time.perf_counter() - t0) * 1e3)[0]
+        assert gh.shape[0] == B
+        assert torch.equal(gg[lo:hi], out.g[lo:hi])            # the shard's rows of the gathered result == the unsharded launch
+        strong = {"value": B / (s_per * 1e-3), "unit": UNIT, "halfspaces_total": B, "kernel_ms_per_step": s_per,
+                  "gather_ms": gather_ms, "value_incl_gather": B / ((s_per + gather_ms) * 1e-3),
+                  "note": f"config 4 ({a.scenarios} scenarios) split over {world} ranks by sharding.plan_shards; kernel time = max "
+                          "over ranks; gather = all_gather_into_tensor of (h [B,2], g [B,3])"}
+
+    # ---- end to end through the public API with HOST buffers
     e2e_steps = max(3, min(a.steps, 10))
-    for _ in range(2):
-        hres = pkg.compute_halfspaces(host_np, ego_h, **RISK)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        hres = pkg.compute_halfspaces(host_np, ego_h, **RISK)
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * Be * e2e_steps / float(te[0])
-    h2d = Be * N * 2 * elem + Be * 16
-    d2h = Be * (16 + 16 + 24 + 8 + 8 + 8 + 4)
+    e2e, hres = e2e_leg(cx, pkg, samples, min(a.e2e_halfspaces, B), N, elem, e2e_steps)
     torch.cuda.synchronize(device)
-    assert np.array_equal(hres.g, out.g[:Be].cpu().numpy()), "host path and device path disagree"
+    assert np.array_equal(hres.g, out.g[:hres.g.shape[0]].cpu().numpy()), "host path and device path disagree"
+
+    # ---- CPU baseline beside it (rank 0, one GPU only) + parity check of the timed results (every run, rank 0)
+    cpu = None
+    parity = None
+    if rank == 0:
+        nb = min(B, 1024)
+        s_np = samples[:nb].cpu().numpy()
+        e_np = ego[:nb].cpu().numpy()
+        if world == 1 and not a.no_cpu_baseline:
+            v, n_done, dt, res = cpu_baseline_leg(s_np, e_np, a.cpu_seconds)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{n_done} oracle evaluations cycling over the first {nb} halfspaces of the same batch in "
+                             f"{dt:.1f} s, numpy closed-form port of the reference path (1 core)"}
+        else:
+            _CPU_DATA["s"], _CPU_DATA["ego"] = s_np, e_np
+            res = _cpu_chunk((0, 64))
+        g_gpu = out.g[:len(res)].cpu().numpy()
+        ref = np.array(res)
+        err = float(np.max(np.abs(g_gpu - ref) / np.maximum(1.0, np.abs(ref))))
+        parity = {"halfspaces": len(res), "bar": PARITY_BAR[a.dtype], "max_err": err,
+                  "what": "max |g - oracle| / max(1, |oracle|) over (g_mean, g_cvar, g_drcvar) of the timed launch's results"}
+        if not err <= PARITY_BAR[a.dtype]:
+            print(json.dumps({"error": "parity check of the timed results failed", "parity_spot_check": parity}), flush=True)
+            raise SystemExit(3)
 
     # ---- generate mode: the same batch with the samples drawn inside the kernel — no sample bytes
     #      in HBM or over PCIe; compute-bound (Philox + Box-Muller), reported beside the headline, not instead of it
@@ -358,126 +563,132 @@ def run_ours(a):
                 mean_t.data_ptr(), chol_t.data_ptr(), 42, rank * B, B, N, ego.data_ptr(), None,
                 RISK["alpha"], RISK["delta"], RISK["epsilon"], RISK["robot_radius"], RISK["obstacle_radius"], 0,
                 gout.h.data_ptr(), gout.h_mean.data_ptr(), gout.g.data_ptr(), None, None, None,
-                gout.status.data_ptr(), None, None, local_rank, C.c_void_p(stream.cuda_stream))
+                gout.status.data_ptr(), None, None, cx.local_rank, C.c_void_p(stream.cuda_stream))
             _lib.check(rc)
 
-        gen_step()
-        torch.cuda.synchronize(device)
-        g_steps = 3
-        gs, ge = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        gs.record(stream)
-        for _ in range(g_steps):
-            gen_step()
-        ge.record(stream)
-        torch.cuda.synchronize(device)
-        g_ms = gs.elapsed_time(ge) / g_steps
+        _g_total, g_ms = cx.timed(gen_step, 3, 1)
         # end to end from HOST inputs (nominal positions, covariance, ego: 56 B per halfspace) to HOST outputs
         Bg = min(B, 65536)
         mean_h, ego_g = mean_t[:Bg].cpu().numpy(), np.zeros((Bg, 2))
         cov_h = np.diag([0.01, 0.01])
         pkg.compute_halfspaces_generated(mean_h, cov_h, N, 42, ego=ego_g, **RISK)
+        cx.barrier()
         t0 = time.perf_counter()
         for _ in range(3):
             gres = pkg.compute_halfspaces_generated(mean_h, cov_h, N, 42, ego=ego_g, **RISK)
-        g_e2e = 3 * Bg / (time.perf_counter() - t0)
+        g_dt = cx.max_over_ranks(time.perf_counter() - t0)[0]
         generated = {"value": world * B / (g_ms * 1e-3), "unit": UNIT, "ms_per_launch": g_ms,
                      "samples_per_s": world * B * N / (g_ms * 1e-3),
-                     "e2e": {"value": world * g_e2e, "unit": UNIT, "halfspaces_per_step": Bg,
+                     "e2e": {"value": world * 3 * Bg / g_dt, "unit": UNIT, "halfspaces_per_step": Bg,
                              "h2d_bytes_per_step": Bg * 56, "d2h_bytes_per_step": Bg * 84},
                      "fallback_halfspaces": int((gres.status & 2 != 0).sum()),
-                     "note": "samples drawn in-kernel (Philox4x32-10 + fp32 Box-Muller, oracle/sample_gen.py); "
-                             "per-rank numbers scaled by world size"}
+                     "note": "samples drawn in-kernel (Philox4x32-10 + fp32 Box-Muller, oracle/sample_gen.py); every rank timed, "
+                             "max over ranks"}
+        del mean_t, chol_t, gout
 
-    # ---- BASELINE config 5 sample count (N = 100 000) on a shard that fits next to the headline batch: the cluster /
-    #      DSMEM kernel (one cluster of 4 CTAs per halfspace, every sample read once) beside the two-pass streaming kernel
-    large_n = None
+    status_fallback = int((out.status != 0).sum().item())
+    small_n = None
+    if rank == 0 and not a.no_small_n:
+        small_n = small_n_leg()
+
+    # ---- the legs below need the memory of the headline batch
+    del samples, ego, out
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE config 5 (N = 100 000; 65 536 scenarios x 8 x 20 = 10 485 760 halfspaces = 8.4 TB, never resident): one
+    #      resident chunk per GPU through the cluster / DSMEM kernel (every sample read once), every rank timed, max over
+    #      ranks; the two-pass streaming kernel on the same chunk beside it
+    config5 = None
     if a.dtype == "f32" and not a.no_large_n and N <= 32768:
-        NL, BL = 100000, a.large_n_halfspaces
+        NL = 100000
         free, _t = torch.cuda.mem_get_info(device)
-        BL = int(max(0, min(BL, (free - (6 << 30)) // (NL * 8))))
+        BL = int(max(0, min(a.large_n_halfspaces, (free - (8 << 30)) // (NL * 8))))
         if BL >= 1024:
             sl, egl = make_device_batch(BL, NL, torch.float32, device, seed=777 + rank, chunk=256)
             bytes_l = algorithmic_bytes_per_halfspace(NL, 4) * BL
-            large_n = {"samples_per_halfspace": NL, "halfspaces_per_gpu": BL, "unit": UNIT}
+            total_hs = 65536 * 8 * 20
+            config5 = {"samples_per_halfspace": NL, "halfspaces_per_gpu_chunk": BL, "unit": UNIT,
+                       "chunk_bytes_per_gpu": BL * NL * 8, "config5_halfspaces_total": total_hs}
+            keep = None
             for name, fl in (("cluster_kernel", 0), ("streaming_kernel", _lib.FLAG_NO_CLUSTER)):
                 lo = None
-                for _ in range(2):
+
+                def l_step():
+                    nonlocal lo
                     lo = pkg.compute_halfspaces(sl, egl, stream=stream, out=lo, flags=fl, **RISK)
-                torch.cuda.synchronize(device)
-                ls, le = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ls.record(stream)
-                for _ in range(3):
-                    lo = pkg.compute_halfspaces(sl, egl, stream=stream, out=lo, flags=fl, **RISK)
-                le.record(stream)
-                torch.cuda.synchronize(device)
-                l_ms = ls.elapsed_time(le) / 3
-                large_n[name] = {"value": world * BL / (l_ms * 1e-3), "ms_per_launch": l_ms,
-                                 "hbm_gbs": bytes_l / (l_ms * 1e-3) / 1e9,
+
+                _lt, l_ms = cx.timed(l_step, 3, 2)
+                gbs = bytes_l / (l_ms * 1e-3) / 1e9
+                config5[name] = {"value": world * BL / (l_ms * 1e-3), "ms_per_launch": l_ms, "hbm_gbs_per_gpu": gbs,
+                                 "roofline_frac": gbs / peak,
                                  "general_path_halfspaces": int((lo.status & 2 != 0).sum().item())}
                 if name == "cluster_kernel":
                     keep = (lo.h.clone(), lo.var.clone())
+                    config5["projected_s_for_config5"] = total_hs / (world * BL / (l_ms * 1e-3))
                 else:
-                    large_n["bit_identical_h_and_T"] = bool(torch.equal(keep[0], lo.h) and torch.equal(keep[1], lo.var))
-            del sl, egl
+                    config5["bit_identical_h_and_T"] = bool(torch.equal(keep[0], lo.h) and torch.equal(keep[1], lo.var))
+            config5["note"] = ("one resident chunk per GPU of BASELINE config 5's scenario-sharded batch; kernel time = max over "
+                               "ranks; projected_s = config-5 total / measured rate (chunks stream through the same buffers)")
+            del sl, egl, lo, keep
+            torch.cuda.empty_cache()
 
-    # ---- roofline of the (single) kernel
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak = float(json.load(open(peaks_path))["hbm_gbs"])
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    alg_bytes = algorithmic_bytes_per_halfspace(N, elem) * B
-    achieved = alg_bytes / (kern_ms_avg * 1e-3) / 1e9
-    traffic = None
-    for tname in ("traffic.json", "traffic_n100k.json"):   # DRAM bytes per halfspace from the committed ncu captures
-        tpath = os.path.join(ROOT, "profiles", tname)
-        if os.path.exists(tpath):
-            try:
-                tj = json.load(open(tpath))
-                if tj.get("samples") == N and tj.get("dtype") == a.dtype:
-                    traffic = tj["dram_bytes_per_halfspace"] * B
-            except Exception:
-                pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "kernel": "halfspace_kernel" if N <= pkg.max_samples(np.float32 if a.dtype == "f32" else np.float64)
-                else ("cluster_kernel_f32" if a.dtype == "f32" and N > 32768 else "streaming_kernel"),
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_avg": kern_ms_avg}
+    # ---- fp64 samples (the reference's own dtype, 1e-9 bar): the same config-4 batch when it fits (105 GB), else the
+    #      largest resident one
+    f64_inputs = None
+    if a.dtype == "f32" and not a.no_f64 and N <= pkg.max_samples(np.float64):
+        free, _t = torch.cuda.mem_get_info(device)
+        scn64 = int(min(a.scenarios, (free - (10 << 30)) // (per_scn * N * 16)))
+        if scn64 >= 8:
+            B64 = scn64 * per_scn
+            s64, e64 = make_device_batch(B64, N, torch.float64, device, seed=42 + rank)
+            o64 = None
 
-    # ---- CPU baseline beside it (rank 0, N = 1 GPU only) + parity spot-check of the timed results
-    cpu = None
-    parity = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        nb = min(B, 1024)
-        s_np = samples[:nb].cpu().numpy()
-        e_np = ego[:nb].cpu().numpy()
-        v, n_done, dt, res = cpu_baseline_leg(s_np, e_np, a.cpu_seconds)
-        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{n_done} oracle evaluations cycling over the first {nb} halfspaces of the same batch in "
-                         f"{dt:.1f} s, numpy closed-form port of the reference path (1 core)"}
-        g_gpu = out.g[:len(res)].cpu().numpy()
-        ref = np.array(res)
-        parity = {"halfspaces": len(res), "tolerance": "1e-6 m (fp32 inputs) / 1e-9 rel (fp64 inputs)",
-                  "max_rel_err": float(np.max(np.abs(g_gpu - ref) / np.maximum(1.0, np.abs(ref))))}
+            def step64():
+                nonlocal o64
+                o64 = pkg.compute_halfspaces(s64, e64, stream=stream, out=o64, **RISK)
+
+            t64, per64 = cx.timed(step64, max(3, a.steps // 4), 2)
+            bytes64 = algorithmic_bytes_per_halfspace(N, 8) * B64
+            gbs64 = bytes64 / (per64 * 1e-3) / 1e9
+            e2e64, hres64 = e2e_leg(cx, pkg, s64, min(a.e2e_halfspaces // 2, B64), N, 8, 3)
+            par64 = None
+            if rank == 0:
+                _CPU_DATA["s"], _CPU_DATA["ego"] = s64[:32].cpu().numpy(), e64[:32].cpu().numpy()
+                ref = np.array(_cpu_chunk((0, 32)))
+                err = float(np.max(np.abs(o64.g[:32].cpu().numpy() - ref) / np.maximum(1.0, np.abs(ref))))
+                par64 = {"halfspaces": 32, "bar": PARITY_BAR["f64"], "max_err": err}
+                if not err <= PARITY_BAR["f64"]:
+                    print(json.dumps({"error": "parity check of the fp64 leg failed", "parity_spot_check": par64}), flush=True)
+                    raise SystemExit(3)
+            f64_inputs = {"value": world * B64 / (per64 * 1e-3), "unit": UNIT, "halfspaces_per_gpu": B64, "ms_per_step": per64,
+                          "dtype": "f64-in/f64-acc",
+                          "roofline": {"bound": "hbm", "achieved": gbs64, "peak": peak, "unit": "GB/s", "frac": gbs64 / peak,
+                                       "kernel": "halfspace_kernel<double>", "algorithmic_bytes_per_launch": bytes64,
+                                       "traffic": None},
+                          "e2e": e2e64, "parity_spot_check": par64,
+                          "note": ("the full config-4 batch in fp64" if scn64 == a.scenarios else
+                                   f"largest resident fp64 batch ({scn64} of {a.scenarios} scenarios)") +
+                                  "; every sample read once, exact canonical fp64 loss of every sample (no fp32 screening)"}
+            del s64, e64, o64
+            torch.cuda.empty_cache()
 
     if rank == 0:
         line = {
             "metric": METRIC if N == 10000 else f"DR-CVaR halfspaces/sec at N={N} samples", "value": value, "unit": UNIT,
-            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "n_gpus": world, "steps": a.steps, "warmup": warm,
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f32-in/f64-acc" if a.dtype == "f32" else "f64-in/f64-acc", "data": "synthetic",
             "config": {"workload": workload_name(a), "halfspaces_per_gpu": B, "samples_per_halfspace": N,
                        "input_dtype": a.dtype, "parallelism": f"scenario-shard x{world} (no collective on the hot path)",
-                       "l2": f"inputs ({need / 1e9:.1f} GB per GPU) are larger than L2; no flush needed"},
-            "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "halfspaces_per_step": Be, "steps": e2e_steps,
-                    "note": "compute_halfspaces() on pinned host numpy buffers: chunked H2D + kernel + D2H inside the timed region"},
+                       "l2": f"inputs ({need / 1e9:.1f} GB per GPU) are larger than L2; no flush needed",
+                       "precision": "fp32 samples: fp32 screening with rigorous bounds, exact fp64 threshold / window losses, fp32 "
+                                    "partial sums of the surely-above set (1e-5 m north-star bar); fp64 samples: see f64_inputs"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks, "hbm_gbs_aggregate": achieved * world, "generated": generated,
-            "large_n": None if large_n is None else dict(large_n, hbm_peak_gbs=peak, note="per-rank shard, scaled by world size"),
+            "config5": None if config5 is None else dict(config5, hbm_peak_gbs=peak),
+            "f64_inputs": f64_inputs, "strong_scaling": strong, "small_n": small_n,
             "gather_ms": gather_ms, "parity_spot_check": parity,
-            "status_fallback_halfspaces": int((out.status != 0).sum().item()),
+            "status_fallback_halfspaces": status_fallback, "kernel_source_sha16": kernel_source_hash(),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
