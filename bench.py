@@ -502,6 +502,7 @@ def run_ours(a):
             sub_out = pkg.compute_halfspaces(sub_s, sub_e, stream=stream, out=sub_out, **RISK)
 
         s_total, s_per = cx.timed(strong_step, a.steps, 2)
+        sharding.gather_results(sub_out.h, sub_out.g, a.scenarios, per_scn)    # (first collective of the run: NCCL connects here)
         cx.barrier()
         t0 = time.perf_counter()
         gh, gg = sharding.gather_results(sub_out.h, sub_out.g, a.scenarios, per_scn)

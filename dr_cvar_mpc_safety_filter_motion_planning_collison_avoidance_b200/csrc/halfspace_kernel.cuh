@@ -54,6 +54,8 @@ constexpr int kSweepThreads = kSweepWarps * 32;      // 256
 constexpr int kThreads = kSweepThreads + 64;         // + finisher warp + director warp
 constexpr int kFinisherWarp = kSweepWarps;
 constexpr int kDirectorWarp = kSweepWarps + 1;
+// (a second finisher warp — one per parity buffer — was measured: the single finisher is busy 99 % of the time since its loops
+//  are rolled, but 11 warps leave 80 registers per thread and the step got 2.5 % slower: profiles/r2_ab_two_finishers.txt)
 constexpr int kSlots = 512;                          // canonical cross-lane tree width (2 slots per sweep thread)
 constexpr int kWarpCand = 128;                       // doubles per sweep warp in the candidate buffer ...
 constexpr int kCandCap = 96;                         // ... of which candidate losses; the last 32 hold per-lane (sum dx, sum dy)
