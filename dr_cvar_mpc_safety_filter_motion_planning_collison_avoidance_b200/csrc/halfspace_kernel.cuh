@@ -130,6 +130,7 @@ struct Ctl {                        // one per parity buffer
   unsigned long long key_lo;       // key(t_lo): histogram origin
   double T;
   double h0, h1, t_lo, t_hi, m0, m1;
+  double hn;                       // ||h|| (canonical), written by the director with h
   double f0, f1;                   // first sample (fp32 path: shift origin)
   float h0f, h1f, thr_above, thr_keep;
   int hist_shift;
@@ -334,33 +335,55 @@ __device__ __forceinline__ float warp_sum_any4(float a, float b, float c, float 
   return v;
 }
 
-// Histogram scan by ONE warp: finds the bucket (from the top) that holds rank r (1-based).
+// Histogram scan by ONE warp: finds the bucket (from the top) that holds rank r (1-based).  Lane l takes the eight buckets
+// 255-8l .. 248-8l (two 16-byte loads), ONE inclusive scan over the 32 lane totals locates the lane, the lane walks its
+// eight counts.  (The earlier form — eight dependent rounds of load + warp reduction — was ~900 cycles of the finisher's
+// serial chain.)
 __device__ __forceinline__ void scan_hist_warp(const unsigned* hist, int r, int lane, int& bstar, int& rprime, int& cnt_in) {
-  int run = 0, row = -1, r_row = 0;
-#pragma unroll 1
-  for (int i = 0; i < kHistBuckets / 32; ++i) {
-    const int tot = __reduce_add_sync(kFull, static_cast<int>(hist[kHistBuckets - 1 - (32 * i + lane)]));
-    if (row < 0 && run + tot >= r) {
-      row = i;
-      r_row = r - run;
-    }
-    run += tot;
-  }
-  if (row < 0) { row = kHistBuckets / 32 - 1; r_row = 1; }  // unreachable when r <= #candidates in range
-  const int bucket = kHistBuckets - 1 - (32 * row + lane);
-  const int c = static_cast<int>(hist[bucket]);
-  int incl = c;
+  static_assert(kHistBuckets == 256, "lane l owns buckets 255-8l .. 248-8l");
+  const uint4* h4 = reinterpret_cast<const uint4*>(hist);
+  const uint4 lo = h4[62 - 2 * lane], hi = h4[63 - 2 * lane];   // hist[248-8l .. 251-8l], hist[252-8l .. 255-8l]
+  const int c[8] = {static_cast<int>(hi.w), static_cast<int>(hi.z), static_cast<int>(hi.y), static_cast<int>(hi.x),
+                    static_cast<int>(lo.w), static_cast<int>(lo.z), static_cast<int>(lo.y), static_cast<int>(lo.x)};   // from the top
+  const int tot = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+  int incl = tot;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const int t = __shfl_up_sync(kFull, incl, d);
     if (lane >= d) incl += t;
   }
-  const int excl = incl - c;
-  const unsigned hit = __ballot_sync(kFull, excl < r_row && r_row <= incl);
-  const int src = __ffs(hit) - 1;
-  bstar = __shfl_sync(kFull, bucket, src);
-  rprime = __shfl_sync(kFull, r_row - excl, src);
-  cnt_in = __shfl_sync(kFull, c, src);
+  const int excl = incl - tot;
+  const unsigned hit = __ballot_sync(kFull, excl < r && r <= incl);
+  int bk = 0, rp = 1, ci = c[7];   // (no lane holds the rank: unreachable when r <= #candidates in range)
+  int run = excl;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (run < r && r <= run + c[i]) {
+      bk = kHistBuckets - 1 - (8 * lane + i);
+      rp = r - run;
+      ci = c[i];
+    }
+    run += c[i];
+  }
+  const int src = hit ? __ffs(hit) - 1 : 31;
+  bstar = __shfl_sync(kFull, bk, src);
+  rprime = __shfl_sync(kFull, rp, src);
+  cnt_in = __shfl_sync(kFull, ci, src);
+}
+
+// Four (non-canonical) fp64 warp sums at once (transposed butterfly, 9 shuffles instead of 20): returns (a, b, c, d) totals
+// in every lane.
+__device__ __forceinline__ void warp_sum_any4d(double& a, double& b, double& c, double& d, int lane) {
+  const bool b0 = lane & 1, b1 = lane & 2;
+  const double k0 = (b0 ? c : a) + shfl_xor_d(b0 ? a : c, 1);   // even lanes: a, odd lanes: c   (pairs)
+  const double k1 = (b0 ? d : b) + shfl_xor_d(b0 ? b : d, 1);   // even lanes: b, odd lanes: d
+  double v = (b1 ? k1 : k0) + shfl_xor_d(b1 ? k0 : k1, 2);      // lane & 3 = 0: a, 1: c, 2: b, 3: d   (quads)
+#pragma unroll
+  for (int m = 4; m <= 16; m <<= 1) v += shfl_xor_d(v, m);
+  a = __shfl_sync(kFull, v, 0);
+  c = __shfl_sync(kFull, v, 1);
+  b = __shfl_sync(kFull, v, 2);
+  d = __shfl_sync(kFull, v, 3);
 }
 
 // Exact r-th largest (1-based) among the enumerated losses whose keys lie in [lo, hi] — generic narrowing loop.
@@ -446,10 +469,10 @@ __device__ __forceinline__ void write_mean_outputs(const KernelArgs& a, long lon
 }
 
 // CVaR / DR-CVaR offsets of one halfspace from (h, CVaR ingredients); one thread.      core/risk_metrics.py:84-338
+// hn = ||h|| by the canonical chain (norm2_canon(h0, h1)): the resident kernel's director warp has it ready in ctl->hn.
 __device__ __forceinline__ void write_risk_outputs(const KernelArgs& a, long long b, const Ctl* ctl, bool nonfinite,
-                                                   double s_tot, int c_tot, double T_thr, int status) {
+                                                   double s_tot, int c_tot, double T_thr, int status, double hn) {
   const double h0 = ctl->h0, h1 = ctl->h1;
-  const double hn = norm2_canon(h0, h1);
   const double r = __dmul_rn(a.R, hn);
   double cvar, g_cvar, g_star, g_dr, var_t;
   if (nonfinite) {
@@ -475,6 +498,10 @@ __device__ __forceinline__ void write_risk_outputs(const KernelArgs& a, long lon
   if (a.var_out) a.var_out[b] = var_t;
   if (a.gstar_out) a.gstar_out[b] = g_star;
   if (a.status_out) a.status_out[b] = status;
+}
+__device__ __forceinline__ void write_risk_outputs(const KernelArgs& a, long long b, const Ctl* ctl, bool nonfinite,
+                                                   double s_tot, int c_tot, double T_thr, int status) {
+  write_risk_outputs(a, b, ctl, nonfinite, s_tot, c_tot, T_thr, status, norm2_canon(ctl->h0, ctl->h1));
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -606,7 +633,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           if (lane < cnt_in) small[rank] = mineL;
           __syncwarp();
           const bool mineAbove = lane < cnt_in && lane < r - 1 && key_of(small[lane]) > key_of(T_thr);
-          s4 = warp_sum_any(mineAbove ? small[lane] : 0.0);
+          s4 = mineAbove ? small[lane] : 0.0;   // (lane partial: reduced with the other sums below)
           c4 = __popc(__ballot_sync(kFull, mineAbove));
         } else {
           // dense / heavily tied bucket: narrow further inside the finisher warp
@@ -629,33 +656,38 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
             }
           });
           c4 = __reduce_add_sync(kFull, c4);
-          s4 = warp_sum_any(s4);
         }
         const int c3t = __reduce_add_sync(kFull, c3);
-        const double s3t = warp_sum_any(s3);
         double lx = 0.0, ly = 0.0;   // "surely above" coordinate sums: lane partials of the 8 sweep warps, fixed order
         if constexpr (kF32) {
+          double lx2 = 0.0, ly2 = 0.0;   // (two chains: half the latency of the rolled loop)
 #pragma unroll 1
-          for (int w = 0; w < kSweepWarps; ++w) {
+          for (int w = 0; w < kSweepWarps; w += 2) {
             const float2 p = reinterpret_cast<const float2*>(cand + w * kWarpCand + kCandCap)[lane];
+            const float2 q = reinterpret_cast<const float2*>(cand + (w + 1) * kWarpCand + kCandCap)[lane];
             lx += static_cast<double>(p.x);
             ly += static_cast<double>(p.y);
+            lx2 += static_cast<double>(q.x);
+            ly2 += static_cast<double>(q.y);
           }
+          lx += lx2;
+          ly += ly2;
         }
-        const double s_x = warp_sum_any(lx), s_y = warp_sum_any(ly);
+        double s3t = s3, s_x = lx, s_y = ly;
+        warp_sum_any4d(s3t, s4, s_x, s_y, lane);   // the four sums of the result in one transposed butterfly
         if (lane == 0) {
-          double s_e = 0.0, n_lin = 0.0;
+          double s_e = 0.0, n_lin = static_cast<double>(cnt_hi);   // fp32 inputs: every "above" sample is in the linear sums
+          if constexpr (!kF32) {
+            n_lin = 0.0;
 #pragma unroll 1
-          for (int w = 0; w < kSweepWarps; ++w) {
-            s_e += fin[w * 4 + 2];
-            n_lin += fin[w * 4 + 3];
+            for (int w = 0; w < kSweepWarps; ++w) s_e += fin[w * 4 + 2];
           }
           // loss sum of the "surely above" set by linearity (fp32 inputs), xi_i = f + d_i:
           //   sum_i -(h.xi_i) = -(h0 (n f0 + sum dx) + h1 (n f1 + sum dy))
           const double s_lin = -(ctl->h0 * (n_lin * ctl->f0 + s_x) + ctl->h1 * (n_lin * ctl->f1 + s_y));
           const double s_tot = ((s_e + s_lin) + s3t) + s4;
           const int c_tot = cnt_hi + c3t + c4;
-          write_risk_outputs(a, b, ctl, false, s_tot, c_tot, T_thr, ctl->status);
+          write_risk_outputs(a, b, ctl, false, s_tot, c_tot, T_thr, ctl->status, ctl->hn);
           {   // learn where the threshold sits in z units: (T - mean loss) / sigma = (pm + T + c) / sigma
             ctl->z_missrun = 0;
             if (ctl->z_learned) {
@@ -735,8 +767,10 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         }
       }
       nonfinite |= !(isfinite(h0) && isfinite(h1));
+      const double hn = norm2_canon(h0, h1);   // ||h|| for the offsets (the team needs h only after sweep B: time to spare)
       if (lane == 0) {
         ctl->h0 = h0; ctl->h1 = h1; ctl->m0 = m0; ctl->m1 = m1;
+        ctl->hn = hn;
         ctl->nonfinite = nonfinite;
         ctl->degenerate = degenerate;
       }
