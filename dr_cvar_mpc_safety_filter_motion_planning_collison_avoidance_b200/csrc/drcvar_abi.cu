@@ -381,9 +381,13 @@ struct HostCtx {
   size_t d_io_cap[2] = {0, 0};
   void* h_out_stage[2] = {nullptr, nullptr};    // pinned: the whole output block of a chunk comes back in ONE copy
   size_t h_out_cap[2] = {0, 0};
+  unsigned char* h_small = nullptr;   // pinned: inputs | outputs of a small call, one copy each way
+  unsigned char* d_small = nullptr;
+  size_t small_cap = 0;
   double last_stage_ms = 0, last_kernel_ms = 0;
   long long last_h2d = 0, last_d2h = 0;
 };
+constexpr size_t kSmallCallBytes = static_cast<size_t>(1) << 20;   // host calls up to this many input bytes take run_host_small
 // One context per device: a process that drives several GPUs through DRCVAR_HOST (cudaSetDevice between calls, or one
 // thread per GPU) keeps every device's streams, events and staging buffers; nothing is torn down on a device switch and
 // calls on different devices do not serialise on each other.
@@ -433,6 +437,84 @@ int grow_pinned(void** p, size_t* cap, size_t need) {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Small host calls (the reference's own use: one halfspace per call, evaluation/timing_analysis.py:74,101, or one
+// trajectory, simulation/environment.py:60-106): everything the kernel reads is packed into ONE pinned block and goes over
+// in one copy, everything it writes comes back in one copy, one stream synchronisation, no events — the call is pure
+// latency, and every CUDA API call in it costs more than the arithmetic.
+template <typename T>
+int run_host_small(const Call& c, HostCtx& hc, long long kc) {
+  const size_t dbl = sizeof(double);
+  const size_t nb = static_cast<size_t>(c.B);
+  const size_t row_pitch = align_up(static_cast<size_t>(c.N) * 2 * sizeof(T), 16);
+  const size_t off_s = 0, off_ego = off_s + nb * row_pitch, off_hin = off_ego + nb * 2 * dbl, in_bytes = off_hin + nb * 2 * dbl;
+  const size_t off_h = align_up(in_bytes, 16), off_hm = off_h + nb * 2 * dbl, off_g = off_hm + nb * 2 * dbl,
+               off_cvar = off_g + nb * 3 * dbl, off_var = off_cvar + nb * dbl, off_gs = off_var + nb * dbl,
+               off_st = off_gs + nb * dbl, off_tail = align_up(off_st + nb * sizeof(int32_t), 16),
+               total = off_tail + (c.tail_idx_out ? nb * static_cast<size_t>(kc) * sizeof(int32_t) : 0);
+  if (hc.small_cap < total) {
+    if (hc.h_small) cudaFreeHost(hc.h_small);
+    if (hc.d_small) cudaFree(hc.d_small);
+    hc.h_small = hc.d_small = nullptr;
+    hc.small_cap = 0;
+    const size_t want = std::max(total, static_cast<size_t>(1) << 18);
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&hc.h_small), want));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&hc.d_small), want));
+    hc.small_cap = want;
+  }
+  unsigned char* hb = hc.h_small;
+  unsigned char* db = hc.d_small;
+  const bool rows_contig = (c.stride_c == 1 && c.stride_n == 2);
+  for (size_t b = 0; b < nb; ++b) {   // (strided views, e.g. traj[:, t, :] of simulation/environment.py:88, are packed here)
+    T* row = reinterpret_cast<T*>(hb + off_s + b * row_pitch);
+    const T* sb = reinterpret_cast<const T*>(c.samples) + static_cast<long long>(b) * c.stride_b;
+    if (rows_contig) {
+      std::memcpy(row, sb, static_cast<size_t>(c.N) * 2 * sizeof(T));
+    } else {
+      for (long long i = 0; i < c.N; ++i) {
+        row[2 * i] = sb[i * c.stride_n];
+        row[2 * i + 1] = sb[i * c.stride_n + c.stride_c];
+      }
+    }
+  }
+  if (c.ego) std::memcpy(hb + off_ego, c.ego, nb * 2 * dbl);
+  if (c.h_in) std::memcpy(hb + off_hin, c.h_in, nb * 2 * dbl);
+  cudaStream_t st = hc.streams[0];
+  CUDA_TRY(cudaMemcpyAsync(db, hb, in_bytes, cudaMemcpyHostToDevice, st));
+  Call d = c;
+  d.samples = db + off_s;
+  d.stride_b = static_cast<long long>(row_pitch / sizeof(T));
+  d.stride_n = 2;
+  d.stride_c = 1;
+  d.ego = c.ego ? reinterpret_cast<const double*>(db + off_ego) : nullptr;
+  d.h_in = c.h_in ? reinterpret_cast<const double*>(db + off_hin) : nullptr;
+  d.h_out = reinterpret_cast<double*>(db + off_h);
+  d.h_mean_out = reinterpret_cast<double*>(db + off_hm);
+  d.g_out = reinterpret_cast<double*>(db + off_g);
+  d.cvar_out = reinterpret_cast<double*>(db + off_cvar);
+  d.var_out = reinterpret_cast<double*>(db + off_var);
+  d.gstar_out = reinterpret_cast<double*>(db + off_gs);
+  d.status_out = reinterpret_cast<int32_t*>(db + off_st);
+  d.tail_idx_out = c.tail_idx_out ? reinterpret_cast<int32_t*>(db + off_tail) : nullptr;
+  const int rc = launch_on_device<T>(d, hc.device, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(hb + off_h, db + off_h, total - off_h, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  hc.last_h2d = static_cast<long long>(in_bytes);
+  hc.last_d2h = static_cast<long long>(total - off_h);
+  auto put = [&](void* host, size_t off, size_t bytes) {
+    if (host) std::memcpy(host, hb + off, bytes);
+  };
+  put(c.h_out, off_h, nb * 2 * dbl);
+  put(c.h_mean_out, off_hm, nb * 2 * dbl);
+  put(c.g_out, off_g, nb * 3 * dbl);
+  put(c.cvar_out, off_cvar, nb * dbl);
+  put(c.var_out, off_var, nb * dbl);
+  put(c.gstar_out, off_gs, nb * dbl);
+  put(c.status_out, off_st, nb * sizeof(int32_t));
+  put(c.tail_idx_out, off_tail, nb * static_cast<size_t>(kc) * sizeof(int32_t));
+  return DRCVAR_OK;
+}
+
 template <typename T>
 int run_host(const Call& c) {
   HostCtx* hcp = nullptr;
@@ -448,6 +530,9 @@ int run_host(const Call& c) {
   hc.last_stage_ms = hc.last_kernel_ms = 0;
   hc.last_h2d = hc.last_d2h = 0;
   if (c.B == 0) return DRCVAR_OK;
+  if (static_cast<size_t>(c.B) * static_cast<size_t>(c.N) * 2 * sizeof(T) <= kSmallCallBytes &&
+      (!c.tail_idx_out || static_cast<size_t>(c.B) * static_cast<size_t>(kc) * 4 <= kSmallCallBytes))
+    return run_host_small<T>(c, hc, kc);
 
   const size_t row_bytes = static_cast<size_t>(c.N) * 2 * sizeof(T);
   const size_t row_pitch = align_up(row_bytes, 16);  // device rows are 16-B aligned so the bulk loader applies

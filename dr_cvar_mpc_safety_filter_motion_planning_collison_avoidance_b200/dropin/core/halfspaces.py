@@ -6,7 +6,6 @@ of each halfspace is the one the kernel derived from the canonical sample mean, 
 
 compute_safe_halfspaces() evaluates all obstacles and all three metrics in ONE launch.
 """
-import json
 import time
 
 import numpy as np
@@ -44,14 +43,6 @@ class SafeHalfspace:
 
 def _zero_info():
     return {'setup_time': 0, 'solve_time': 0, 'solve_call_time': 0}
-
-
-def _read_info(key):
-    try:
-        with open(f'tmp/timing_info_{key}.json', 'r') as f:
-            return json.load(f)
-    except Exception:
-        return None
 
 
 def _evaluate(samples_list, ego_ref_pos, alpha, delta, epsilon, robot_radius, obstacle_radius):
@@ -93,11 +84,11 @@ class CVaRSafeHalfspace(SafeHalfspace):
             g_value = float(res.g[0, 1])
             if _rm.cvar_optimizer is None or _rm.cvar_optimizer.n_samples != len(samples):
                 _rm.cvar_optimizer = _rm.CVaROptimizer(alpha, delta, len(samples))
-            _rm.save_timing_info('cvar', 0.0, time.time() - t0)
+            solve_time = time.time() - t0
+            _rm.save_timing_info('cvar', 0.0, solve_time)
         halfspace = CVaRSafeHalfspace(np.array(res.h[0]), g_value)
-        info = _read_info('cvar')
-        if info is not None:
-            halfspace.info = info
+        # what the reference reads back from tmp/timing_info_cvar.json (core/halfspaces.py:142-147): the values just written
+        halfspace.info = {'setup_time': 0.0, 'solve_time': solve_time}
         return halfspace
 
 
@@ -114,11 +105,11 @@ class DRCVaRSafeHalfspace(SafeHalfspace):
             g_tilde = float(res.g[0, 2])
             if _rm.drcvar_optimizer is None or _rm.drcvar_optimizer.n_samples != len(samples):
                 _rm.drcvar_optimizer = _rm.DRCVaROptimizer(alpha, epsilon, delta, len(samples))
-            _rm.save_timing_info('drcvar', 0.0, time.time() - t0)
+            solve_time = time.time() - t0
+            _rm.save_timing_info('drcvar', 0.0, solve_time)
         halfspace = DRCVaRSafeHalfspace(np.array(res.h[0]), g_tilde)
-        info = _read_info('drcvar')
-        if info is not None:
-            halfspace.info = info
+        # what the reference reads back from tmp/timing_info_drcvar.json (core/halfspaces.py:187-192): the values just written
+        halfspace.info = {'setup_time': 0.0, 'solve_time': solve_time}
         return halfspace
 
 

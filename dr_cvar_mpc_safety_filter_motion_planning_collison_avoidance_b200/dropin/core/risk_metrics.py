@@ -32,11 +32,21 @@ cvar_optimizer = None
 SENTINEL = 100.0
 
 
+_timing_files = {}   # (cwd, key) -> open file: the side channel is rewritten in place, not re-created, on every call
+
+
 def save_timing_info(key, setup_time, solve_time):
-    """Write tmp/timing_info_<key>.json (seconds) and print the DEBUG line the reference prints."""
-    os.makedirs('tmp', exist_ok=True)
-    with open(f'tmp/timing_info_{key}.json', 'w') as f:
-        json.dump({'setup_time': setup_time, 'solve_time': solve_time}, f)
+    """Write tmp/timing_info_<key>.json (seconds) and print the DEBUG line the reference prints
+    (reference core/risk_metrics.py:16-33: same file, same keys, same line)."""
+    where = (os.getcwd(), key)
+    f = _timing_files.get(where)
+    if f is None or f.closed or not os.path.exists(f.name):
+        os.makedirs('tmp', exist_ok=True)
+        f = _timing_files[where] = open(os.path.abspath(f'tmp/timing_info_{key}.json'), 'w')
+    f.seek(0)
+    f.write(json.dumps({'setup_time': setup_time, 'solve_time': solve_time}))
+    f.truncate()
+    f.flush()
     print(f"DEBUG - Saved {key} timing: setup={setup_time*1000:.2f}ms, solve={solve_time*1000:.2f}ms")
 
 
