@@ -877,9 +877,10 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       stage_generic(b);
       team_sync();
     }
+    PH_MARK(9)   // (profiling builds: wait for the first chunk)
     // parity buffers must have been handed back by the finisher (two iterations ago)
     if (use > 0) mbar_wait(&bars->empty[par], (use - 1) & 1);
-    PH_MARK(0)
+    PH_MARK(0)   // (wait for the finisher)
 
     // ------------------------------------------------------------------ sweep A: canonical lane sums + second moments
     // Row r = the 16-byte vector r*256 + tid.  fp32: samples 2(r*256+tid)+{0,1} = lanes 2 slot + {0,1} of tile r/2,
@@ -887,7 +888,9 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     bool rest_pending = a.bulk != 0;
     auto wait_rest = [&]() {   // chunks 1.. of halfspace b (a no-op when the whole copy fits the first chunk)
       if (rest_pending) {
+        PH_MARK(1)
         if (copy_bytes > kBulkChunk) mbar_wait(&bars->data, phase);
+        PH_MARK(10)
         phase ^= 1u;
         rest_pending = false;
       }
@@ -962,27 +965,40 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     } else {
       double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
       q_xx = q_yy = q_xy = 0.0;
-      auto rows = [&](int r_lo, int r_hi) {
-        for (int r = r_lo; r < r_hi; ++r) {
+      // one row = one sample per thread; even rows feed slot tid, odd rows slot tid + 256, each in increasing row order
+      // (canonical); second moments on every 4th row.  Groups of four rows with the loads up front: with one CTA
+      // per SM (160 KB slot) there are two sweep warps per scheduler and nothing else hides the shared-memory latency.
+      auto acc_row = [&](const V2 v, bool odd, bool mom) {
+        if (!odd) {
+          s00 = __dadd_rn(s00, v.x);
+          s01 = __dadd_rn(s01, v.y);
+        } else {
+          s10 = __dadd_rn(s10, v.x);
+          s11 = __dadd_rn(s11, v.y);
+        }
+        if (mom) {
+          const double dx = v.x - first.x, dy = v.y - first.y;
+          q_dx += dx;
+          q_dy += dy;
+          q_xx = fma(dx, dx, q_xx);
+          q_yy = fma(dy, dy, q_yy);
+          q_xy = fma(dx, dy, q_xy);
+        }
+      };
+      auto rows = [&](int r_lo, int r_hi) {   // r_lo is a multiple of 4
+        int r = r_lo;
+        const int g_hi = r_lo + (((r_hi < full_rows ? r_hi : full_rows) - r_lo) & ~3);
+#pragma unroll 1
+        for (; r < g_hi; r += 4) {
+          V2 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = sm[(r + k) * kRowSamples + tid];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc_row(v[k], (k & 1) != 0, k == 0);
+        }
+        for (; r < r_hi; ++r) {   // (a masked group of four was measured for these last rows: slower)
           const int i = r * kRowSamples + tid;
-          if (i < N) {
-            const V2 v = sm[i];
-            if ((r & 1) == 0) {
-              s00 = __dadd_rn(s00, v.x);
-              s01 = __dadd_rn(s01, v.y);
-            } else {
-              s10 = __dadd_rn(s10, v.x);
-              s11 = __dadd_rn(s11, v.y);
-            }
-            if ((r & 3) == 0) {
-              const double dx = v.x - first.x, dy = v.y - first.y;
-              q_dx += dx;
-              q_dy += dy;
-              q_xx = fma(dx, dx, q_xx);
-              q_yy = fma(dy, dy, q_yy);
-              q_xy = fma(dx, dy, q_xy);
-            }
-          }
+          if (i < N) acc_row(sm[i], (r & 1) != 0, (r & 3) == 0);
         }
       };
       const int r_first = rows_all < kRowsPerChunk ? rows_all : kRowsPerChunk;
@@ -1236,18 +1252,28 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           const int r_lo = wd * kRowsPerWord;
           const int r_hi = rows_all < r_lo + kRowsPerWord ? rows_all : r_lo + kRowsPerWord;
           unsigned bit = 1u;
-          for (int r = r_lo; r < r_hi; ++r, bit <<= 1) {
-            const int i = r * kRowSamples + tid;
-            if (i < N) {
-              const V2 v = sm[i];
-              const double L = loss_of(h0, h1, v.x, v.y);
-              if (L > t_hi) {
-                ++c_gt;
-                s_gt += L;
-              } else if (L >= t_lo) {
-                mask[wd] |= bit;
-              }
+          auto one = [&](const V2 v, unsigned bt) {   // exact canonical loss of one sample (rows in increasing order: s_gt is deterministic)
+            const double L = loss_of(h0, h1, v.x, v.y);
+            if (L > t_hi) {
+              ++c_gt;
+              s_gt += L;
+            } else if (L >= t_lo) {
+              mask[wd] |= bt;
             }
+          };
+          int r = r_lo;
+          const int g_hi = r_lo + (((r_hi < full_rows ? r_hi : full_rows) - r_lo) & ~3);
+#pragma unroll 1
+          for (; r < g_hi; r += 4, bit <<= 4) {   // four complete rows, loads up front
+            V2 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = sm[(r + k) * kRowSamples + tid];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) one(v[k], bit << k);
+          }
+          for (; r < r_hi; ++r, bit <<= 1) {
+            const int i = r * kRowSamples + tid;
+            if (i < N) one(sm[i], bit);
           }
         }
       }

@@ -39,8 +39,8 @@ ms = e0.elapsed_time(e1)
 grid = min(B, 296, int(os.environ.get('DRCVAR_DEBUG_GRID', '296')))
 c = buf[:grid].double().cpu().numpy()
 per = B / grid
-names_s = ["wait data/empty", "sweep A + warp reduce", "S1 wait", "direction (S2 wait)", "sweep B", "phase 2", "partials",
-           "S3 wait", "post (handoff/general/tail)", "-", "-", "-"]
+names_s = ["wait for the finisher (empty[par])", "sweep A + warp reduce", "S1 wait", "direction (S2 wait)", "sweep B", "phase 2", "partials",
+           "S3 wait", "post (handoff/general/tail)", "wait for the first chunk (data0)", "wait for the other chunks (inside sweep A)", "-"]
 names_f = ["wait full", "select + epilogue", "-"]
 print(f"B={B} N={N} {dt}: {ms:.3f} ms, {B/ms/1e3:.2f} M halfspaces/s, {B*N*2*s.element_size()/ms/1e6:.0f} GB/s; {per:.1f} halfspaces per CTA")
 tot = c[:, 0, :].sum(axis=1).mean() / per
