@@ -47,6 +47,13 @@
 #define PH_MARK(k)
 #endif
 
+#ifndef DRCVAR_PF_WHERE
+#define DRCVAR_PF_WHERE 0
+#endif
+#ifndef DRCVAR_PF_DIST
+#define DRCVAR_PF_DIST 1
+#endif
+
 namespace drcvar {
 
 constexpr int kSweepWarps = 8;
@@ -231,6 +238,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// L2 prefetch of a halfspace that is still one slot release away (no shared-memory destination needed): the later bulk
+// copy then reads L2 instead of waiting for HBM
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 // Named barriers 2..7 (one per parity): handshakes towards the two helper warps.  The producer side arrives without
 // waiting (bar.arrive), the helper blocks in hardware (bar.sync) instead of polling an mbarrier.  A barrier id is
@@ -728,6 +740,14 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       const int par = iter & 1;
       Ctl* ctl = ctl_base + par;
       const double* red = red_base + par * kRedDoubles;
+#if DRCVAR_PF_WHERE == 0
+      if (a.bulk && lane == 0) {
+        const long long b_pf = b + static_cast<long long>(DRCVAR_PF_DIST) * gridDim.x;
+        if (b_pf < a.B)
+          bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(a.samples) + static_cast<size_t>(b_pf) * a.stride_b * sizeof(T),
+                           copy_bytes & ~15u);
+      }
+#endif
       bar_sync(kBarADone + par, 64);   // red[par] is complete
       double w[2];
 #pragma unroll
@@ -776,6 +796,14 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->hdone[par]);
+#if DRCVAR_PF_WHERE == 1
+      if (a.bulk && lane == 0) {
+        const long long b_pf = b + static_cast<long long>(DRCVAR_PF_DIST) * gridDim.x;
+        if (b_pf < a.B)
+          bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(a.samples) + static_cast<size_t>(b_pf) * a.stride_b * sizeof(T),
+                           copy_bytes & ~15u);
+      }
+#endif
       // TMA producer: as soon as all 8 sweep warps are done with the sample slot, fetch the next halfspace
       bar_sync(kBarSlotFree + par, kSweepThreads + 32);
       if (a.bulk) {
