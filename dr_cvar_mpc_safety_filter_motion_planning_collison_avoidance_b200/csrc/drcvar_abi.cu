@@ -19,6 +19,7 @@
 #include "streaming_kernel.cuh"
 #include "cluster_kernel.cuh"
 #include "cluster_kernel_f64.cuh"
+#include "pipelined_kernel.cuh"
 
 namespace {
 
@@ -335,6 +336,49 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
     return DRCVAR_OK;
+  }
+  // ---- pipelined resident kernel (pipelined_kernel.cuh): contiguous samples, window planned, no tail indices.  Halfspaces
+  // it hands back (window miss / not placeable / overflow) are computed by the streaming kernel's redo pass on the same stream.
+  {
+    const long long rows_all = (c.N + 256 * (16 / (2 * sizeof(T))) - 1) / (256 * (16 / (2 * sizeof(T))));
+    const size_t psmem = slot_bytes_for(c.N, sizeof(T)) + pipelined_fixed_smem_bytes(sizeof(T));
+    static const bool env_off = getenv("DRCVAR_NO_PIPELINE") != nullptr;
+    if (!tail && c.gen_mean == nullptr && a.bulk && a.use_window && !(c.flags & DRCVAR_FLAG_NO_PIPELINE) && !env_off &&
+        c.B < 0x7fffffffLL && rows_all * (16 / (2 * sizeof(T))) <= 32 * kMaskWords &&
+        psmem <= static_cast<size_t>(di->max_smem_optin)) {
+      auto pk = pipelined_kernel<T>;
+      CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem)));
+      int p_per_sm = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p_per_sm, pk, kThreads, psmem));
+      if (p_per_sm >= 1) {
+        int* redo = nullptr;   // redo flag of halfspace b at redo[b]; stream-ordered allocation, freed on every path below
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&redo), sizeof(int) * static_cast<size_t>(c.B), stream));
+        auto pass = [&]() -> cudaError_t {
+          cudaError_t e = cudaMemsetAsync(redo, 0, sizeof(int) * static_cast<size_t>(c.B), stream);
+          if (e != cudaSuccess) return e;
+          KernelArgs pa = a;
+          pa.redo_list = redo;
+          const long long pgrid = std::min<long long>(c.B, static_cast<long long>(p_per_sm) * di->sms);
+          pk<<<static_cast<unsigned>(pgrid), kThreads, psmem, stream>>>(pa);
+          e = cudaGetLastError();
+          if (e != cudaSuccess) return e;
+          g_launches.fetch_add(1);
+          KernelArgs ra = a;   // the streaming kernel places its own windows (and learns them after two misses in a row)
+          ra.redo_list = redo;
+          ra.bulk = 1;
+          const long long rgrid = std::min<long long>(c.B, di->sms);
+          streaming_kernel<T, false><<<static_cast<unsigned>(rgrid), kStreamThreads, 0, stream>>>(ra);
+          e = cudaGetLastError();
+          if (e == cudaSuccess) g_launches.fetch_add(1);
+          return e;
+        };
+        const cudaError_t pe = pass();
+        const cudaError_t fe = cudaFreeAsync(redo, stream);
+        if (pe != cudaSuccess || fe != cudaSuccess)
+          return fail(DRCVAR_ERR_CUDA, "pipelined kernel path failed: %s", cudaGetErrorString(pe != cudaSuccess ? pe : fe));
+        return DRCVAR_OK;
+      }
+    }
   }
   auto kern = tail ? halfspace_kernel<T, true> : halfspace_kernel<T, false>;
   if constexpr (sizeof(T) == 4) {

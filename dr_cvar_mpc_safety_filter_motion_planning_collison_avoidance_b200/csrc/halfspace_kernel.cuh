@@ -482,7 +482,8 @@ __device__ __forceinline__ void write_mean_outputs(const KernelArgs& a, long lon
 
 // CVaR / DR-CVaR offsets of one halfspace from (h, CVaR ingredients); one thread.      core/risk_metrics.py:84-338
 // hn = ||h|| by the canonical chain (norm2_canon(h0, h1)): the resident kernel's director warp has it ready in ctl->hn.
-__device__ __forceinline__ void write_risk_outputs(const KernelArgs& a, long long b, const Ctl* ctl, bool nonfinite,
+template <class CtlT>
+__device__ __forceinline__ void write_risk_outputs(const KernelArgs& a, long long b, const CtlT* ctl, bool nonfinite,
                                                    double s_tot, int c_tot, double T_thr, int status, double hn) {
   const double h0 = ctl->h0, h1 = ctl->h1;
   const double r = __dmul_rn(a.R, hn);

@@ -57,6 +57,7 @@ extern "C" {
 #define DRCVAR_FLAG_FORCE_STREAMING 8u /* use the two-pass streaming kernel even when one CTA could hold N samples */
 #define DRCVAR_FLAG_NO_CLUSTER 16u   /* large N: do not use the cluster / DSMEM single-read kernel (streaming kernel instead) */
 #define DRCVAR_FLAG_FORCE_CLUSTER 32u /* fp64 samples, large N: use the fp64 cluster kernel (opt-in: the streaming kernel is faster there) */
+#define DRCVAR_FLAG_NO_PIPELINE 64u  /* resident sizes: use halfspace_kernel (inline general path) instead of the pipelined kernel + redo pass */
 
 /* per-halfspace status bits written to status_out */
 #define DRCVAR_STATUS_NONFINITE 1   /* non-finite input: sentinel 100.0 emitted (core/risk_metrics.py:177,265,303,338) */
