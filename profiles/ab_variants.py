@@ -27,12 +27,24 @@ for _ in range(3):
     out = pkg.compute_halfspaces(s, ego, out=out, **P)
 torch.cuda.synchronize()
 ts = []
-for _ in range(10):
+clk, pw, why = [], [], 0
+try:
+    import pynvml
+    pynvml.nvmlInit(); hnd = pynvml.nvmlDeviceGetHandleByIndex(0)
+except Exception:
+    hnd = None
+for _ in range(int(os.environ.get("AB_ITERS", "20"))):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); out = pkg.compute_halfspaces(s, ego, out=out, **P); e1.record(); torch.cuda.synchronize()
+    e0.record(); out = pkg.compute_halfspaces(s, ego, out=out, **P); e1.record()
+    if hnd is not None:   # sampled while the launch is in flight
+        clk.append(pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM)); pw.append(pynvml.nvmlDeviceGetPowerUsage(hnd) / 1000.0)
+        why |= pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hnd)
+    torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
-ts.sort()
-print(json.dumps({"ms_median": ts[len(ts) // 2], "ms_min": ts[0], "B": B, "N": N, "elem": s.element_size()}))
+ts.sort(); clk.sort(); pw.sort()
+print(json.dumps({"ms_median": ts[len(ts) // 2], "ms_min": ts[0], "B": B, "N": N, "elem": s.element_size(),
+                  "clk_min": clk[0] if clk else None, "clk_med": clk[len(clk) // 2] if clk else None,
+                  "pw_med": pw[len(pw) // 2] if pw else None, "why": why}))
 ''' % ROOT
 
 libs = sys.argv[1:]
@@ -49,4 +61,5 @@ for rep in range(2):
 for l in libs:
     for d in res[l]:
         gbs = d["B"] * (d["N"] * 2 * d["elem"] + 56) / d["ms_median"] / 1e6
-        print(f"{os.path.basename(l):28s} median {d['ms_median']:.3f} ms  min {d['ms_min']:.3f} ms  {d['B'] / d['ms_median'] / 1e3:.2f} M hs/s  {gbs:.0f} GB/s = {gbs / peak:.3f} of measured peak")
+        print(f"{os.path.basename(l):28s} median {d['ms_median']:.3f} ms  min {d['ms_min']:.3f} ms  {d['B'] / d['ms_median'] / 1e3:.2f} M hs/s  {gbs:.0f} GB/s = {gbs / peak:.3f} of measured peak"
+              f"  | SM MHz min/med {d.get('clk_min')}/{d.get('clk_med')}  {d.get('pw_med')} W  throttle reasons 0x{d.get('why') or 0:x}")

@@ -143,9 +143,11 @@ def test_random_batches(eng, dtype, n, alpha):
     p = dict(PARAMS, alpha=alpha, epsilon=0.01)
     res = eng.compute_halfspaces(s, ego, want_tail=True, **p)
     check_batch(res, s, ego, p)
-    # without the tail output (the timed configuration) results are identical
+    # without the tail output (the timed configuration: pipelined kernel where the window applies) the direction, the mean
+    # halfspace and the threshold are the same bits; the CVaR sum is taken in another order (last-bit differences)
     res2 = eng.compute_halfspaces(s, ego, **p)
-    assert np.array_equal(res2.g, res.g) and np.array_equal(res2.h, res.h) and np.array_equal(res2.cvar, res.cvar)
+    assert np.array_equal(res2.h, res.h) and np.array_equal(res2.var, res.var) and np.array_equal(res2.g[:, 0], res.g[:, 0])
+    assert rel_close(res2.g, res.g, 1e-12 if dtype == np.float64 else 1e-7) and rel_close(res2.cvar, res.cvar, 1e-12 if dtype == np.float64 else 1e-7)
     # forcing the general select or the generic loader changes nothing but the last-bit summation order
     from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
     res3 = eng.compute_halfspaces(s, ego, want_tail=True, flags=_lib.FLAG_GENERAL_ONLY | _lib.FLAG_NO_BULK, **p)

@@ -1,0 +1,110 @@
+"""
+Pipelined resident kernel (csrc/pipelined_kernel.cuh: window placement on the director warp, deferred exact phase, no
+barrier inside the sweep team, misses handed to the streaming kernel's redo pass) against
+  * the oracle (oracle/closed_form.py),
+  * halfspace_kernel on the same inputs (FLAG_NO_PIPELINE: inline general path, team barriers),
+through the C ABI.  Bars as in test_gpu_parity.py: h and the threshold T (`var`) bit-exact, offsets <= 1e-9 relative
+(fp64 samples) / <= 1e-6 m (fp32 samples).
+"""
+import numpy as np
+import pytest
+
+from oracle import closed_form as cf
+
+pytestmark = pytest.mark.gpu
+PARAMS = dict(alpha=0.1, delta=0.1, epsilon=0.01, robot_radius=0.3, obstacle_radius=0.3)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 as pkg
+    return pkg
+
+
+def _batch(rng, B, n, dtype, sigma=0.1):
+    mu = rng.uniform(-5, 5, size=(B, 1, 2))
+    s = (mu + sigma * rng.standard_normal((B, n, 2)) * np.array([1.0, 0.6])).astype(dtype)
+    return s, rng.uniform(-1, 1, size=(B, 2))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1024, 4096, 4098, 6001, 10000])
+def test_pipelined_equals_inline_kernel_and_oracle(eng, dtype, n):
+    """Several halfspaces per CTA (the deferred phase, the drain iteration and both parity buffers are exercised),
+    single-chunk and multi-chunk copies, ragged last rows."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    rng = np.random.RandomState(n + (1 if dtype == np.float64 else 0))
+    for B in (1, 2, 296, 297, 296 * 3 + 5):
+        s, ego = _batch(rng, B, n, dtype)
+        a = eng.compute_halfspaces(s, ego, **PARAMS)
+        b = eng.compute_halfspaces(s, ego, flags=_lib.FLAG_NO_PIPELINE, **PARAMS)
+        assert np.array_equal(a.h, b.h) and np.array_equal(a.h_mean, b.h_mean) and np.array_equal(a.var, b.var), (n, B)
+        assert np.array_equal(a.g[:, 0], b.g[:, 0])                       # mean halfspace: same chain, same bits
+        tol = 1e-6 if dtype == np.float32 else 1e-12
+        assert np.abs(a.g - b.g).max() <= tol and np.abs(a.cvar - b.cvar).max() <= tol and np.abs(a.g_star - b.g_star).max() <= tol
+        assert (a.status == b.status).all() or ((a.status | b.status) & _lib.STATUS_GENERAL).any()
+        for k in sorted({0, B // 2, B - 1}):
+            o = cf.halfspace(s[k], ego[k], PARAMS["alpha"], PARAMS["delta"], PARAMS["epsilon"], PARAMS["robot_radius"],
+                             PARAMS["obstacle_radius"])
+            assert np.array_equal(a.h[k], o.h) and a.var[k] == o.var, (n, B, k)
+            bar = 1e-6 if dtype == np.float32 else 1e-9 * max(1.0, abs(o.g_cvar))
+            assert abs(a.g[k, 1] - o.g_cvar) <= bar and abs(a.g[k, 2] - o.g_dr) <= bar and abs(a.g[k, 0] - o.g_mean) <= 1e-9
+
+
+def test_pipelined_handbacks_are_recomputed_exactly(eng):
+    """Halfspaces the pipelined kernel cannot finish (non-finite sample, all-identical samples, heavy ties, a bimodal
+    cloud that defeats the window) sit between ordinary ones: the redo pass computes them, the neighbours are untouched."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    rng = np.random.RandomState(77)
+    n, B = 10000, 296 * 2 + 40
+    s, ego = _batch(rng, B, n, np.float32)
+    odd = {5: "nan", 300: "const", 301: "ties", 420: "bimodal", B - 1: "const"}
+    for k, kind in odd.items():
+        if kind == "nan":
+            s[k, 1234, 1] = np.nan
+        elif kind == "const":
+            s[k] = np.array([4.0, -1.0], dtype=np.float32)
+        elif kind == "ties":
+            s[k] = (2.0 + rng.randint(0, 4, size=(n, 2)) * 0.25).astype(np.float32)
+        else:
+            s[k] = (np.where(rng.rand(n, 1) < 0.15, 6.0, 2.0) + 0.05 * rng.standard_normal((n, 2))).astype(np.float32)
+    a = eng.compute_halfspaces(s, ego, **PARAMS)
+    b = eng.compute_halfspaces(s, ego, flags=_lib.FLAG_NO_PIPELINE, **PARAMS)
+    assert a.status[5] & _lib.STATUS_NONFINITE and a.g[5, 1] == 100.0
+    assert np.array_equal(a.h[np.isfinite(a.h)], b.h[np.isfinite(b.h)])
+    keep = np.array([k for k in range(B) if k != 5])
+    assert np.array_equal(a.var[keep], b.var[keep])
+    assert np.abs(a.g[keep] - b.g[keep]).max() <= 1e-6
+    for k, kind in odd.items():
+        if kind == "nan":
+            continue
+        o = cf.halfspace(s[k], ego[k], PARAMS["alpha"], PARAMS["delta"], PARAMS["epsilon"], PARAMS["robot_radius"],
+                         PARAMS["obstacle_radius"])
+        assert a.var[k] == o.var and np.array_equal(a.h[k], o.h), (k, kind)
+        assert abs(a.g[k, 1] - o.g_cvar) <= 1e-6 and abs(a.g[k, 2] - o.g_dr) <= 1e-6, (k, kind)
+    plain = np.array([k for k in range(B) if k not in odd])
+    assert (a.status[plain] == 0).all()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pipelined_is_deterministic_also_on_non_gaussian_batches(eng, dtype):
+    """The learned-window chain (fixed lag of three halfspaces per CTA) must give run-to-run identical bits, and the exact
+    thresholds, on Laplace / uniform noise where the Gaussian plan misses."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    rng = np.random.RandomState(9)
+    n, B = 4096, 296 * 10
+    mu = rng.uniform(1.0, 4.0, size=(B, 1, 2))
+    lap = rng.laplace(scale=0.1 / np.sqrt(2), size=(B // 2, n, 2))
+    uni = rng.uniform(-0.1 * np.sqrt(3), 0.1 * np.sqrt(3), size=(B - B // 2, n, 2))
+    s = (mu + np.concatenate([lap, uni])).astype(dtype)
+    ego = np.zeros((B, 2))
+    r1 = eng.compute_halfspaces(s, ego, **PARAMS)
+    r2 = eng.compute_halfspaces(s, ego, **PARAMS)
+    assert np.array_equal(r1.g, r2.g) and np.array_equal(r1.var, r2.var) and np.array_equal(r1.status, r2.status)
+    exact = eng.compute_halfspaces(s, ego, flags=_lib.FLAG_GENERAL_ONLY, **PARAMS)
+    assert np.array_equal(r1.var, exact.var) and np.array_equal(r1.h, exact.h)
+    tol = 1e-6 if dtype == np.float32 else 1e-9
+    assert np.abs(r1.g - exact.g).max() <= tol
