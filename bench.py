@@ -238,7 +238,7 @@ def run_reference_arm(a):
 
 
 # ------------------------------------------------------------------------------------------ our arm
-KERNEL_SOURCES = ("halfspace_kernel.cuh", "streaming_kernel.cuh", "cluster_kernel.cuh", "cluster_kernel_f64.cuh", "sample_gen.cuh",
+KERNEL_SOURCES = ("halfspace_kernel.cuh", "pipelined_kernel.cuh", "streaming_kernel.cuh", "cluster_kernel.cuh", "cluster_kernel_f64.cuh", "sample_gen.cuh",
                   "drcvar_abi.cu")
 PARITY_BAR = {"f32": 1e-6, "f64": 1e-9}   # vs the oracle on the same samples: metres (fp32 inputs) / relative (fp64 inputs)
 
@@ -479,7 +479,8 @@ def run_ours(a):
     clocks = sampler.stop()
     launches = pkg.launch_count() - launches0
     value = world * B * a.steps / (total_ms * 1e-3)
-    kernel_name = ("halfspace_kernel" if N <= pkg.max_samples(np.float32 if a.dtype == "f32" else np.float64)
+    resident = N <= pkg.max_samples(np.float32 if a.dtype == "f32" else np.float64)
+    kernel_name = (("pipelined_kernel" if a.dtype == "f32" and N >= 1024 else "halfspace_kernel") if resident
                    else ("cluster_kernel_f32" if a.dtype == "f32" and N > 32768 else "streaming_kernel"))
     alg_bytes = algorithmic_bytes_per_halfspace(N, elem) * B
     achieved = alg_bytes / (kern_ms_avg * 1e-3) / 1e9

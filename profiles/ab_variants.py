@@ -42,17 +42,20 @@ for _ in range(int(os.environ.get("AB_ITERS", "20"))):
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 ts.sort(); clk.sort(); pw.sort()
-print(json.dumps({"ms_median": ts[len(ts) // 2], "ms_min": ts[0], "B": B, "N": N, "elem": s.element_size(),
+fallback = int((out.status.cpu().numpy() != 0).sum()) if getattr(out, "status", None) is not None else -1
+print(json.dumps({"ms_median": ts[len(ts) // 2], "ms_min": ts[0], "B": B, "N": N, "elem": s.element_size(), "fallback": fallback,
                   "clk_min": clk[0] if clk else None, "clk_med": clk[len(clk) // 2] if clk else None,
                   "pw_med": pw[len(pw) // 2] if pw else None, "why": why}))
 ''' % ROOT
 
-libs = sys.argv[1:]
+libs = sys.argv[1:]   # "lib.so" or "lib.so:ENV=value[,ENV=value]" (environment of that variant's child process)
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6537.3
 res = {l: [] for l in libs}
 for rep in range(2):
     for l in libs:
-        env = dict(os.environ, DRCVAR_LIB=os.path.abspath(l))
+        env = dict(os.environ, DRCVAR_LIB=os.path.abspath(l.split(":")[0]))
+        for kv in (l.split(":")[1].split(",") if ":" in l else []):
+            env[kv.split("=")[0]] = kv.split("=")[1]
         r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
         if r.returncode != 0:
             print(l, "FAILED", r.stderr[-500:])
@@ -62,4 +65,4 @@ for l in libs:
     for d in res[l]:
         gbs = d["B"] * (d["N"] * 2 * d["elem"] + 56) / d["ms_median"] / 1e6
         print(f"{os.path.basename(l):28s} median {d['ms_median']:.3f} ms  min {d['ms_min']:.3f} ms  {d['B'] / d['ms_median'] / 1e3:.2f} M hs/s  {gbs:.0f} GB/s = {gbs / peak:.3f} of measured peak"
-              f"  | SM MHz min/med {d.get('clk_min')}/{d.get('clk_med')}  {d.get('pw_med')} W  throttle reasons 0x{d.get('why') or 0:x}")
+              f"  fallbacks {d.get('fallback')}  | SM MHz min/med {d.get('clk_min')}/{d.get('clk_med')}  {d.get('pw_med')} W  throttle reasons 0x{d.get('why') or 0:x}")
