@@ -50,6 +50,22 @@ class SafetyFilteringEnvironment:
         if n_steps == 0 or len(obstacle_sample_trajectories) == 0:
             return out
         ego_steps = np.stack([self.C @ np.asarray(ego_ref_trajectory[t]) for t in range(n_steps)])
+        # sample trajectories that exist only as (nominal trajectory, covariance, Philox key) — the drop-in
+        # simulation/obstacles.py returns them: the samples are drawn inside the kernel, one launch per obstacle
+        lazy = [tr for tr in obstacle_sample_trajectories if hasattr(tr, "kernel_inputs") and not tr.materialised]
+        if len(lazy) == len(obstacle_sample_trajectories) and all(
+                tr.shape[1] >= n_steps and tr.shape[2] == 2 for tr in lazy):
+            t0 = time.time()
+            cols = []
+            for tr in lazy:
+                mean, chol = tr.kernel_inputs(n_steps)
+                cols.append(_engine.compute_halfspaces_generated(
+                    mean, None, tr.n_samples, tr.key, ego=ego_steps, chol=chol, alpha=self.ALPHA, delta=self.DELTA,
+                    epsilon=self.EPSILON, robot_radius=self.ROBOT_RADIUS, obstacle_radius=self.OBSTACLE_RADIUS))
+            h = np.stack([c.h for c in cols], axis=1)
+            hm = np.stack([c.h_mean for c in cols], axis=1)
+            g = np.stack([c.g for c in cols], axis=1)
+            return self._wrap(h, hm, g, n_steps, len(cols), time.time() - t0)
         trajs = [np.asarray(tr, dtype=np.float64) for tr in obstacle_sample_trajectories]
         uniform = all(tr.shape == trajs[0].shape for tr in trajs) and trajs[0].shape[1] >= n_steps
         t0 = time.time()

@@ -50,6 +50,12 @@ EXPECTED = {
         "SafetyFilteringEnvironment.compute_safe_halfspaces_for_trajectory": "(self, obstacle_sample_trajectories, ego_ref_trajectory)",
         "SafetyFilteringEnvironment.compute_distance_to_collision": "(self, ego_trajectory, obstacle_trajectories)",
     },
+    "simulation.obstacles": {
+        "generate_nominal_trajectory": "(start_pos, direction, speed, n_steps, dt)",
+        "generate_obstacle_sample_trajectories": "(nominal_trajectory, n_samples, noise_cov, dt)",
+        "generate_laplace_realization": "(nominal_trajectory, noise_cov, dt)",
+        "generate_obstacle_scenarios": "(scenario_config, horizon, dt, n_samples=100)",
+    },
     "core.mpc_filter": {
         "MPCSafetyFilter.__init__": "(self, A, B, C, Q, R, horizon, dt)",
         "MPCSafetyFilter.filter_trajectory":
@@ -106,11 +112,44 @@ def test_frozen_table_matches_the_reference_itself():
     _purge()
     with ref_harness.reference_modules() as ref:
         mods = {"core.risk_metrics": ref.risk_metrics, "core.halfspaces": ref.halfspaces, "core.geometry": ref.geometry,
-                "simulation.environment": ref.environment, "_stopwatch": importlib.import_module("utils.timing"),
+                "simulation.environment": ref.environment, "simulation.obstacles": ref.obstacles,
+                "_stopwatch": importlib.import_module("utils.timing"),
                 "core.mpc_filter": ref.mpc_filter}
         for modname, table in EXPECTED.items():
             for dotted, sig in table.items():
                 assert _sig(mods[modname], dotted) == sig, (modname, dotted)
+
+
+def test_obstacle_module_host_parts_equal_the_reference(dropin):
+    """simulation/obstacles.py drop-in: nominal trajectories and the Laplace realization are the reference's numbers
+    (same recurrence, same numpy draws in the same order); the sample trajectories are a lazy array-like."""
+    ob = dropin["simulation.obstacles"]
+    nom = ob.generate_nominal_trajectory(np.array([5.0, 0.5]), np.array([-3.0, 0.1]), 0.7, 40, 0.1)
+    assert nom.shape == (41, 2) and np.array_equal(nom[0], [5.0, 0.5])
+    still = ob.generate_nominal_trajectory(np.array([1.0, 2.0]), np.array([0.0, 0.0]), 1.0, 5, 0.1)
+    assert np.array_equal(still, np.tile([1.0, 2.0], (6, 1)))
+    np.random.seed(3)
+    lazy = ob.generate_obstacle_sample_trajectories(nom, 64, np.diag([0.01, 0.04]), 0.1)
+    assert lazy.shape == (64, 41, 2) and len(lazy) == 64 and lazy.ndim == 3 and not lazy.materialised
+    mean, chol = lazy.kernel_inputs(30)
+    assert np.array_equal(mean, nom[:30]) and np.array_equal(chol[0], [0, 0, 0]) and np.allclose(chol[1], [0.1, 0.0, 0.2])
+    np.random.seed(3)
+    assert ob.generate_obstacle_sample_trajectories(nom, 64, np.diag([0.01, 0.04]), 0.1).key == lazy.key   # np.random.seed reproduces it
+    data = ob.generate_obstacle_scenarios({"obstacles": [{"start": np.array([4.0, 1.0]), "direction": np.array([-1.0, 0.0])},
+                                                          {"start": np.array([4.0, -1.0]), "direction": np.array([-1.0, 0.2]),
+                                                           "speed": 0.5}]}, 3.0, 0.1, n_samples=32)
+    assert [len(v) for v in data.values()] == [2, 2, 2] and data["sample_trajectories"][1].shape == (32, 31, 2)
+    assert data["sample_trajectories"][0].key != data["sample_trajectories"][1].key
+    from oracle import ref_harness
+    if not ref_harness.available():
+        return
+    _purge()
+    with ref_harness.reference_modules() as ref:
+        assert np.array_equal(ref.obstacles.generate_nominal_trajectory(np.array([5.0, 0.5]), np.array([-3.0, 0.1]), 0.7, 40, 0.1), nom)
+        np.random.seed(11)
+        want = ref.obstacles.generate_laplace_realization(nom, np.diag([0.01, 0.04]), 0.1)
+    np.random.seed(11)
+    assert np.array_equal(ob.generate_laplace_realization(nom, np.diag([0.01, 0.04]), 0.1), want)
 
 
 def test_dead_helpers_keep_reference_semantics(dropin):
@@ -226,3 +265,45 @@ def test_nominal_trajectory_extension(dropin, golden_dir):
             assert np.array_equal(hs.h, o.h) and abs(hs.g_tilde - o.g_dr) <= 1e-6
             assert abs(res["cvar"][t][i].g_tilde - o.g_cvar) <= 1e-6
             assert abs(res["mean"][t][i].g_tilde - o.g_mean) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_obstacle_dropin_feeds_the_generate_mode(dropin):
+    """main.py's flow with the drop-in simulation/obstacles.py: generate_obstacle_scenarios -> lazy sample trajectories ->
+    SafetyFilteringEnvironment.compute_safe_halfspaces_for_trajectory draws the samples inside the kernel.  The result
+    must equal (a) the oracle on the samples the generator is specified to draw (oracle/sample_gen.py), (b) the ordinary
+    stored-sample path fed with the materialised array (what the reference's visualisation code would read)."""
+    from oracle import closed_form as cf
+    from oracle import sample_gen as sg
+    ob, env_mod = dropin["simulation.obstacles"], dropin["simulation.environment"]
+    alpha, delta, eps, rr, ro, horizon, dt, n = 0.1, 0.1, 0.01, 0.3, 0.3, 12, 0.2, 4000
+    env = env_mod.SafetyFilteringEnvironment(rr, ro, horizon, dt, alpha, delta, eps)
+    np.random.seed(42)
+    data = ob.generate_obstacle_scenarios({"obstacles": [
+        {"start": np.array([4.0, 0.6]), "direction": np.array([-1.0, 0.0]), "speed": 0.8},
+        {"start": np.array([3.0, -2.0]), "direction": np.array([-0.3, 1.0])}]}, 4.0, dt, n_samples=n)
+    lazy = data["sample_trajectories"]
+    x_ref = np.stack([np.array([0.25 * t, 0.0, 1.25, 0.0]) for t in range(21)])
+    hs = env.compute_safe_halfspaces_for_trajectory(lazy, x_ref)                     # main.py:95
+    assert not any(tr.materialised for tr in lazy)                                   # nothing was stored on the host
+    assert len(hs["dr_cvar"]) == horizon and len(hs["cvar"][0]) == 2
+    cov = np.diag([0.01, 0.01])
+    for i, tr in enumerate(lazy):
+        for t in (0, 1, horizon - 1):
+            chol = np.zeros((1, 3)) if t == 0 else sg.cholesky2(cov)[None]
+            s = sg.generate(data["nominal_trajectories"][i][t][None], chol, n, tr.key, index_offset=t)[0]
+            o = cf.halfspace(s, x_ref[t][:2], alpha, delta, eps, rr, ro)
+            assert np.array_equal(hs["dr_cvar"][t][i].h, o.h)
+            assert abs(hs["dr_cvar"][t][i].g_tilde - o.g_dr) <= 1e-6 and abs(hs["cvar"][t][i].g_tilde - o.g_cvar) <= 1e-6
+            assert abs(hs["mean"][t][i].g_tilde - o.g_mean) <= 1e-9
+    dense = [np.asarray(tr) for tr in lazy]                                          # materialised through the kernel's dump
+    assert dense[0].shape == (n, 21, 2) and dense[0].dtype == np.float64 and all(tr.materialised for tr in lazy)
+    assert np.array_equal(dense[1][:, 0, :], np.tile(data["nominal_trajectories"][1][0], (n, 1)))
+    assert np.array_equal(lazy[0][:, 3, :], dense[0][:, 3, :])                       # indexing like environment.py:88
+    s3 = sg.generate(data["nominal_trajectories"][0][3][None], sg.cholesky2(cov)[None], n, lazy[0].key, index_offset=3)[0]
+    assert np.array_equal(dense[0][:, 3, :].astype(np.float32), s3)                  # the specified stream, bit for bit
+    again = env.compute_safe_halfspaces_for_trajectory(dense, x_ref)                 # stored-sample path (fp64 arrays)
+    for t in range(1, horizon):
+        for i in range(2):
+            assert abs(again["dr_cvar"][t][i].g_tilde - hs["dr_cvar"][t][i].g_tilde) <= 1e-6
+            assert np.abs(again["dr_cvar"][t][i].h - hs["dr_cvar"][t][i].h).max() <= 1e-9   # fp64 mean vs shifted fp32 lane sums
