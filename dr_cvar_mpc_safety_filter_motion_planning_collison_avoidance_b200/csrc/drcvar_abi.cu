@@ -588,6 +588,21 @@ int run_host(const Call& c) {
   chunk_b = std::min(chunk_b, c.B);
   const long long n_chunks = (c.B + chunk_b - 1) / chunk_b;
 
+  // is the caller's sample array page-locked?  (numpy arrays are not; drcvar_host_alloc / cudaHostRegister memory is)
+  bool pageable = true;
+  {
+    cudaPointerAttributes pa{};
+    if (cudaPointerGetAttributes(&pa, c.samples) == cudaSuccess) pageable = pa.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+  }
+  static const int stage_threads = [] {
+    const char* e = getenv("DRCVAR_STAGE_THREADS");
+    const int hw = static_cast<int>(std::thread::hardware_concurrency());
+    if (e) return std::max(1, atoi(e));
+    const char* lw = getenv("LOCAL_WORLD_SIZE");   // torchrun: one process per GPU shares the host's cores
+    const int ranks = lw ? std::max(1, atoi(lw)) : 1;
+    return std::max(1, std::min(16, hw / ranks));   // 16 threads: 35 GB/s of staging on a 16-core box (profiles/r2_pageable_e2e.txt)
+  }();
   struct Pending {
     bool live;
     long long b0, nb;
@@ -637,20 +652,42 @@ int run_host(const Call& c) {
 
     // ---- samples H2D
     const T* src = reinterpret_cast<const T*>(c.samples) + b0 * c.stride_b;
-    if (contiguous) {
+    if (contiguous && !pageable) {
       CUDA_TRY(cudaMemcpyAsync(hc.d_samples[s], src, static_cast<size_t>(nb) * row_bytes, cudaMemcpyHostToDevice, st));
     } else {
-      // strided host view (e.g. traj[:, t, :], simulation/environment.py:88): pack into pinned memory first
+      // pageable numpy arrays (what the reference's callers hand over) and strided host views (traj[:, t, :],
+      // simulation/environment.py:88) are staged into this slot's pinned buffer by a few host threads; the copy of chunk
+      // ci then runs by DMA while the threads stage chunk ci + 1.  (A pageable cudaMemcpyAsync is staged by the driver on
+      // ONE thread at ~11 GB/s and blocks the caller meanwhile.)
       rc = grow_pinned(&hc.h_pack[s], &hc.h_pack_cap[s], static_cast<size_t>(nb) * row_pitch);
       if (rc) return rc;
       unsigned char* dst = static_cast<unsigned char*>(hc.h_pack[s]);
-      for (long long b = 0; b < nb; ++b) {
-        T* row = reinterpret_cast<T*>(dst + static_cast<size_t>(b) * row_pitch);
-        const T* sb = src + b * c.stride_b;
-        for (long long i = 0; i < c.N; ++i) {
-          row[2 * i] = sb[i * c.stride_n];
-          row[2 * i + 1] = sb[i * c.stride_n + c.stride_c];
+      const Call* cp = &c;
+      auto stage_rows = [=](long long lo, long long hi) {
+        if (contiguous) {
+          std::memcpy(dst + static_cast<size_t>(lo) * row_pitch, reinterpret_cast<const unsigned char*>(src) + static_cast<size_t>(lo) * row_bytes,
+                      static_cast<size_t>(hi - lo) * row_bytes);
+          return;
         }
+        for (long long b = lo; b < hi; ++b) {
+          T* row = reinterpret_cast<T*>(dst + static_cast<size_t>(b) * row_pitch);
+          const T* sb = src + b * cp->stride_b;
+          for (long long i = 0; i < cp->N; ++i) {
+            row[2 * i] = sb[i * cp->stride_n];
+            row[2 * i + 1] = sb[i * cp->stride_n + cp->stride_c];
+          }
+        }
+      };
+      const size_t chunk_bytes = static_cast<size_t>(nb) * row_bytes;
+      const long long n_thr = std::max<long long>(1, std::min<long long>({static_cast<long long>(stage_threads), nb,
+                                                                         static_cast<long long>(chunk_bytes >> 21)}));
+      if (n_thr == 1) {
+        stage_rows(0, nb);
+      } else {
+        std::vector<std::thread> pool;
+        for (long long k = 1; k < n_thr; ++k) pool.emplace_back(stage_rows, nb * k / n_thr, nb * (k + 1) / n_thr);
+        stage_rows(0, nb / n_thr);
+        for (auto& th : pool) th.join();
       }
       CUDA_TRY(cudaMemcpyAsync(hc.d_samples[s], dst, static_cast<size_t>(nb) * row_pitch, cudaMemcpyHostToDevice, st));
     }
