@@ -238,8 +238,7 @@ def run_reference_arm(a):
 
 
 # ------------------------------------------------------------------------------------------ our arm
-KERNEL_SOURCES = ("halfspace_kernel.cuh", "pipelined_kernel.cuh", "streaming_kernel.cuh", "cluster_kernel.cuh", "cluster_kernel_f64.cuh", "sample_gen.cuh",
-                  "drcvar_abi.cu")
+KERNEL_SOURCES = ("halfspace_kernel.cuh", "pipelined_kernel.cuh", "streaming_kernel.cuh", "cluster_kernel.cuh", "cluster_kernel_f64.cuh", "sample_gen.cuh")
 PARITY_BAR = {"f32": 1e-6, "f64": 1e-9}   # vs the oracle on the same samples: metres (fp32 inputs) / relative (fp64 inputs)
 
 
