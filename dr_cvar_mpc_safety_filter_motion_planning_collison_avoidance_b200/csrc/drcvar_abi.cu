@@ -343,9 +343,11 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
     const long long rows_all = (c.N + 256 * (16 / (2 * sizeof(T))) - 1) / (256 * (16 / (2 * sizeof(T))));
     const size_t psmem = slot_bytes_for(c.N, sizeof(T)) + pipelined_fixed_smem_bytes(sizeof(T));
     static const bool env_off = getenv("DRCVAR_NO_PIPELINE") != nullptr;
-    // (fp64 samples classify with the canonical direction: the director's window + div/sqrt chain is then longer than the
-    //  deferred phase that covers it — 0.482 vs 0.505 of the HBM peak — so they stay on halfspace_kernel)
-    if (sizeof(T) == 4 && !tail && c.gen_mean == nullptr && a.bulk && a.use_window && !(c.flags & DRCVAR_FLAG_NO_PIPELINE) && !env_off &&
+    // (fp64 samples classify with the canonical direction: the director's div/sqrt chain + window placement, one after the
+    //  other, is longer than the deferred phase that covers it — 0.622 vs 0.673 of the HBM peak on halfspace_kernel, where
+    //  warp 0 places the window WHILE the director runs the chain — so they stay there; DRCVAR_PIPELINE_F64=1 overrides)
+    static const bool env_f64 = getenv("DRCVAR_PIPELINE_F64") != nullptr;
+    if ((sizeof(T) == 4 || env_f64) && !tail && c.gen_mean == nullptr && a.bulk && a.use_window && !(c.flags & DRCVAR_FLAG_NO_PIPELINE) && !env_off &&
         c.B < 0x7fffffffLL && rows_all * (16 / (2 * sizeof(T))) <= 32 * kMaskWords &&
         psmem <= static_cast<size_t>(di->max_smem_optin)) {
       auto pk = pipelined_kernel<T>;

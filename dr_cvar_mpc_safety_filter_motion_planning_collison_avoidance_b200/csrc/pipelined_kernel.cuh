@@ -325,6 +325,45 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
         w[j] = t[0];
       }
       const double f0 = red[6], f1 = red[7];   // first sample (warp 0's record)
+      // ---------------------------------------------------------------- canonical direction (IEEE div / sqrt chain)
+      double m0 = 0.0, m1 = 0.0;
+      auto canonical_chain = [&]() {
+        m0 = ddiv_canon(w[0], static_cast<double>(N));
+        m1 = ddiv_canon(w[1], static_cast<double>(N));
+        if constexpr (kF32) {  // fp32 inputs: the lane sums were taken relative to the first sample
+          m0 = __dadd_rn(f0, m0);
+          m1 = __dadd_rn(f1, m1);
+        }
+        int nonfinite = !(isfinite(m0) && isfinite(m1));
+        int degenerate = 0;
+        double h0, h1;
+        if (a.h_in != nullptr) {
+          h0 = pre0;
+          h1 = pre1;
+        } else {
+          const double d0 = __dsub_rn(m0, pre0), d1 = __dsub_rn(m1, pre1);
+          const double nrm = norm2_canon(d0, d1);
+          if (nrm < 1e-10) {
+            h0 = 1.0;
+            h1 = 0.0;
+            degenerate = 1;
+          } else {
+            h0 = ddiv_canon(d0, nrm);
+            h1 = ddiv_canon(d1, nrm);
+          }
+        }
+        nonfinite |= !(isfinite(h0) && isfinite(h1));
+        const double hn = norm2_canon(h0, h1);
+        if (lane == 0) {
+          win->hand.h0 = h0; win->hand.h1 = h1;
+          win->hand.hn = hn;
+          win->hand.nonfinite = nonfinite;
+          win->hand.degenerate = degenerate;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->hdone[par]);
+      };
+      if constexpr (!kF32) canonical_chain();  // fp64 samples classify with the canonical direction: it goes first
       {
         const float* redf = reinterpret_cast<const float*>(red);   // warp g: floats 4..9 of its 16 = qxx,qyy,qxy,bound,mdx,mdy
         float q[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -431,41 +470,7 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->wdone[par]);
       }
-      // ---------------------------------------------------------------- canonical direction (IEEE div / sqrt chain)
-      double m0 = ddiv_canon(w[0], static_cast<double>(N));
-      double m1 = ddiv_canon(w[1], static_cast<double>(N));
-      if constexpr (kF32) {  // fp32 inputs: the lane sums were taken relative to the first sample
-        m0 = __dadd_rn(f0, m0);
-        m1 = __dadd_rn(f1, m1);
-      }
-      int nonfinite = !(isfinite(m0) && isfinite(m1));
-      int degenerate = 0;
-      double h0, h1;
-      if (a.h_in != nullptr) {
-        h0 = pre0;
-        h1 = pre1;
-      } else {
-        const double d0 = __dsub_rn(m0, pre0), d1 = __dsub_rn(m1, pre1);
-        const double nrm = norm2_canon(d0, d1);
-        if (nrm < 1e-10) {
-          h0 = 1.0;
-          h1 = 0.0;
-          degenerate = 1;
-        } else {
-          h0 = ddiv_canon(d0, nrm);
-          h1 = ddiv_canon(d1, nrm);
-        }
-      }
-      nonfinite |= !(isfinite(h0) && isfinite(h1));
-      const double hn = norm2_canon(h0, h1);
-      if (lane == 0) {
-        win->hand.h0 = h0; win->hand.h1 = h1;
-        win->hand.hn = hn;
-        win->hand.nonfinite = nonfinite;
-        win->hand.degenerate = degenerate;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->hdone[par]);
+      if constexpr (kF32) canonical_chain();   // fp32 samples: after the window (the team classifies with the fp32 direction)
       // TMA producer: as soon as all 8 sweep warps are done with the sample slot, fetch the next halfspace
       bar_sync(kBarSlotFree + par, kPBarCount);
       {
@@ -775,12 +780,7 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
             unsigned bit = 1u;
             auto one = [&](const V2 v, unsigned bt) {
               const double L = loss_of(h0, h1, v.x, v.y);
-              if (L > t_hi) {
-                ++c_gt;
-                s_gt += L;
-              } else if (L >= t_lo) {
-                mask[wd] |= bt;
-              }
+              classify_f64(L, t_hi, t_lo, s_gt, c_gt, mask[wd], bt);
             };
             int r = r_lo;
             const int g_hi = r_lo + (((r_hi < full_rows ? r_hi : full_rows) - r_lo) & ~3);
