@@ -57,6 +57,7 @@ SYMBOLS = {
     "drcvar_host_alloc": (C.c_void_p, [C.c_size_t]),
     "drcvar_host_free": (None, [C.c_void_p]),
     "drcvar_launch_count": (C.c_int64, []),
+    "drcvar_debug_check_failures": (C.c_int64, [_ip]),
     "drcvar_cluster_ctas": (C.c_int, [C.c_int64, C.c_int, C.c_int64]),
     "drcvar_last_host_call_stats": (C.c_int, [_dp, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }

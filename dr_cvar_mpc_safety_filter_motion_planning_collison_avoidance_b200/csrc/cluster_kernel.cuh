@@ -26,6 +26,8 @@
 #pragma once
 
 #include "halfspace_kernel.cuh"
+#undef DRCVAR_FILE_ID
+#define DRCVAR_FILE_ID 4
 
 #ifdef DRCVAR_PROFILE_PHASES
 #define CL_DBG(bit) ((a.debug & (bit)) != 0)   // ablation switches of the profiling build (wrong results, timing only)
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         reinterpret_cast<const unsigned char*>(a.samples) + static_cast<size_t>(b) * a.stride_b * sizeof(float) + part_lo;
     const uint32_t off = static_cast<uint32_t>(j) * kBulkChunk;
     const uint32_t n = part_b - off < kBulkChunk ? part_b - off : kBulkChunk;
+    DRCVAR_ASSERT(b >= 0 && b < a.B && j >= 0 && j < kClMaxChunks && off + n <= slot_bytes && n > 0u && (n & 15u) == 0u);
     mbar_expect_tx(&sh->full[j], n);
     bulk_g2s(smem_raw + off, src + off, n, &sh->full[j]);
   };
@@ -659,6 +662,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
           if (mk) {
             const unsigned e = static_cast<unsigned>(__ffs(static_cast<int>(mk))) - 1u;
             const int pos = n_list + __popc(bal & lt_mask);
+            DRCVAR_ASSERT(pos >= 0 && base + (e >> 1) * kClLaneRow + (e & 1u) * 8u + 8u <= slot_bytes);
             if (pos < kClWarpList)
               wlist[pos] = lds64(slot_s + base + (e >> 1) * kClLaneRow + (e & 1u) * 8u);
           }
@@ -807,6 +811,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       }
       if (!ovf) {
         const double* wcand = reinterpret_cast<const double*>(wlist);
+        DRCVAR_ASSERT(before >= 0 && static_cast<int>(rank) * cap + before <= kClPool);
         const uint32_t dst = mapa_u32(smem_u32(&sh->pool[rank * cap + before]), static_cast<uint32_t>(leader));
         for (int j = lane; j < nc; j += 32) st_async_f64(dst + 8u * j, wcand[j], bar);
       }

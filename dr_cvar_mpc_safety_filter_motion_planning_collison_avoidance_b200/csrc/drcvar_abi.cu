@@ -1009,6 +1009,21 @@ int drcvar_cluster_ctas(int64_t n_samples, int elem_bytes, int64_t smem_optin_by
 
 int64_t drcvar_launch_count(void) { return g_launches.load(); }
 
+int64_t drcvar_debug_check_failures(int32_t* first_site) {
+  if (first_site) *first_site = 0;
+#ifdef DRCVAR_CHECKED
+  unsigned long long n = 0;
+  int site = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpyFromSymbol(&n, drcvar_check_fail_count, sizeof(n)) != cudaSuccess) return -2;
+  if (cudaMemcpyFromSymbol(&site, drcvar_check_first_site, sizeof(site)) != cudaSuccess) return -2;
+  if (first_site) *first_site = site;
+  return static_cast<int64_t>(n);
+#else
+  return -1;   // not a checked build (make -C csrc checked)
+#endif
+}
+
 #ifdef DRCVAR_PROFILE_PHASES
 // profiling builds only (not part of include/drcvar.h): device buffer receiving per-CTA phase cycle counts
 void drcvar_debug_phase_buffer(long long* dev_buf) { g_phase_cycles = dev_buf; }

@@ -54,6 +54,23 @@
 #define DRCVAR_PF_DIST 1
 #endif
 
+// Checked builds (make -C csrc checked -> libdrcvar_checked.so, never loaded by the product path): every index into a
+// shared-memory list / histogram / candidate pool and every staged byte range is asserted in range; failures are counted
+// in device globals read back by drcvar_debug_check_failures().  compute-sanitizer is not available on the GPU pool this
+// was developed on; tests/test_gpu_checked_build.py runs every kernel path through this build instead.
+#ifdef DRCVAR_CHECKED
+__device__ unsigned long long drcvar_check_fail_count = 0ull;
+__device__ int drcvar_check_first_site = 0;   // 100000 * file id + line of the first failed assertion
+#define DRCVAR_ASSERT_AT(fid, cond)                                                                  \
+  do {                                                                                               \
+    if (!(cond) && atomicAdd(&drcvar_check_fail_count, 1ull) == 0ull) drcvar_check_first_site = 100000 * (fid) + __LINE__; \
+  } while (0)
+#else
+#define DRCVAR_ASSERT_AT(fid, cond) do { } while (0)
+#endif
+#define DRCVAR_ASSERT(cond) DRCVAR_ASSERT_AT(DRCVAR_FILE_ID, cond)
+#define DRCVAR_FILE_ID 1   // halfspace_kernel.cuh (redefined at the top of the other kernel files)
+
 namespace drcvar {
 
 constexpr int kSweepWarps = 8;
@@ -429,7 +446,10 @@ __device__ double select_rank(ForEach&& for_each, Sync&& SYNC, bool leader, int 
     SYNC();
     for_each([&](double L) {
       const unsigned long long k = key_of(L);
-      if (k >= lo && k <= hi) atomicAdd(&hist[static_cast<unsigned>((k - lo) >> shift)], 1u);
+      if (k >= lo && k <= hi) {
+        DRCVAR_ASSERT(((k - lo) >> shift) < static_cast<unsigned long long>(kHistBuckets));
+        atomicAdd(&hist[static_cast<unsigned>((k - lo) >> shift)], 1u);
+      }
     });
     SYNC();
     if (leader) {
@@ -517,6 +537,7 @@ __device__ __forceinline__ void write_risk_outputs(const KernelArgs& a, long lon
     g_star = __dsub_rn(__dadd_rn(cr, a.eoa), a.delta);
     g_dr = __dsub_rn(g_star, r);
   }
+  DRCVAR_ASSERT(b >= 0 && b < a.B);
   a.h_out[2 * b] = h0;
   a.h_out[2 * b + 1] = h1;
   a.g_out[3 * b + 1] = g_cvar;
@@ -579,6 +600,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
     const unsigned char* src =
         reinterpret_cast<const unsigned char*>(a.samples) + static_cast<size_t>(b) * a.stride_b * sizeof(T);
     const uint32_t n0 = copy_bytes < kBulkChunk ? copy_bytes : kBulkChunk;
+    DRCVAR_ASSERT(b >= 0 && b < a.B && copy_bytes <= slot_bytes && (copy_bytes & 15u) == 0u);
     mbar_expect_tx(&bars->data0, n0);
     bulk_g2s(smem_raw, src, n0, &bars->data0);
     if (copy_bytes > n0) {
@@ -586,6 +608,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
 #pragma unroll 1
       for (uint32_t off = n0; off < copy_bytes; off += kBulkChunk) {
         const uint32_t n = copy_bytes - off < kBulkChunk ? copy_bytes - off : kBulkChunk;
+        DRCVAR_ASSERT(off + n <= slot_bytes);
         bulk_g2s(smem_raw + off, src + off, n, &bars->data);
       }
     }
@@ -1355,6 +1378,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
               const unsigned bp = 31u - static_cast<unsigned>(__clz(static_cast<int>(mm)));   // highest set bit (one FLO)
               mm ^= 1u << bp;
               const unsigned off = kF32 ? (((bp & 30u) << 11) | ((bp & 1u) << 3)) : (bp << 12);
+              DRCVAR_ASSERT(dst < wlist + kWarpList && (wbase + off) + sizeof(V2) <= smem_raw + slot_bytes);
               *dst++ = *reinterpret_cast<const V2*>(wbase + off);
             }
           }
@@ -1395,6 +1419,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           if (bal) {
             const int pos = nc + __popc(bal & ((1u << lane) - 1u));
             if (cd && pos < kCandCap) {
+              DRCVAR_ASSERT(pos >= 0 && ((key_of(L) - klo) >> hshift) < static_cast<unsigned long long>(kHistBuckets));
               wcand[pos] = L;
               atomicAdd(&hist[static_cast<unsigned>((key_of(L) - klo) >> hshift)], 1u);
             }
@@ -1590,6 +1615,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
             if (w < warp) out_before += wsel[w];
             tile_sel += wsel[w];
           }
+          DRCVAR_ASSERT(!sel || out_before + __popc(msel & ((1u << lane) - 1u)) < a.kc);
           if (sel) out[out_before + __popc(msel & ((1u << lane) - 1u))] = i;
           run_eq += tile_eq;
           run_out += tile_sel;

@@ -20,6 +20,8 @@
 #pragma once
 
 #include "halfspace_kernel.cuh"
+#undef DRCVAR_FILE_ID
+#define DRCVAR_FILE_ID 2
 
 namespace drcvar {
 
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
   auto issue_bulk = [&](long long b) {
     const unsigned char* src = src_of(b);
     const uint32_t n0 = copy_bytes < kBulkChunk ? copy_bytes : kBulkChunk;
+    DRCVAR_ASSERT(b >= 0 && b < a.B && copy_bytes <= slot_bytes && (copy_bytes & 15u) == 0u);
     mbar_expect_tx(&bars->data0, n0);
     bulk_g2s(smem_raw, src, n0, &bars->data0);
     if (copy_bytes > n0) {
@@ -131,6 +134,7 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
       double* small = small_base + par * kResolveMax;
       bar_sync(kBarFull + par, kPBarCount);   // all 8 sweep warps have delivered halfspace b
       // team totals: sure-above count, window candidates, any overflow
+      DRCVAR_ASSERT(lane >= kSweepWarps || (ired[lane * 2 + 1] >= 0 && ired[lane * 2 + 1] <= kCandCap));
       const int my_hi = lane < kSweepWarps ? ired[lane * 2] : 0;
       const int my_nc = lane < kSweepWarps ? ired[lane * 2 + 1] : 0;
       const int ovf = __reduce_or_sync(kFull, static_cast<unsigned>(my_hi & kPOverflowBit)) != 0u;
@@ -251,6 +255,7 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
           }
         }
       } else if (lane == 0) {
+        DRCVAR_ASSERT(b >= 0 && b < a.B);
         a.redo_list[b] = 1;   // the streaming kernel's redo pass computes this halfspace
         if (placed && !ovf) {
           // a placed window that missed: after two in a row (or already in learned mode) move the centre past the window,
@@ -672,6 +677,7 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
           v.x = 0;
           v.y = 0;
           if (active) {
+            DRCVAR_ASSERT(k < kWarpList);
             v = wlist[k];
             L = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
           }
@@ -688,6 +694,7 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
           if (bal) {
             const int pos = nc + __popc(bal & ((1u << lane) - 1u));
             if (cd && pos < kCandCap) {
+              DRCVAR_ASSERT(pos >= 0 && ((key_of(L) - klo) >> hshift) < static_cast<unsigned long long>(kHistBuckets));
               wcand[pos] = L;
               atomicAdd(&hist[static_cast<unsigned>((key_of(L) - klo) >> hshift)], 1u);
             }
@@ -832,6 +839,7 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
                 const unsigned bp = 31u - static_cast<unsigned>(__clz(static_cast<int>(mm)));
                 mm ^= 1u << bp;
                 const unsigned off = kF32 ? (((bp & 30u) << 11) | ((bp & 1u) << 3)) : (bp << 12);
+                DRCVAR_ASSERT(dst < wlist + kWarpList && (wbase + off) + sizeof(V2) <= smem_raw + slot_bytes);
                 *dst++ = *reinterpret_cast<const V2*>(wbase + off);
               }
             }

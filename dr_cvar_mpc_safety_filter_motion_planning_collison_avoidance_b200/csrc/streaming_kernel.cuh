@@ -15,6 +15,8 @@
 #pragma once
 
 #include "halfspace_kernel.cuh"
+#undef DRCVAR_FILE_ID
+#define DRCVAR_FILE_ID 3
 
 namespace drcvar {
 
@@ -474,6 +476,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) streaming_kernel(const Kern
         const unsigned bal = __ballot_sync(kFull, cd);
         if (bal) {
           const int pos = nc + __popc(bal & ((1u << lane) - 1u));
+          DRCVAR_ASSERT(pos >= 0);
           if (cd && pos < kStreamCand) wcand[pos] = L;
           nc += __popc(bal);
         }

@@ -174,6 +174,11 @@ int drcvar_cluster_ctas(int64_t n_samples, int elem_bytes, int64_t smem_optin_by
 
 /* Telemetry of this process: kernels launched so far; timings (ms) and bytes of the LAST DRCVAR_HOST call. */
 int64_t drcvar_launch_count(void);
+/* Checked builds only (make -C csrc checked -> libdrcvar_checked.so: every shared-memory list / histogram / pool index and
+ * staged byte range of the kernels is asserted in range): number of failed assertions on the current device since the
+ * library was loaded, `*first_site` = 100000 * file id + line of the first one.  -1 in the product build.  There is no
+ * reference counterpart: the reference has no native code; this stands in for compute-sanitizer where that tool is closed. */
+int64_t drcvar_debug_check_failures(int32_t* first_site);
 int drcvar_last_host_call_stats(double* stage_ms, double* kernel_ms, int64_t* h2d_bytes, int64_t* d2h_bytes);
 
 #ifdef __cplusplus
