@@ -67,7 +67,7 @@ class ClockSampler:
     """Samples SM clock / throttle reasons DURING the timed region (NVML, 20 ms period)."""
 
     def __init__(self, torch_device_index):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.reasons, self.max_mhz, self.power, self.power_limit = [], set(), None, [], None
         self._stop = threading.Event()
         self._thr = None
         self._h = None
@@ -93,6 +93,10 @@ class ClockSampler:
                 h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self._h = h
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            try:
+                self.power_limit = pynvml.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+            except Exception:
+                self.power_limit = None
         except Exception:
             self._h = None
 
@@ -109,6 +113,7 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
                 r = int(get_reasons(self._h))
                 for k, bit in names.items():
                     if r & bit:
@@ -131,6 +136,10 @@ class ClockSampler:
             "sm_max_mhz": self.max_mhz,
             "reasons": sorted(self.reasons),
             "n_samples": len(self.samples),
+            # board power while the timed steps ran (NVML averages over ~1 s, so a 50 ms region shows the ramp, not the plateau):
+            # the fp32 kernel reaches the cap within a second of back-to-back steps (profiles/r2_sustained_power.txt)
+            "power_w_max": max(self.power) if self.power else None,
+            "power_limit_w": self.power_limit,
         }
 
 

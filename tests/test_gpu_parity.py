@@ -143,6 +143,9 @@ def test_random_batches(eng, dtype, n, alpha):
     p = dict(PARAMS, alpha=alpha, epsilon=0.01)
     res = eng.compute_halfspaces(s, ego, want_tail=True, **p)
     check_batch(res, s, ego, p)
+    # The timed configuration (no tail output) is not asked for its tail SET: the set is a function of (h, T) alone — the kc
+    # largest canonical losses -(h.xi), ties to the lower index — so bit-equal h and T (`var`) with the parity-mode run above,
+    # whose set was just compared with the oracle's, pin it by construction.
     # without the tail output (the timed configuration: pipelined kernel where the window applies) the direction, the mean
     # halfspace and the threshold are the same bits; the CVaR sum is taken in another order (last-bit differences)
     res2 = eng.compute_halfspaces(s, ego, **p)
