@@ -114,6 +114,89 @@ def test_dropin_mpc_interface_and_fallback(dropin_mods):
                 str(inspect.signature(cls.filter_trajectory.__wrapped__))
 
 
+@pytest.mark.parametrize("scenario,metric", [("head_on", "dr_cvar"), ("multi_obstacle", "cvar")])
+def test_dropin_mpc_optimum_by_an_independent_formulation_and_solver(dropin_mods, scenario, metric):
+    """The golden trajectories and the drop-in filter both come from Mehrotra interior-point solvers (the cvxpy shim's and
+    the drop-in's): same algorithm family.  This check shares neither the formulation nor the solver: the reference's QP
+    (core/mpc_filter.py:58-149) is restated here in CONDENSED form — states eliminated through the dynamics, variables
+    (u, slack) only — and solved by scipy's trust-constr (its own trust-region barrier implementation); the problem is strictly
+    convex (R > 0, slack penalty 50 s^2), so its optimum is unique and the two answers must coincide."""
+    from scipy.optimize import minimize
+    hs = np.load(os.path.join(GOLD, f"{scenario}_seed42.npz"))
+    m = np.load(os.path.join(GOLD, f"mpc_{scenario}_seed42.npz"))
+    A, B, C, Q, R = (np.asarray(m[k], float) for k in ("A", "B", "C", "Q", "R"))
+    H, n, nu = int(m["horizon"]), A.shape[0], B.shape[1]
+    x0, x_ref = np.asarray(m["x0"], float), np.asarray(m["x_ref"], float)
+    h_all, g_all = hs[f"h_{metric}"], hs[f"g_{metric}"]
+    # x[t] = Phi[t] x0 + sum_k Gam[t][k] u[k]
+    Phi = [np.eye(n)]
+    for t in range(H):
+        Phi.append(A @ Phi[-1])
+    Gam = np.zeros((H + 1, n, H * nu))
+    for t in range(1, H + 1):
+        Gam[t] = A @ Gam[t - 1]
+        Gam[t][:, (t - 1) * nu:t * nu] += B
+    cons = [(t, h_all[t - 1, i], float(g_all[t - 1, i])) for t in range(1, H + 1) if t - 1 < h_all.shape[0]
+            for i in range(h_all.shape[1])]
+    n_s = len(cons)
+
+    def states(u):
+        return np.stack([Phi[t] @ x0 + Gam[t] @ u for t in range(H + 1)])
+
+    def cost(v):
+        u, s = v[:H * nu], v[H * nu:]
+        x = states(u)
+        e = x[1:] - x_ref[1:H + 1]
+        return float(np.einsum("ti,ij,tj->", e, Q, e) + np.einsum("ti,ij,tj->", u.reshape(H, nu), R, u.reshape(H, nu))
+                     + 50.0 * s.sum() + 50.0 * (s ** 2).sum())
+
+    def grad(v):
+        u, s = v[:H * nu], v[H * nu:]
+        x = states(u)
+        gu = 2.0 * (np.kron(np.eye(H), R) @ u)
+        for t in range(1, H + 1):
+            gu += 2.0 * Gam[t].T @ (Q @ (x[t] - x_ref[t]))
+        return np.concatenate([gu, 50.0 + 100.0 * s])
+
+    rows, rhs = [], []                                    # G v <= rhs
+    for k, (t, hh, gg) in enumerate(cons):                # h.(C x[t]) + g <= s
+        row = np.zeros(H * nu + n_s)
+        row[:H * nu] = (hh @ C) @ Gam[t]
+        row[H * nu + k] = -1.0
+        rows.append(row)
+        rhs.append(-gg - (hh @ C) @ (Phi[t] @ x0))
+    for t in range(1, H + 1):                             # pos_min <= C x[t] <= pos_max
+        for j in range(C.shape[0]):
+            cj = C[j] @ Gam[t]
+            off = C[j] @ (Phi[t] @ x0)
+            rows.append(np.concatenate([cj, np.zeros(n_s)]))
+            rhs.append(float(m["pos_max"][j]) - off)
+            rows.append(np.concatenate([-cj, np.zeros(n_s)]))
+            rhs.append(off - float(m["pos_min"][j]))
+    G, r = np.array(rows), np.array(rhs)
+    bounds = [(float(m["u_min"][k % nu]), float(m["u_max"][k % nu])) for k in range(H * nu)] + [(0.0, None)] * n_s
+    from scipy.optimize import Bounds, LinearConstraint
+    Hs = 2.0 * np.kron(np.eye(H), R)                      # Hessian of the condensed objective (constant)
+    for t in range(1, H + 1):
+        Hs += 2.0 * Gam[t].T @ Q @ Gam[t]
+    hess = np.zeros((H * nu + n_s, H * nu + n_s))
+    hess[:H * nu, :H * nu] = Hs
+    hess[H * nu:, H * nu:] = 100.0 * np.eye(n_s)
+    lb = np.array([b[0] for b in bounds])
+    ub = np.array([np.inf if b[1] is None else b[1] for b in bounds])
+    v0 = np.concatenate([np.zeros(H * nu), np.ones(n_s)])
+    res = minimize(cost, v0, jac=grad, hess=lambda v: hess, method="trust-constr", bounds=Bounds(lb, ub),
+                   constraints=[LinearConstraint(G, -np.inf, r)],
+                   options={"xtol": 1e-13, "gtol": 1e-11, "barrier_tol": 1e-12, "maxiter": 3000})
+    assert (r - G @ res.x).min() >= -1e-8 and np.isfinite(res.fun), res.message
+    x_f, u_f, info = _run_filter(dropin_mods["core.mpc_filter"].MPCSafetyFilter, m, _halfspace_lists(h_all, g_all))
+    assert info["status"] == "optimal"
+    assert abs(info["objective"] - res.fun) <= 1e-7 * max(1.0, abs(res.fun)), (info["objective"], res.fun)
+    assert np.abs(u_f.ravel() - res.x[:H * nu]).max() <= 1e-4          # trust-constr's accuracy in the argument
+    assert np.abs(x_f - states(res.x[:H * nu])).max() <= 1e-4
+    assert cost(np.concatenate([u_f.ravel(), np.maximum(0.0, G[:n_s, :H * nu] @ u_f.ravel() - r[:n_s])])) <= res.fun * (1 + 1e-9) + 1e-9
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/core"), reason="reference tree not present (GPU box)")
 @pytest.mark.parametrize("scenario", ["head_on", "multi_obstacle"])
 def test_reference_mpc_on_closed_form_halfspaces_gives_identical_trajectories(scenario):
