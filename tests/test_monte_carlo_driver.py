@@ -39,6 +39,13 @@ def test_driver_matches_a_run_by_run_loop(tmp_path, monkeypatch):
         monkeypatch.syspath_prepend(p)
     monkeypatch.chdir(tmp_path)
     try:
+        # the overlay WITHOUT its simulation/obstacles.py (dropin/README.md: optional) — the reference's generator with stored
+        # sample arrays: no GPU here to draw lazy samples with
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("simulation.obstacles", os.path.join(REF, "simulation", "obstacles.py"))
+        ref_obstacles = importlib.util.module_from_spec(spec)
+        sys.modules["simulation.obstacles"] = ref_obstacles
+        spec.loader.exec_module(ref_obstacles)
         env_mod = importlib.import_module("simulation.environment")          # drop-in
         mc = importlib.import_module("evaluation.monte_carlo")               # drop-in
         params = importlib.import_module("config.parameters")                # reference
