@@ -92,6 +92,9 @@ class SafetyFilteringEnvironment:
         method run by run.  This is where the scenario-batch axis of BASELINE config 4 comes from (NUM_MC_RUNS = 300,
         config/parameters.py:33).
         """
+        if all(hasattr(tr, "kernel_inputs") and not tr.materialised for run in runs_sample_trajectories for tr in run):
+            # lazy sample trajectories (drop-in simulation/obstacles.py): generate mode, one launch per obstacle, nothing stored
+            return [self.compute_safe_halfspaces_for_trajectory(run, ego_ref_trajectory) for run in runs_sample_trajectories]
         runs = [[np.asarray(tr, dtype=np.float64) for tr in run] for run in runs_sample_trajectories]
         n_steps = min(len(ego_ref_trajectory), self.HORIZON)
         flat = [tr for run in runs for tr in run]

@@ -296,6 +296,9 @@ def test_obstacle_dropin_feeds_the_generate_mode(dropin):
             assert np.array_equal(hs["dr_cvar"][t][i].h, o.h)
             assert abs(hs["dr_cvar"][t][i].g_tilde - o.g_dr) <= 1e-6 and abs(hs["cvar"][t][i].g_tilde - o.g_cvar) <= 1e-6
             assert abs(hs["mean"][t][i].g_tilde - o.g_mean) <= 1e-9
+    per_run = env.compute_safe_halfspaces_for_runs([lazy, lazy[:1]], x_ref)         # Monte-Carlo entry: still nothing stored
+    assert not any(tr.materialised for tr in lazy) and len(per_run) == 2 and len(per_run[1]["cvar"][0]) == 1
+    assert per_run[0]["dr_cvar"][3][1].g_tilde == hs["dr_cvar"][3][1].g_tilde
     dense = [np.asarray(tr) for tr in lazy]                                          # materialised through the kernel's dump
     assert dense[0].shape == (n, 21, 2) and dense[0].dtype == np.float64 and all(tr.materialised for tr in lazy)
     assert np.array_equal(dense[1][:, 0, :], np.tile(data["nominal_trajectories"][1][0], (n, 1)))
