@@ -76,6 +76,11 @@ struct ClShared {
   unsigned long long xbar1[2];
   unsigned long long xbar2;
   unsigned long long hdone[2];
+  // parity (tail-index) mode: the leader's finisher tells every CTA the threshold, where its indices start and how many
+  // threshold-valued samples it may still emit
+  alignas(8) double tmsg[4];                      // T, first output position of this CTA, its tie quota, 1 = emit / 0 = redo
+  unsigned long long tbar;
+  int tcnt[kClTeamWarps * 2];                     // per sweep warp: samples above T, samples equal to T
 };
 
 __host__ __device__ inline size_t cluster_smem_bytes(long long n, int ctas, size_t elem_bytes = 4) {
@@ -138,7 +143,7 @@ __device__ __forceinline__ double pair_tree8(const double* t_in, int stride) {
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-template <bool kGen>
+template <bool kGen, bool kTail = false>
 __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const KernelArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -169,6 +174,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     mbar_init(&sh->hdone[0], 1);
     mbar_init(&sh->hdone[1], 1);
     mbar_init(&sh->fdone, 1);
+    mbar_init(&sh->tbar, 1);
     mbar_fence_init();
     sh->zpub = 0ull;
     sh->fin_missrun = 0;
@@ -306,6 +312,42 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
           const double s_lin = -(fc->h0 * (n_above * fc->f0 + sdx) + fc->h1 * (n_above * fc->f1 + sdy));
           write_risk_outputs(a, b, fc, false, s_lin + s4, cnt_hi + c4, T_thr, fc->degenerate ? kStatusDegenerate : 0);
         }
+        if constexpr (kTail) {
+          // parity mode: every CTA emits the tail indices of ITS samples (they are still in its shared memory).  The leader
+          // knows, per source CTA s, how many of its samples lie above T — the "surely above" count it sent plus its window
+          // candidates above T — and how many equal T (ties are window candidates too): that fixes where the indices of
+          // CTA s start and how many threshold-valued samples it may emit (ties go to the LOWER index: earlier CTAs first).
+          const int need_eq = a.kc - (cnt_hi + c4);
+          int base = 0, eq_seen = 0, my_base = 0, my_quota = 0;
+          for (int s = 0; s < C; ++s) {
+            const int n_s = static_cast<int>(sh->x2[s][3]);
+            int gt_s = 0, eq_s = 0;
+            for (int j = lane; j < n_s; j += 32) {
+              const double L = sh->pool[s * cap + j];
+              gt_s += L > T_thr;
+              eq_s += L == T_thr;
+            }
+            gt_s = __reduce_add_sync(kFull, gt_s) + static_cast<int>(sh->x2[s][0]);
+            eq_s = __reduce_add_sync(kFull, eq_s);
+            int quota = need_eq - eq_seen;
+            quota = quota < 0 ? 0 : (quota > eq_s ? eq_s : quota);
+            if (lane == s) {
+              my_base = base;
+              my_quota = quota;
+            }
+            base += gt_s + quota;
+            eq_seen += eq_s;
+          }
+          if (lane < C) {   // lane d serves destination CTA d
+            const uint32_t dst = mapa_u32(smem_u32(&sh->tmsg[0]), static_cast<uint32_t>(lane));
+            const uint32_t bar = mapa_u32(smem_u32(&sh->tbar), static_cast<uint32_t>(lane));
+            mbar_arrive_expect_tx_remote(bar, 32u);
+            st_async_f64(dst, T_thr, bar);
+            st_async_f64(dst + 8, static_cast<double>(my_base), bar);
+            st_async_f64(dst + 16, static_cast<double>(my_quota), bar);
+            st_async_f64(dst + 24, 1.0, bar);
+          }
+        }
         if (lane == 0) {   // where the threshold sits, in sigma units around the loss mean (as in the resident kernel)
           const float zT = (fc->pl.pm + static_cast<float>(T_thr + fc->pl.c_shift)) / fc->pl.sigma;
           sh->fin_missrun = 0;
@@ -314,7 +356,16 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
             sh->zpub = (static_cast<unsigned long long>((static_cast<unsigned>(it + 1) << 1) | (fc->z_learned ? 1u : 0u)) << 32) |
                        __float_as_uint(z_new);
         }
-      } else if (lane == 0) {
+      } else {
+       if constexpr (kTail) {   // the teams wait for a message whenever a window was placed: tell them there is nothing to emit
+        if (fc->window_ok != 0 && lane < C) {
+          const uint32_t dst = mapa_u32(smem_u32(&sh->tmsg[0]), static_cast<uint32_t>(lane));
+          const uint32_t bar = mapa_u32(smem_u32(&sh->tbar), static_cast<uint32_t>(lane));
+          mbar_arrive_expect_tx_remote(bar, 32u);
+          for (int i = 0; i < 4; ++i) st_async_f64(dst + 8u * i, 0.0, bar);
+        }
+       }
+       if (lane == 0) {
         a.redo_list[b] = 1;   // redo flag of halfspace b
         // a placed window that missed: after two in a row (or already in learned mode) move a learned centre past the
         // window, towards the side the threshold is on
@@ -330,6 +381,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
               sh->zpub = (static_cast<unsigned long long>((static_cast<unsigned>(it + 1) << 1) | 1u) << 32) | __float_as_uint(z_new);
           }
         }
+       }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->fdone);
@@ -345,6 +397,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
   int it = 0;
   PH_DECL
   uint32_t n_lead = 0;    // halfspaces this CTA has led so far (phase of fdone)
+  uint32_t tphase = 0;    // parity mode: phase of tbar (one message per halfspace whose window was placed)
   for (long long b = q; b < a.B; b += n_clusters, ++it) {
     const int par = it & 1;
     const int leader = it % C;
@@ -625,7 +678,7 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
     const bool window = ctl->window_ok != 0;
 
     int rel = 0;   // chunks this warp has handed back (warp-uniform)
-    auto release_upto = [&](int c) {   // chunks [rel, c) are no longer read by this warp
+    auto release_now = [&](int c) {   // chunks [rel, c) are no longer read by this warp
       if (c > rel) {
         __syncwarp();
         if (lane == 0)
@@ -633,9 +686,12 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         rel = c;
       }
     };
+    auto release_upto = [&](int c) {   // parity mode keeps the whole part resident until the tail indices are written
+      if constexpr (!kTail) release_now(c);
+    };
     if (!window) {
       // no usable window (degenerate / non-finite / tiny tails): the streaming kernel redoes this halfspace
-      release_upto(n_chunks);
+      release_now(n_chunks);
       mbar_wait(&sh->hdone[par], (it >> 1) & 1);   // the director is done with x1[par] / ctl[par] before we run ahead
       if (lane == 0) {   // the leader's finisher puts the halfspace on the redo list (fin_ctl.window_ok == 0)
         if (tid == 0 && static_cast<int>(rank) == leader) {
@@ -837,6 +893,78 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         }
       }
       if (static_cast<int>(rank) == leader) ++n_lead;
+    }
+    if constexpr (kTail) {
+      // ---------------------------------------------------------------- parity mode: tail indices from the resident samples
+      // Sweep warp w owns a contiguous byte range of this CTA's part (so the indices it emits are ascending and the warps'
+      // ranges follow each other): pass 1 counts its samples above / equal to T, one team barrier, pass 2 writes the
+      // indices at (CTA start from the leader) + (what the warps before it emit).  Ties go to the lower index.
+      mbar_wait(&sh->tbar, tphase);
+      tphase ^= 1u;
+      const double T_thr = sh->tmsg[0];
+      const bool emit = sh->tmsg[3] != 0.0 && a.tail_idx_out != nullptr;
+      if (emit) {
+        const long long cta_base = static_cast<long long>(sh->tmsg[1]);
+        const int cta_quota = static_cast<int>(sh->tmsg[2]);
+        const uint32_t seg = ((part_b + kClTeamWarps - 1) / kClTeamWarps + 511u) & ~511u;   // whole warp-rows of 32 x 16 bytes
+        const uint32_t lo = warp * seg < part_b ? warp * seg : part_b;
+        const uint32_t hi = lo + seg < part_b ? lo + seg : part_b;
+        const unsigned lt_mask = (1u << lane) - 1u;
+        auto losses = [&](uint32_t off, bool& ok0, bool& ok1, double& L0, double& L1) {
+          ok0 = off + 8u <= hi;
+          ok1 = off + 16u <= hi;
+          L0 = L1 = 0.0;
+          if (ok0) {
+            const float4 v = ok1 ? lds128(slot_s + off) : make_float4(lds64(slot_s + off).x, lds64(slot_s + off).y, 0.f, 0.f);
+            L0 = loss_of(h0, h1, static_cast<double>(v.x), static_cast<double>(v.y));
+            if (ok1) L1 = loss_of(h0, h1, static_cast<double>(v.z), static_cast<double>(v.w));
+          }
+        };
+        int n_gt = 0, n_eq = 0;
+        for (uint32_t off = lo + 16u * lane; off < hi; off += 512u) {
+          bool ok0, ok1;
+          double L0, L1;
+          losses(off, ok0, ok1, L0, L1);
+          n_gt += (ok0 && L0 > T_thr) + (ok1 && L1 > T_thr);
+          n_eq += (ok0 && L0 == T_thr) + (ok1 && L1 == T_thr);
+        }
+        n_gt = __reduce_add_sync(kFull, n_gt);
+        n_eq = __reduce_add_sync(kFull, n_eq);
+        if (lane == 0) {
+          sh->tcnt[warp * 2] = n_gt;
+          sh->tcnt[warp * 2 + 1] = n_eq;
+        }
+        cl_team_sync();
+        int gt_before = 0, eq_before = 0;
+#pragma unroll
+        for (int w = 0; w < kClTeamWarps; ++w) {
+          gt_before += w < warp ? sh->tcnt[w * 2] : 0;
+          eq_before += w < warp ? sh->tcnt[w * 2 + 1] : 0;
+        }
+        long long run = cta_base + gt_before + (eq_before < cta_quota ? eq_before : cta_quota);
+        int eq_run = eq_before;   // threshold-valued samples of this CTA before the current position
+        int* out = a.tail_idx_out + b * static_cast<long long>(a.kc);
+        for (uint32_t off0 = lo; off0 < hi; off0 += 512u) {   // warp-uniform trip count
+          const uint32_t off = off0 + 16u * lane;
+          bool ok0, ok1;
+          double L0, L1;
+          losses(off, ok0, ok1, L0, L1);
+          const bool eq0 = ok0 && L0 == T_thr, eq1 = ok1 && L1 == T_thr;
+          const unsigned be0 = __ballot_sync(kFull, eq0), be1 = __ballot_sync(kFull, eq1);
+          const int rank0 = eq_run + __popc(be0 & lt_mask) + __popc(be1 & lt_mask), rank1 = rank0 + (eq0 ? 1 : 0);
+          const bool sel0 = ok0 && (L0 > T_thr || (eq0 && rank0 < cta_quota));
+          const bool sel1 = ok1 && (L1 > T_thr || (eq1 && rank1 < cta_quota));
+          const unsigned bs0 = __ballot_sync(kFull, sel0), bs1 = __ballot_sync(kFull, sel1);
+          const long long pos0 = run + __popc(bs0 & lt_mask) + __popc(bs1 & lt_mask);
+          const int i0 = static_cast<int>((part_lo + off) >> 3);
+          DRCVAR_ASSERT(!(sel0 || sel1) || (pos0 >= 0 && pos0 + (sel0 && sel1 ? 1 : 0) < a.kc));
+          if (sel0) out[pos0] = i0;
+          if (sel1) out[pos0 + (sel0 ? 1 : 0)] = i0 + 1;
+          run += __popc(bs0) + __popc(bs1);
+          eq_run += __popc(be0) + __popc(be1);
+        }
+      }
+      release_now(n_chunks);   // only now may the next halfspace stream in
     }
     PH_MARK(9)
     // (list / wsum / wcnt are next written behind the team barriers of the next halfspace's octant trees)

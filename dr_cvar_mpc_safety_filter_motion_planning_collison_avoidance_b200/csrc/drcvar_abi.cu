@@ -240,8 +240,10 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   const bool tail = c.tail_idx_out != nullptr;
   a.cl_ctas = 0;
   a.redo_list = nullptr;
+  // (tail indices — parity mode — on the cluster path: fp32 stored samples only; every CTA emits the indices of its resident part)
+  const bool cluster_tail_ok = !tail || (sizeof(T) == 4 && c.gen_mean == nullptr && c.N < 0x7fffffffLL / 2);
   if (streaming && !(c.flags & (DRCVAR_FLAG_FORCE_STREAMING | DRCVAR_FLAG_NO_CLUSTER | DRCVAR_FLAG_GENERAL_ONLY)) &&
-      !tail && c.N > kOctantMinN && c.B < 0x7fffffffLL &&
+      cluster_tail_ok && c.N > kOctantMinN && c.B < 0x7fffffffLL &&
       (sizeof(T) == 4 || (c.gen_mean == nullptr && (c.flags & DRCVAR_FLAG_FORCE_CLUSTER)))) {
     // (fp64 samples: the two-pass streaming kernel is faster — 1.96 vs 1.73 M halfspaces/s at N = 100 000: 1.6 MB per
     //  halfspace leaves no room for a second halfspace in flight per cluster — so the fp64 cluster kernel is opt-in)
@@ -253,7 +255,8 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
                                      (row_bytes % 16 == 0));
     const int ctas = cluster_ctas_for(c.N, sizeof(T), static_cast<size_t>(di->max_smem_optin));
     double zl = 0, zh = 0;
-    void (*ck)(const KernelArgs) = sizeof(T) == 4 ? (gen_mode ? cluster_kernel_f32<true> : cluster_kernel_f32<false>) : cluster_kernel_f64;
+    void (*ck)(const KernelArgs) = sizeof(T) == 4 ? (gen_mode ? cluster_kernel_f32<true> : (tail ? cluster_kernel_f32<false, true> : cluster_kernel_f32<false>))
+                                                  : cluster_kernel_f64;
     const long long cl_n_sigma = sizeof(T) == 4 ? c.N : std::max<long long>(1, c.N / 4);   // fp64: moments on every 4th row
     if (bulk_ok && ctas && plan_window(c.N, kc, cl_n_sigma, 0.7 * kClPool, &zl, &zh)) {
       KernelArgs ca = a;
@@ -303,7 +306,7 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
         KernelArgs ra = a;   // the streaming kernel's own window plan; a CTA that misses twice in a row learns the centre
         ra.redo_list = redo;
         ra.bulk = 1;
-        auto rk = streaming_kernel<T, false>;
+        auto rk = tail ? streaming_kernel<T, true> : streaming_kernel<T, false>;   // (parity mode: the redo pass writes the indices too)
         if constexpr (sizeof(T) == 4) {
           if (gen_mode) rk = streaming_kernel<float, false, true>;
         }

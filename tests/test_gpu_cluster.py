@@ -199,3 +199,62 @@ def test_fp64_cluster_redo_and_explicit_normals(eng):
     s2, _ = gaussian_batch64(rng, B, n)
     res2 = eng.compute_halfspaces(s2, None, h=h, flags=_lib.FLAG_FORCE_CLUSTER, **P)
     check_against_oracle64(res2, s2, np.zeros((B, 2)), P, (0, 4, 9), h_in=h)
+
+
+@pytest.mark.parametrize("n,ctas", [(40000, 2), (100000, 4), (100002, 4), (180000, 8)])
+def test_tail_indices_from_the_cluster_kernel(eng, n, ctas):
+    """Parity mode at cluster sizes: every CTA emits the tail indices of its resident part (one read of the samples) at the
+    positions the leader's finisher assigns; bit-exact against the oracle and the streaming kernel, ties to the lower index,
+    hand-backs (heavy ties, non-finite) through the redo pass."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    assert _lib.load().drcvar_cluster_ctas(n, 4, 232448) == ctas
+    rng = np.random.RandomState(n % 1000 + ctas)
+    B = 7
+    p = dict(alpha=0.1, delta=0.1, epsilon=0.01, robot_radius=0.3, obstacle_radius=0.3)
+    s = (rng.uniform(-4, 4, size=(B, 1, 2)) + 0.1 * rng.standard_normal((B, n, 2))).astype(np.float32)
+    ego = rng.uniform(-1, 1, size=(B, 2))
+    # exact ties AT the threshold inside an otherwise continuous cloud: duplicate the sample that sits at the threshold
+    o0 = cf.halfspace(s[1], ego[1], p["alpha"], p["delta"], p["epsilon"], p["robot_radius"], p["obstacle_radius"])
+    at_T = int(o0.tail_idx[np.argmin(-(s[1][o0.tail_idx].astype(np.float64) @ o0.h))])      # the kc-th largest loss
+    for k in (5, n // 3, n // 2 + 1, n - 2):
+        s[1, k] = s[1, at_T]
+    s[3] = (2.0 + rng.randint(0, 4, size=(n, 2)) * 0.25).astype(np.float32)                 # massive ties: window miss -> redo pass
+    s[5, n // 2, 0] = np.nan                                                                 # non-finite: redo pass, indices -1
+    l0 = eng.launch_count()
+    res = eng.compute_halfspaces(s, ego, want_tail=True, **p)
+    assert eng.launch_count() - l0 == 2                                                      # cluster kernel + redo pass
+    ref = eng.compute_halfspaces(s, ego, want_tail=True, flags=_lib.FLAG_NO_CLUSTER, **p)    # streaming kernel
+    assert np.array_equal(res.tail_idx, ref.tail_idx) and np.array_equal(res.var[[0, 1, 2, 3, 4, 6]], ref.var[[0, 1, 2, 3, 4, 6]])
+    assert np.all(res.tail_idx[5] == -1) and (res.status[5] & _lib.STATUS_NONFINITE)
+    for b in (0, 1, 3, 6):
+        o = cf.halfspace(s[b], ego[b], p["alpha"], p["delta"], p["epsilon"], p["robot_radius"], p["obstacle_radius"])
+        assert np.array_equal(res.tail_idx[b], o.tail_idx), b
+        assert res.var[b] == o.var and np.array_equal(res.h[b], o.h)
+    plain = eng.compute_halfspaces(s, ego, **p)                                              # the timed instantiation: same T
+    assert np.array_equal(plain.var[[0, 1, 2, 4, 6]], res.var[[0, 1, 2, 4, 6]])
+
+
+@pytest.mark.parametrize("n,B", [(40000, 170), (100000, 75)])
+def test_tail_indices_with_several_halfspaces_per_cluster(eng, n, B):
+    """More halfspaces than resident clusters: the message barrier, the leader rotation and the deferred slot release of the
+    parity mode run through several halfspaces per cluster."""
+    import torch
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(n + B)
+    mu = torch.rand(B, 1, 2, generator=g, device="cuda") * 8 - 4
+    s = (mu + 0.1 * torch.randn(B, n, 2, generator=g, device="cuda")).contiguous()
+    ego = torch.rand(B, 2, generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+    p = dict(alpha=0.05, delta=0.1, epsilon=0.01, robot_radius=0.3, obstacle_radius=0.3)
+    a = eng.compute_halfspaces(s, ego, want_tail=True, **p)
+    a2 = eng.compute_halfspaces(s, ego, want_tail=True, **p)
+    b = eng.compute_halfspaces(s, ego, want_tail=True, flags=_lib.FLAG_NO_CLUSTER, **p)
+    torch.cuda.synchronize()
+    assert bool((a.tail_idx == b.tail_idx).all()) and bool((a.var == b.var).all()) and bool((a.h == b.h).all())
+    assert bool((a.tail_idx == a2.tail_idx).all()) and bool((a.g == a2.g).all())
+    kc = a.tail_idx.shape[1]
+    assert kc == int(np.ceil(0.05 * n - 1e-9))
+    idx = a.tail_idx.cpu().numpy()
+    assert (np.diff(idx, axis=1) > 0).all() and idx.min() >= 0 and idx.max() < n          # ascending, in range
+    sn, en = s[B - 1].cpu().numpy(), ego[B - 1].cpu().numpy()
+    o = cf.halfspace(sn, en, p["alpha"], p["delta"], p["epsilon"], p["robot_radius"], p["obstacle_radius"])
+    assert np.array_equal(idx[B - 1], o.tail_idx)
