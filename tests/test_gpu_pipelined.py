@@ -108,3 +108,36 @@ def test_pipelined_is_deterministic_also_on_non_gaussian_batches(eng, dtype):
     assert np.array_equal(r1.var, exact.var) and np.array_equal(r1.h, exact.h)
     tol = 1e-6 if dtype == np.float32 else 1e-9
     assert np.abs(r1.g - exact.g).max() <= tol
+
+
+def test_pipelined_with_explicit_normals_and_padded_rows(eng):
+    """cvar_halfspace / dr_cvar_halfspace with a caller-given h (core/risk_metrics.py:267-338) through the pipelined kernel,
+    including non-unit normals, and device batches whose rows are padded (stride_b > 2 N)."""
+    import torch
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    rng = np.random.RandomState(5)
+    B, n = 600, 6000
+    s, ego = _batch(rng, B, n, np.float32)
+    for h in ((0.6, 0.8), (3.0e2, -1.0e2), (1.0e-3, 2.0e-3)):
+        l0 = eng.launch_count()
+        a = eng.compute_halfspaces(s, None, h=h, **PARAMS)
+        assert eng.launch_count() - l0 == 2                                  # pipelined kernel + redo pass
+        b = eng.compute_halfspaces(s, None, h=h, flags=_lib.FLAG_NO_PIPELINE, **PARAMS)
+        assert np.array_equal(a.var, b.var) and np.array_equal(a.h, b.h)
+        scale = max(abs(h[0]), abs(h[1]))
+        assert np.abs(a.g - b.g).max() <= 1e-6 * max(1.0, scale)
+        for k in (0, B - 1):
+            o = cf.halfspace(s[k], np.zeros(2), PARAMS["alpha"], PARAMS["delta"], PARAMS["epsilon"], PARAMS["robot_radius"],
+                             PARAMS["obstacle_radius"], np.array(h))
+            assert a.var[k] == o.var and abs(a.cvar[k] - o.cvar) <= 1e-6 * max(1.0, scale)
+    # padded device rows: a [B, n + 6, 2] buffer viewed as [B, n, 2] (row stride 2 n + 12 floats, 16-byte aligned)
+    big = torch.zeros(B, n + 6, 2, dtype=torch.float32, device="cuda")
+    big[:, :n, :] = torch.from_numpy(s).cuda()
+    view = big[:, :n, :]
+    assert view.stride(0) == 2 * (n + 6)
+    l0 = eng.launch_count()
+    d = eng.compute_halfspaces(view, torch.from_numpy(ego).cuda(), **PARAMS)
+    torch.cuda.synchronize()
+    assert eng.launch_count() - l0 == 2
+    ref = eng.compute_halfspaces(s, ego, **PARAMS)
+    assert np.array_equal(d.var.cpu().numpy(), ref.var) and np.array_equal(d.g.cpu().numpy(), ref.g)
