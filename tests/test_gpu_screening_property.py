@@ -1,5 +1,5 @@
 """
-Property test of the fp32 screening bounds (csrc/halfspace_kernel.cuh: window placement with a rigorous direction bound
+Property test of the fp32 screening bounds (csrc/halfspace_kernel.cuh and csrc/pipelined_kernel.cuh — the timed configuration: window placement with a rigorous direction bound
 err_h, classification thresholds thr_above / thr_keep) — run on the B200 box: pytest -m gpu.
 
 The screening only decides HOW the exact threshold is found: every sample it calls "surely above" must really lie above the
