@@ -20,6 +20,9 @@
 #include "cluster_kernel.cuh"
 #include "cluster_kernel_f64.cuh"
 #include "pipelined_kernel.cuh"
+#ifndef DRCVAR_PIPELINE_F64_DEFAULT
+#define DRCVAR_PIPELINE_F64_DEFAULT 0   // fp64 samples at resident sizes: 0 = halfspace_kernel<double>, 16 = pipelined_kernel<double, 16>
+#endif
 
 namespace {
 
@@ -343,47 +346,73 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
   // ---- pipelined resident kernel (pipelined_kernel.cuh): contiguous samples, window planned, no tail indices.  Halfspaces
   // it hands back (window miss / not placeable / overflow) are computed by the streaming kernel's redo pass on the same stream.
   {
-    const long long rows_all = (c.N + 256 * (16 / (2 * sizeof(T))) - 1) / (256 * (16 / (2 * sizeof(T))));
-    const size_t psmem = slot_bytes_for(c.N, sizeof(T)) + pipelined_fixed_smem_bytes(sizeof(T));
     static const bool env_off = getenv("DRCVAR_NO_PIPELINE") != nullptr;
-    // (fp64 samples classify with the canonical direction: the director's div/sqrt chain + window placement, one after the
-    //  other, is longer than the deferred phase that covers it — 0.622 vs 0.673 of the HBM peak on halfspace_kernel, where
-    //  warp 0 places the window WHILE the director runs the chain — so they stay there; DRCVAR_PIPELINE_F64=1 overrides)
-    static const bool env_f64 = getenv("DRCVAR_PIPELINE_F64") != nullptr;
-    if ((sizeof(T) == 4 || env_f64) && !tail && c.gen_mean == nullptr && a.bulk && a.use_window && !(c.flags & DRCVAR_FLAG_NO_PIPELINE) && !env_off &&
-        c.B < 0x7fffffffLL && rows_all * (16 / (2 * sizeof(T))) <= 32 * kMaskWords &&
-        psmem <= static_cast<size_t>(di->max_smem_optin)) {
-      auto pk = pipelined_kernel<T>;
+    static const int env_f64 = getenv("DRCVAR_PIPELINE_F64") ? atoi(getenv("DRCVAR_PIPELINE_F64")) : DRCVAR_PIPELINE_F64_DEFAULT;
+    const long long per_load = 16 / (2 * sizeof(T));
+    // returns DRCVAR_OK after launching, a negative error, or 1 when the path does not apply (fall through)
+    auto run_pipelined = [&](auto pk, int threads, size_t psmem, long long row_samples, const KernelArgs& base) -> int {
+      const long long rows_all = (c.N + row_samples - 1) / row_samples;
+      if (rows_all * per_load > 32 * kMaskWords || psmem > static_cast<size_t>(di->max_smem_optin)) return 1;
       CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem)));
       int p_per_sm = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p_per_sm, pk, kThreads, psmem));
-      if (p_per_sm >= 1) {
-        int* redo = nullptr;   // redo flag of halfspace b at redo[b]; stream-ordered allocation, freed on every path below
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&redo), sizeof(int) * static_cast<size_t>(c.B), stream));
-        auto pass = [&]() -> cudaError_t {
-          cudaError_t e = cudaMemsetAsync(redo, 0, sizeof(int) * static_cast<size_t>(c.B), stream);
-          if (e != cudaSuccess) return e;
-          KernelArgs pa = a;
-          pa.redo_list = redo;
-          const long long pgrid = std::min<long long>(c.B, static_cast<long long>(p_per_sm) * di->sms);
-          pk<<<static_cast<unsigned>(pgrid), kThreads, psmem, stream>>>(pa);
-          e = cudaGetLastError();
-          if (e != cudaSuccess) return e;
-          g_launches.fetch_add(1);
-          KernelArgs ra = a;   // the streaming kernel places its own windows (and learns them after two misses in a row)
-          ra.redo_list = redo;
-          ra.bulk = 1;
-          const long long rgrid = std::min<long long>(c.B, di->sms);
-          streaming_kernel<T, false><<<static_cast<unsigned>(rgrid), kStreamThreads, 0, stream>>>(ra);
-          e = cudaGetLastError();
-          if (e == cudaSuccess) g_launches.fetch_add(1);
-          return e;
-        };
-        const cudaError_t pe = pass();
-        const cudaError_t fe = cudaFreeAsync(redo, stream);
-        if (pe != cudaSuccess || fe != cudaSuccess)
-          return fail(DRCVAR_ERR_CUDA, "pipelined kernel path failed: %s", cudaGetErrorString(pe != cudaSuccess ? pe : fe));
-        return DRCVAR_OK;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p_per_sm, pk, threads, psmem));
+      if (p_per_sm < 1) return 1;
+      int* redo = nullptr;   // redo flag of halfspace b at redo[b]; stream-ordered allocation, freed on every path below
+      CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&redo), sizeof(int) * static_cast<size_t>(c.B), stream));
+      auto pass = [&]() -> cudaError_t {
+        cudaError_t e = cudaMemsetAsync(redo, 0, sizeof(int) * static_cast<size_t>(c.B), stream);
+        if (e != cudaSuccess) return e;
+        KernelArgs pa = base;
+        pa.redo_list = redo;
+        const long long pgrid = std::min<long long>(c.B, static_cast<long long>(p_per_sm) * di->sms);
+        pk<<<static_cast<unsigned>(pgrid), threads, psmem, stream>>>(pa);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        g_launches.fetch_add(1);
+        KernelArgs ra = a;   // the streaming kernel places its own windows (and learns them after two misses in a row)
+        ra.redo_list = redo;
+        ra.bulk = 1;
+        const long long rgrid = std::min<long long>(c.B, di->sms);
+        streaming_kernel<T, false><<<static_cast<unsigned>(rgrid), kStreamThreads, 0, stream>>>(ra);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) g_launches.fetch_add(1);
+        return e;
+      };
+      const cudaError_t pe = pass();
+      const cudaError_t fe = cudaFreeAsync(redo, stream);
+      if (pe != cudaSuccess || fe != cudaSuccess)
+        return fail(DRCVAR_ERR_CUDA, "pipelined kernel path failed: %s", cudaGetErrorString(pe != cudaSuccess ? pe : fe));
+      return DRCVAR_OK;
+    };
+    const bool applies = !tail && c.gen_mean == nullptr && a.bulk && a.use_window && !(c.flags & DRCVAR_FLAG_NO_PIPELINE) && !env_off &&
+                         c.B < 0x7fffffffLL;
+    if constexpr (sizeof(T) == 4) {
+      if (applies) {
+        const int r = run_pipelined(pipelined_kernel<float, 8>, pipelined_threads<8>(),
+                                    slot_bytes_for(c.N, 4) + pipelined_fixed_smem_bytes<8>(4), 512, a);
+        if (r <= 0) return r;
+      }
+    } else {
+      // fp64 samples: 16 sweep warps + placer warp in the one CTA per SM the 160 KB slot allows (DRCVAR_PIPELINE_F64=16);
+      // =8 runs the two-CTA layout of the fp32 path (measured slower than halfspace_kernel<double>), 0 = halfspace_kernel<double>
+      if (applies && env_f64 == 16) {
+        KernelArgs pa = a;   // second moments on rows 0, 4, 8, ... of 512 samples: re-plan the window for that subsample
+        const long long rows = (c.N + 511) / 512, r4 = (rows + 3) / 4, last = (r4 - 1) * 4 * 512;
+        const long long ns16 = (r4 - 1) * 512 + std::min<long long>(512, c.N - last);
+        if (plan_window(c.N, kc, ns16, 0.6 * PCaps<16>::kCandCap * 16, &pa.z_lo, &pa.z_hi)) {
+          pa.z_mid_f = static_cast<float>(0.5 * (pa.z_lo + pa.z_hi));
+          pa.z_half_f = static_cast<float>(0.5 * (pa.z_hi - pa.z_lo));
+          pa.z_lo_f = pa.z_mid_f - pa.z_half_f;
+          pa.z_hi_f = pa.z_mid_f + pa.z_half_f;
+          pa.z_half_adapt_f = 2.5f * pa.z_half_f;
+          const int r = run_pipelined(pipelined_kernel<double, 16>, pipelined_threads<16>(),
+                                      slot_bytes_for(c.N, 8) + pipelined_fixed_smem_bytes<16>(8), 512, pa);
+          if (r <= 0) return r;
+        }
+      } else if (applies && env_f64 == 8) {
+        const int r = run_pipelined(pipelined_kernel<double, 8>, pipelined_threads<8>(),
+                                    slot_bytes_for(c.N, 8) + pipelined_fixed_smem_bytes<8>(8), 256, a);
+        if (r <= 0) return r;
       }
     }
   }

@@ -50,21 +50,41 @@ struct PBars {
 constexpr int kPBarCount = kSweepThreads + 32;   // every named barrier: the 8 sweep warps arrive, one helper warp waits
 constexpr int kPOverflowBit = 1 << 30;
 
+// Sweep warps per CTA: 8 (two CTAs per SM: fp32 samples) or 16 (fp64 samples: the 160 KB slot allows ONE CTA per SM, so the
+// CTA itself brings the warps that hide the sweeps' latency; per-warp list capacities halve with the per-warp share).
+template <int W> struct PCaps {
+  static constexpr int kWarpCand = W == 8 ? drcvar::kWarpCand : 80;   // doubles per sweep warp in the candidate buffer ...
+  static constexpr int kCandCap = W == 8 ? drcvar::kCandCap : 48;     // ... of which candidate losses (the rest: per-lane sums)
+  static constexpr int kWarpList = W == 8 ? drcvar::kWarpList : 80;   // masked samples (raw copies) per sweep warp
+};
+template <int W = 8>
 __host__ __device__ inline size_t pipelined_fixed_smem_bytes(size_t elem_bytes) {
-  return sizeof(double) * 2 * kWarpCand * kSweepWarps   // cand   [2][warps][kWarpCand]
+  return sizeof(double) * 2 * PCaps<W>::kWarpCand * W   // cand   [2][warps][kWarpCand]
          + sizeof(unsigned) * 2 * kHistBuckets          // hist   [2][256]
-         + sizeof(double) * 2 * kRedDoubles             // red    [2]
-         + sizeof(double) * 2 * kFinDoubles             // fin    [2]
+         + sizeof(double) * 2 * (W * 8)                 // red    [2]
+         + sizeof(double) * 2 * (W * 4)                 // fin    [2]
          + sizeof(double) * 2 * kResolveMax             // small  [2]
-         + sizeof(int) * 2 * 2 * kSweepWarps            // ired   [2][warps][2]
-         + 2 * elem_bytes * kWarpList * kSweepWarps     // raw copies of the masked samples [warps][kWarpList]
+         + sizeof(int) * 2 * 2 * W                      // ired   [2][warps][2]
+         + 2 * elem_bytes * PCaps<W>::kWarpList * W     // raw copies of the masked samples [warps][kWarpList]
+         + (W == 16 ? sizeof(double) * 2 * 256 : 0)     // xch    (W = 16: slots 256..511 on their way to threads 0..255)
          + 2 * sizeof(PWin) + 2 * sizeof(PHand) + 4 * sizeof(PZState) + sizeof(Ctl) + sizeof(PBars);
 }
+template <int W> __host__ __device__ constexpr int pipelined_threads() { return W * 32 + 64 + (W == 16 ? 32 : 0); }   // W = 16: + placer warp
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs a) {
+template <typename T, int W = 8>
+__global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipelined_kernel(const KernelArgs a) {
   using V2 = typename Vec2<T>::type;
   constexpr bool kF32 = sizeof(T) == 4;
+  static_assert(W == 8 || (W == 16 && !kF32), "16 sweep warps: fp64 samples (one thread per slot of the 512-wide canonical tree)");
+  // the names of halfspace_kernel.cuh, for THIS instantiation's team size (they shadow the namespace-level constants)
+  constexpr int kSweepWarps = W, kSweepThreads = W * 32, kThreads = pipelined_threads<W>();
+  constexpr int kFinisherWarp = W, kDirectorWarp = W + 1, kPlacerWarp = W + 2;   // (placer: W = 16 only)
+  constexpr int kPBarCount = kSweepThreads + 32;
+  constexpr int kWarpCand = PCaps<W>::kWarpCand, kCandCap = PCaps<W>::kCandCap, kWarpList = PCaps<W>::kWarpList;
+  constexpr int kRedDoubles = W * 8, kFinDoubles = W * 4;
+  constexpr uint32_t kRowBytes = 16u * kSweepThreads;                 // one 16-byte load per sweep thread
+  constexpr int kRowsPerChunk = kBulkChunk / kRowBytes;
+  constexpr bool kPlacer = W == 16;                                   // window placement on its own warp, next to the director's chain
   constexpr int kPerLoad = kF32 ? 2 : 1;
   constexpr int kRowSamples = kSweepThreads * kPerLoad;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -79,7 +99,8 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
   double* small_base = fin_base + 2 * kFinDoubles;
   int* ired_base = reinterpret_cast<int*>(small_base + 2 * kResolveMax);
   V2* list_base = reinterpret_cast<V2*>(ired_base + 2 * 2 * kSweepWarps);
-  PWin* win_base = reinterpret_cast<PWin*>(list_base + kWarpList * kSweepWarps);
+  double* xch = reinterpret_cast<double*>(list_base + kWarpList * kSweepWarps);
+  PWin* win_base = reinterpret_cast<PWin*>(xch + (W == 16 ? 2 * 256 : 0));
   PHand* hand_base = reinterpret_cast<PHand*>(win_base + 2);
   PZState* zring = reinterpret_cast<PZState*>(hand_base + 2);
   Ctl* fscr = reinterpret_cast<Ctl*>(zring + 4);   // finisher-private scratch of select_rank (dense buckets only)
@@ -282,7 +303,10 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
 
   // ============================================================================================ director warp
   // window placement first (the team is waiting for it), then the canonical direction and the mean halfspace
-  if (warp == kDirectorWarp) {
+  if (warp == kDirectorWarp || (kPlacer && warp == kPlacerWarp)) {
+    const bool do_window = !kPlacer || warp == kPlacerWarp;   // no placer warp: the director does both, window first
+    const bool do_canon = warp == kDirectorWarp;
+    constexpr int kADoneCount = kPBarCount + (kPlacer ? 32 : 0);
     const double inv_n = 1.0 / static_cast<double>(N);
     double inv_sub = inv_n;   // 1 / (#samples in the second moments): all samples (fp32) / every 4th row (fp64)
     if (!kF32) {
@@ -297,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
       const int par = iter & 1;
       PWin* win = win_base + par;
       const double* red = red_base + par * kRedDoubles;
-      if (lane == 0) {
+      if (lane == 0 && do_canon) {
         const long long b_pf = b + gridDim.x;
         if (b_pf < a.B) bulk_prefetch_l2(src_of(b_pf), copy_bytes & ~15u);
       }
@@ -311,20 +335,20 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
       }
       // learned-window state with a fixed lag of three halfspaces (deterministic)
       PZState zs{0.f, 0, 0, 0};
-      if (iter >= 3) {
+      if (do_window && iter >= 3) {
         mbar_wait(&bars->empty[(iter - 3) & 1], ((iter - 3) >> 1) & 1);
         zs = zring[(iter - 3) & 3];
       }
-      bar_sync(kBarADone + par, kPBarCount);   // red[par] is complete
+      bar_sync(kBarADone + par, kADoneCount);   // red[par] is complete
       // ---------------------------------------------------------------- window placement (speed only, never the result)
       double w[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        double t[kSweepWarps];
+        double t[8];   // the 8 group totals of the 256-wide canonical tree (sweep warps 0..7 in both team sizes)
 #pragma unroll
-        for (int g = 0; g < kSweepWarps; ++g) t[g] = red[g * 8 + j];
+        for (int g = 0; g < 8; ++g) t[g] = red[g * 8 + j];
 #pragma unroll
-        for (int n = kSweepWarps; n > 1; n >>= 1)
+        for (int n = 8; n > 1; n >>= 1)
 #pragma unroll
           for (int g = 0; g < n / 2; ++g) t[g] = __dadd_rn(t[2 * g], t[2 * g + 1]);  // adjacent-pair tree (canonical)
         w[j] = t[0];
@@ -368,8 +392,8 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->hdone[par]);
       };
-      if constexpr (!kF32) canonical_chain();  // fp64 samples classify with the canonical direction: it goes first
-      {
+      if (!kF32 && !kPlacer) canonical_chain();  // fp64 samples classify with the canonical direction: it goes first
+      if (do_window) {
         const float* redf = reinterpret_cast<const float*>(red);   // warp g: floats 4..9 of its 16 = qxx,qyy,qxy,bound,mdx,mdy
         float q[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         float b2 = 0.f;
@@ -475,7 +499,8 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->wdone[par]);
       }
-      if constexpr (kF32) canonical_chain();   // fp32 samples: after the window (the team classifies with the fp32 direction)
+      if (!do_canon) continue;   // (placer warp: done with this halfspace)
+      if (kF32 || kPlacer) canonical_chain();   // fp32 samples: after the window (the team classifies with the fp32 direction)
       // TMA producer: as soon as all 8 sweep warps are done with the sample slot, fetch the next halfspace
       bar_sync(kBarSlotFree + par, kPBarCount);
       {
@@ -577,6 +602,50 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
         q_yy = sq.y;
         q_xy = sxy;
         bound2 = sq.x + sq.y;
+      } else if constexpr (W == 16) {
+        // 512 sweep threads: thread t IS slot t of the canonical 512-slot sum (samples i = t mod 512 in increasing i: one
+        // chain per coordinate); slots 256..511 then travel through shared memory to threads 0..255 (u[j] = s[j] + s[j+256])
+        double s0 = 0.0, s1 = 0.0;
+        q_xx = q_yy = q_xy = 0.0;
+        auto acc_row = [&](const V2 v, bool mom) {
+          s0 = __dadd_rn(s0, v.x);
+          s1 = __dadd_rn(s1, v.y);
+          if (mom) {
+            const double dx = v.x - first.x, dy = v.y - first.y;
+            q_dx += dx;
+            q_dy += dy;
+            q_xx = fma(dx, dx, q_xx);
+            q_yy = fma(dy, dy, q_yy);
+            q_xy = fma(dx, dy, q_xy);
+          }
+        };
+        auto rows = [&](int r_lo, int r_hi) {   // r_lo is a multiple of 4
+          int r = r_lo;
+          const int g_hi = r_lo + (((r_hi < full_rows ? r_hi : full_rows) - r_lo) & ~3);
+#pragma unroll 1
+          for (; r < g_hi; r += 4) {
+            V2 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = sm[(r + k) * kRowSamples + tid];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc_row(v[k], k == 0);
+          }
+          for (; r < r_hi; ++r) {
+            const int i = r * kRowSamples + tid;
+            if (i < N) acc_row(sm[i], (r & 3) == 0);
+          }
+        };
+        const int r_first = rows_all < kRowsPerChunk ? rows_all : kRowsPerChunk;
+        rows(0, r_first);
+        wait_rest();
+        rows(r_first, rows_all);
+        if (tid >= 256) {
+          xch[2 * (tid - 256)] = s0;
+          xch[2 * (tid - 256) + 1] = s1;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kSweepThreads) : "memory");   // the one barrier inside this team (xch is reused a halfspace later)
+        u_x = tid < 256 ? __dadd_rn(s0, xch[2 * tid]) : 0.0;
+        u_y = tid < 256 ? __dadd_rn(s1, xch[2 * tid + 1]) : 0.0;
       } else {
         double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
         q_xx = q_yy = q_xy = 0.0;
@@ -642,7 +711,7 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
         }
       }
       __syncwarp();
-      bar_arrive(kBarADone + par, kPBarCount);   // the director places the window of halfspace `it`
+      bar_arrive(kBarADone + par, kPBarCount + (kPlacer ? 32 : 0));   // director (and placer) take over from here
     }
 
     // ------------------------------------------------------------------ deferred exact phase (2b) of halfspace it-1
@@ -834,11 +903,11 @@ __global__ void __launch_bounds__(kThreads, 2) pipelined_kernel(const KernelArgs
           for (int wd = 0; wd < kMaskWords; ++wd) {
             if (wd * 32 < rows_all * kPerLoad) {
               unsigned mm = mask[wd];
-              const unsigned char* wbase = tbase + (kF32 ? 16u : 32u) * 4096u * wd;
+              const unsigned char* wbase = tbase + (kF32 ? 16u : 32u) * kRowBytes * wd;
               while (mm) {
                 const unsigned bp = 31u - static_cast<unsigned>(__clz(static_cast<int>(mm)));
                 mm ^= 1u << bp;
-                const unsigned off = kF32 ? (((bp & 30u) << 11) | ((bp & 1u) << 3)) : (bp << 12);
+                const unsigned off = kF32 ? ((bp >> 1) * kRowBytes + ((bp & 1u) << 3)) : bp * kRowBytes;
                 DRCVAR_ASSERT(dst < wlist + kWarpList && (wbase + off) + sizeof(V2) <= smem_raw + slot_bytes);
                 *dst++ = *reinterpret_cast<const V2*>(wbase + off);
               }
