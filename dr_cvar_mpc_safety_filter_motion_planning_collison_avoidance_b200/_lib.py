@@ -18,6 +18,7 @@ OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4
 FLAG_SYNC, FLAG_GENERAL_ONLY, FLAG_NO_BULK, FLAG_FORCE_STREAMING, FLAG_NO_CLUSTER, FLAG_FORCE_CLUSTER = 1, 2, 4, 8, 16, 32
 FLAG_NO_PIPELINE = 64
+FLAG_LARGE_COORDS = 128   # fp32 samples far from the origin: first-sample-relative sums in the pipelined kernel (speed only)
 STATUS_NONFINITE, STATUS_GENERAL, STATUS_DEGENERATE = 1, 2, 4
 
 _dp = C.POINTER(C.c_double)

@@ -388,8 +388,14 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
                          c.B < 0x7fffffffLL;
     if constexpr (sizeof(T) == 4) {
       if (applies) {
-        const int r = run_pipelined(pipelined_kernel<float, 8>, pipelined_threads<8>(),
-                                    slot_bytes_for(c.N, 4) + pipelined_fixed_smem_bytes<8>(4), 512, a);
+        // raw-coordinate sweep B unless the caller says the coordinates are far from the origin (or DRCVAR_LARGE_COORDS=1):
+        // halfspaces too large for raw fp32 sums are handed to the redo pass, so the flag only ever changes the speed
+        static const bool env_large = getenv("DRCVAR_LARGE_COORDS") != nullptr;
+        const bool large = (c.flags & DRCVAR_FLAG_LARGE_COORDS) || env_large;
+        const int r = large ? run_pipelined(pipelined_kernel<float, 8, false>, pipelined_threads<8>(),
+                                            slot_bytes_for(c.N, 4) + pipelined_fixed_smem_bytes<8>(4), 512, a)
+                            : run_pipelined(pipelined_kernel<float, 8, true>, pipelined_threads<8>(),
+                                            slot_bytes_for(c.N, 4) + pipelined_fixed_smem_bytes<8>(4), 512, a);
         if (r <= 0) return r;
       }
     } else {

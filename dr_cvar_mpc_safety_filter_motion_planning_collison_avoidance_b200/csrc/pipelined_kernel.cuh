@@ -26,7 +26,7 @@
 namespace drcvar {
 
 struct PHand {                     // what the finisher needs of a halfspace: copied out of PWin at the hand-over
-  double h0, h1, hn, f0, f1, t_hi, c_shift;
+  double h0, h1, hn, f0, f1, t_hi, c_shift;   // (f0, f1): origin of the fp32 "above" sums = first sample, or (0, 0) in raw mode
   unsigned long long key_lo;
   float pm, sigma;
   int hist_shift, degenerate;
@@ -50,8 +50,6 @@ struct PBars {
 constexpr int kPBarCount = kSweepThreads + 32;   // every named barrier: the 8 sweep warps arrive, one helper warp waits
 constexpr int kPOverflowBit = 1 << 30;
 
-// Sweep warps per CTA: 8 (two CTAs per SM: fp32 samples) or 16 (fp64 samples: the 160 KB slot allows ONE CTA per SM, so the
-// CTA itself brings the warps that hide the sweeps' latency; per-warp list capacities halve with the per-warp share).
 template <int W> struct PCaps {
   static constexpr int kWarpCand = W == 8 ? drcvar::kWarpCand : 80;   // doubles per sweep warp in the candidate buffer ...
   static constexpr int kCandCap = W == 8 ? drcvar::kCandCap : 48;     // ... of which candidate losses (the rest: per-lane sums)
@@ -71,10 +69,15 @@ __host__ __device__ inline size_t pipelined_fixed_smem_bytes(size_t elem_bytes) 
 }
 template <int W> __host__ __device__ constexpr int pipelined_threads() { return W * 32 + 64 + (W == 16 ? 32 : 0); }   // W = 16: + placer warp
 
-template <typename T, int W = 8>
+// kRawB (fp32 samples): sweep B classifies and sums the RAW coordinates instead of the coordinates relative to the first sample
+// (one FADD2 less per sample).  Raw fp32 partial sums are only as good as the coordinates are small, so a halfspace whose
+// coordinates are too large for them (see `raw_ok` in the window placement) is handed to the redo pass; callers whose frames
+// are far from the origin select the shifted instantiation (DRCVAR_FLAG_LARGE_COORDS), which has no such limit.
+template <typename T, int W = 8, bool kRawB = false>
 __global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipelined_kernel(const KernelArgs a) {
   using V2 = typename Vec2<T>::type;
   constexpr bool kF32 = sizeof(T) == 4;
+  static_assert(!kRawB || kF32, "raw-coordinate sweep B: fp32 samples");
   static_assert(W == 8 || (W == 16 && !kF32), "16 sweep warps: fp64 samples (one thread per slot of the 512-wide canonical tree)");
   // the names of halfspace_kernel.cuh, for THIS instantiation's team size (they shadow the namespace-level constants)
   constexpr int kSweepWarps = W, kSweepThreads = W * 32, kThreads = pipelined_threads<W>();
@@ -264,6 +267,8 @@ __global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipeli
 #pragma unroll 1
             for (int w = 0; w < kSweepWarps; ++w) s_e += fin[w * 4 + 2];
           }
+          // fp32 samples: the "above" set through linearity; its coordinate sums are relative to (f0, f1) = the first sample,
+          // or to the origin when sweep B ran on raw coordinates
           const double s_lin = -(hd->h0 * (n_lin * hd->f0 + s_x) + hd->h1 * (n_lin * hd->f1 + s_y));
           const double s_tot = ((s_e + s_lin) + s3t) + s4;
           const int c_tot = cnt_hi + c3t + c4;
@@ -476,16 +481,35 @@ __global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipeli
         const float af0 = fabsf(static_cast<float>(f0)) * 1.0001f, af1 = fabsf(static_cast<float>(f1)) * 1.0001f;
         const float habs = fabsf(h0f) + fabsf(h1f);
         const float eps = (habs * (af0 + af1 + dmax)) * 1e-15f + err_h * 1.5f * (af0 + af1 + 2.0f * dmax);
-        const float bound = habs * dmax * 1.9073486e-06f + 1.1754944e-38f + eps * 1.0001f;
-        const float thr_keep = a_lo + (bound + fabsf(a_lo) * 2.3841858e-07f);
-        const float thr_above = a_hi - (bound + fabsf(a_hi) * 2.3841858e-07f);
+        float thr_keep, thr_above;
+        bool raw_ok = true;
+        if constexpr (kRawB) {
+          // Sweep B classifies p = fma(h1f, y, h0f * x) of the RAW coordinates and sums them as they are.
+          //   |p - h_a.xi| <= 2^-24 (|h0f x| + |p|) <= 2^-23 habs vmax (1 + 2^-24), vmax = |first| + dmax; taken twice over.
+          //   The window edges move into that space through c = h_a . first (double) and one rounding to fp32 (2^-24 |edge|;
+          //   2^-21 |edge| is allowed for it and for the additions below).
+          // The per-thread sums of the "above" set are chains of m = kc / 256 fp32 adds, each within 2^-24 of a partial sum
+          // <= m vmax; the finisher adds the 256 of them in fp64: the CVaR moves by about 2^-24 (m vmax / 2) / sqrt(kc).  With
+          // m vmax <= 256 that is 2.4e-7 at kc = 1 000 (1e-8 typical at |xi| < 8, config 4).  Larger coordinates: redo pass.
+          const float vmax = af0 + af1 + dmax;
+          const float m_adds = fmaxf(1.0f, static_cast<float>(a.kc) * (1.0f / kSweepThreads));
+          raw_ok = vmax * m_adds <= 256.0f;
+          const float bound = habs * vmax * 2.3841858e-07f + 1.1754944e-38f + eps * 1.0001f;
+          const float r_lo = static_cast<float>(static_cast<double>(a_lo) + c), r_hi = static_cast<float>(static_cast<double>(a_hi) + c);
+          thr_keep = r_lo + (bound + fabsf(r_lo) * 4.7683716e-07f);
+          thr_above = r_hi - (bound + fabsf(r_hi) * 4.7683716e-07f);
+        } else {
+          const float bound = habs * dmax * 1.9073486e-06f + 1.1754944e-38f + eps * 1.0001f;
+          thr_keep = a_lo + (bound + fabsf(a_lo) * 2.3841858e-07f);
+          thr_above = a_hi - (bound + fabsf(a_hi) * 2.3841858e-07f);
+        }
         const unsigned long long klo = key_of(t_lo), khi = key_of(t_hi);
         const unsigned long long span = khi - klo;
         const int bits = span ? 64 - __clzll(static_cast<long long>(span)) : 0;
         window_ok = window_ok && isfinite(thr_keep) && isfinite(thr_above) && (khi >= klo) && (thr_above <= thr_keep) &&
-                    isfinite(t_lo) && isfinite(t_hi);
+                    isfinite(t_lo) && isfinite(t_hi) && raw_ok;
         if (lane == 0) {
-          win->hand.f0 = f0; win->hand.f1 = f1;
+          win->hand.f0 = kRawB ? 0.0 : f0; win->hand.f1 = kRawB ? 0.0 : f1;
           win->t_lo = t_lo;
           win->hand.t_hi = t_hi;
           win->h0f = h0f; win->h1f = h1f; win->thr_keep = thr_keep; win->thr_above = thr_above;
@@ -733,7 +757,7 @@ __global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipeli
       const double t_lo = win->t_lo, t_hi = win->hand.t_hi;
       const unsigned long long klo = win->hand.key_lo;
       const int hshift = win->hand.hist_shift;
-      const float pfx = static_cast<float>(win->hand.f0), pfy = static_cast<float>(win->hand.f1);   // shift origin of it-1
+      const float pfx = static_cast<float>(win->hand.f0), pfy = static_cast<float>(win->hand.f1);   // origin of it-1's "above" sums
       bool overflow = n_list_prev < 0;
       int nc = 0;
       float ax = ax_prev, ay = ay_prev, cf = cf_prev;
@@ -808,8 +832,10 @@ __global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipeli
         if constexpr (kF32) {
           const float4* sm4 = reinterpret_cast<const float4*>(smem_raw);
           const float h0f = win->h0f, h1f = win->h1f, thr_keep = win->thr_keep, thr_above = win->thr_above;
-          const float2 nf = make_float2(-first.x, -first.y);
           const int full4 = full_rows & ~3;
+          // kRawB: coordinates as they are (thresholds are in that space); otherwise relative to the first sample
+          const float2 nf = make_float2(-first.x, -first.y);
+          auto shifted = [&](float x, float y) { return kRawB ? make_float2(x, y) : __fadd2_rn(make_float2(x, y), nf); };
 #pragma unroll
           for (int wd = 0; wd < kMaskWords; ++wd) {
             const int r_lo = wd * kRowsPerWord;
@@ -818,7 +844,7 @@ __global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipeli
 #pragma unroll 4
             for (int r = r_lo; r < r_hi; ++r) {
               const float4 v = sm4[r * kSweepThreads + tid];
-              const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nf), d1 = __fadd2_rn(make_float2(v.z, v.w), nf);
+              const float2 d0 = shifted(v.x, v.y), d1 = shifted(v.z, v.w);
               const float p0 = fmaf(h1f, d0.y, h0f * d0.x), p1 = fmaf(h1f, d1.y, h0f * d1.x);
               classify_f32(p0, thr_above, thr_keep, d0.x, d0.y, ax, ay, cf, mask[wd], bit);
               classify_f32(p1, thr_above, thr_keep, d1.x, d1.y, ax, ay, cf, mask[wd], bit + bit);
@@ -834,7 +860,7 @@ __global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipeli
               const int rr = row < rows_all ? row : rows_all - 1;
               const float4 v = sm4[rr * kSweepThreads + tid];
               const int i0 = row * kRowSamples + 2 * tid;
-              const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nf), d1 = __fadd2_rn(make_float2(v.z, v.w), nf);
+              const float2 d0 = shifted(v.x, v.y), d1 = shifted(v.z, v.w);
               float p0 = fmaf(h1f, d0.y, h0f * d0.x), p1 = fmaf(h1f, d1.y, h0f * d1.x);
               if (i0 >= N) p0 = __int_as_float(0x7f800000);
               if (i0 + 1 >= N) p1 = __int_as_float(0x7f800000);

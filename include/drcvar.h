@@ -58,6 +58,9 @@ extern "C" {
 #define DRCVAR_FLAG_NO_CLUSTER 16u   /* large N: do not use the cluster / DSMEM single-read kernel (streaming kernel instead) */
 #define DRCVAR_FLAG_FORCE_CLUSTER 32u /* fp64 samples, large N: use the fp64 cluster kernel (opt-in: the streaming kernel is faster there) */
 #define DRCVAR_FLAG_NO_PIPELINE 64u  /* resident sizes: use halfspace_kernel (inline general path) instead of the pipelined kernel + redo pass */
+#define DRCVAR_FLAG_LARGE_COORDS 128u /* fp32 samples at resident sizes whose coordinates are far from the origin (|xi| beyond ~64 / (alpha N / 256)):
+                                         keep the first-sample-relative sums of the pipelined kernel.  Without it such halfspaces are still exact
+                                         (handed to the redo pass) but slower; with it small coordinates lose ~3 % of throughput.  Speed only. */
 
 /* per-halfspace status bits written to status_out */
 #define DRCVAR_STATUS_NONFINITE 1   /* non-finite input: sentinel 100.0 emitted (core/risk_metrics.py:177,265,303,338) */

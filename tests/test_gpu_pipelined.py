@@ -141,3 +141,41 @@ def test_pipelined_with_explicit_normals_and_padded_rows(eng):
     assert eng.launch_count() - l0 == 2
     ref = eng.compute_halfspaces(s, ego, **PARAMS)
     assert np.array_equal(d.var.cpu().numpy(), ref.var) and np.array_equal(d.g.cpu().numpy(), ref.g)
+
+
+def test_raw_coordinate_sweep_bounds(eng):
+    """fp32 samples, default instantiation (pipelined_kernel<float, 8, true>): sweep B classifies and sums the RAW coordinates
+    (no shift by the first sample; thresholds moved into that space with a rigorous rounding bound); halfspaces whose
+    coordinates are too large for raw fp32 sums (|xi| m > 256, m = kc / 256 adds per thread) go to the redo pass.  The regime where
+    that bound matters is offset / spread = 1e2 ... 1e5 (the fp32 band becomes comparable to the window): thresholds must stay
+    bit-exact against the exact general select, offsets within 1e-6 m of it and of the oracle; larger coordinates (shifted
+    sums) sit in the same batch."""
+    from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import _lib
+    rng = np.random.RandomState(77)
+    n = 10000
+    B = 296 * 4
+    off = rng.choice([0.5, 3.0, 12.0, 30.0, 44.0, 70.0, 300.0], size=B)
+    ratio = 10.0 ** rng.uniform(1.0, 5.0, size=B)
+    sigma = np.maximum(off, 0.5) / ratio
+    ang = rng.uniform(0, 2 * np.pi, size=B)
+    mu = off[:, None] * np.stack([np.cos(ang), np.sin(ang)], axis=1)
+    s = (mu[:, None, :] + sigma[:, None, None] * rng.standard_normal((B, n, 2)) * np.array([1.0, 0.7])).astype(np.float32)
+    ego = np.where(rng.random((B, 1)) < 0.5, 0.0, mu + rng.uniform(-2, 2, size=(B, 2)))
+    for alpha in (0.1, 0.03, 0.4):
+        p = dict(PARAMS, alpha=alpha)
+        a = eng.compute_halfspaces(s, ego, **p)
+        exact = eng.compute_halfspaces(s, ego, flags=_lib.FLAG_GENERAL_ONLY, **p)
+        assert np.array_equal(a.var, exact.var) and np.array_equal(a.h, exact.h), alpha
+        tol = 1e-6 * np.maximum(1.0, sigma)[:, None]
+        assert np.all(np.abs(a.g - exact.g) <= tol), (alpha, np.abs(a.g - exact.g).max())
+        rel = eng.compute_halfspaces(s, ego, flags=_lib.FLAG_LARGE_COORDS, **p)   # the first-sample-relative instantiation
+        assert np.array_equal(rel.var, exact.var) and np.array_equal(rel.h, exact.h), alpha
+        assert np.all(np.abs(rel.g - exact.g) <= tol), (alpha, np.abs(rel.g - exact.g).max())
+        if alpha == 0.1:
+            direct = (a.status & _lib.STATUS_GENERAL) == 0
+            assert direct[(off < 35) & (ratio > 100) & (ratio < 3e3)].all()        # the raw window path is the one under test
+            # (off >= 70: too large for raw fp32 sums - the redo pass computes them; the bars above hold for them all the same)
+            assert ((rel.status & _lib.STATUS_GENERAL) == 0)[(off < 35) & (ratio > 100) & (ratio < 3e3)].all()
+        for k in range(0, B, 97):
+            o = cf.halfspace(s[k], ego[k], p["alpha"], p["delta"], p["epsilon"], p["robot_radius"], p["obstacle_radius"])
+            assert a.var[k] == o.var and abs(a.g[k, 1] - o.g_cvar) <= tol[k, 0], (alpha, k)
