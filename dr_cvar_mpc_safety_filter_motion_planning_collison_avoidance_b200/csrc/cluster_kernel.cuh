@@ -143,7 +143,9 @@ __device__ __forceinline__ double pair_tree8(const double* t_in, int stride) {
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-template <bool kGen, bool kTail = false>
+// kRawB: sweep B classifies and sums the RAW coordinates instead of the coordinates relative to the first sample (one FADD2
+// less per sample; same bound and same hand-back rule as pipelined_kernel<float, 8, true>, see pipelined_kernel.cuh).
+template <bool kGen, bool kTail = false, bool kRawB = false>
 __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const KernelArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -309,7 +311,9 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         s4 = warp_sum_any(s4);
         if (lane == 0) {
           // loss sum of the "surely above" set by linearity, xi_i = f + d_i:  sum_i -(h.xi_i) = -(h0 (n f0 + sum dx) + h1 (n f1 + sum dy))
-          const double s_lin = -(fc->h0 * (n_above * fc->f0 + sdx) + fc->h1 * (n_above * fc->f1 + sdy));
+          // (kRawB: the sums are of the raw coordinates)
+          const double s_lin = kRawB ? -(fc->h0 * sdx + fc->h1 * sdy)
+                                     : -(fc->h0 * (n_above * fc->f0 + sdx) + fc->h1 * (n_above * fc->f1 + sdy));
           write_risk_outputs(a, b, fc, false, s_lin + s4, cnt_hi + c4, T_thr, fc->degenerate ? kStatusDegenerate : 0);
         }
         if constexpr (kTail) {
@@ -656,12 +660,24 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
       const float af0 = fabsf(static_cast<float>(f0)) * 1.0001f, af1 = fabsf(static_cast<float>(f1)) * 1.0001f;
       const float habs = fabsf(h0f) + fabsf(h1f);
       const float eps = (habs * (af0 + af1 + dmax)) * 1e-15f + err_h * 1.5f * (af0 + af1 + 2.0f * dmax);
-      const float bound = habs * dmax * 1.9073486e-06f + 1.1754944e-38f + eps * 1.0001f;
-      const float thr_keep = a_lo + (bound + fabsf(a_lo) * 2.3841858e-07f);
-      const float thr_above = a_hi - (bound + fabsf(a_hi) * 2.3841858e-07f);
+      float thr_keep, thr_above;
+      bool raw_ok = true;
+      if constexpr (kRawB) {   // thresholds in the space of the raw projection; m = kc / (C x 512) adds per thread (pipelined_kernel.cuh)
+        const float vmax = af0 + af1 + dmax;
+        const float m_adds = fmaxf(1.0f, static_cast<float>(a.kc) / static_cast<float>(C * kClTeam));
+        raw_ok = vmax * m_adds <= 256.0f;
+        const float bound = habs * vmax * 2.3841858e-07f + 1.1754944e-38f + eps * 1.0001f;
+        const float r_lo = static_cast<float>(static_cast<double>(a_lo) + c), r_hi = static_cast<float>(static_cast<double>(a_hi) + c);
+        thr_keep = r_lo + (bound + fabsf(r_lo) * 4.7683716e-07f);
+        thr_above = r_hi - (bound + fabsf(r_hi) * 4.7683716e-07f);
+      } else {
+        const float bound = habs * dmax * 1.9073486e-06f + 1.1754944e-38f + eps * 1.0001f;
+        thr_keep = a_lo + (bound + fabsf(a_lo) * 2.3841858e-07f);
+        thr_above = a_hi - (bound + fabsf(a_hi) * 2.3841858e-07f);
+      }
       const unsigned long long klo = key_of(t_lo), khi = key_of(t_hi);
       window_ok = window_ok && isfinite(thr_keep) && isfinite(thr_above) && (khi >= klo) && (thr_above <= thr_keep) &&
-                  isfinite(t_lo) && isfinite(t_hi);
+                  isfinite(t_lo) && isfinite(t_hi) && raw_ok;
       if (lane == 0) {
         ctl->t_lo = t_lo;
         ctl->t_hi = t_hi;
@@ -747,7 +763,8 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         }
       };
       auto classify4 = [&](const float4& v, unsigned& mk, unsigned bit, bool ok0, bool ok1) {
-        const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nf), d1 = __fadd2_rn(make_float2(v.z, v.w), nf);
+        const float2 d0 = kRawB ? make_float2(v.x, v.y) : __fadd2_rn(make_float2(v.x, v.y), nf);
+        const float2 d1 = kRawB ? make_float2(v.z, v.w) : __fadd2_rn(make_float2(v.z, v.w), nf);
         float p0 = fmaf(h1f, d0.y, h0f * d0.x), p1 = fmaf(h1f, d1.y, h0f * d1.x);
         if (!ok0) p0 = __int_as_float(0x7f800000);
         if (!ok1) p1 = __int_as_float(0x7f800000);
@@ -821,8 +838,8 @@ __global__ void __launch_bounds__(kClThreads, 1) cluster_kernel_f32(const Kernel
         const bool cd = active && !up && (L >= t_lo);
         if (up) {  // inside the fp32 uncertainty band but exactly above the window: joins the "above" set
           cf += 1.0f;
-          ax += v.x - first.x;
-          ay += v.y - first.y;
+          ax += kRawB ? v.x : v.x - first.x;
+          ay += kRawB ? v.y : v.y - first.y;
         }
         const unsigned bal = __ballot_sync(kFull, cd);   // (all lanes have read their entry: the ballot orders the overwrite)
         if (cd) wcand[nc + __popc(bal & ((1u << lane) - 1u))] = L;

@@ -258,7 +258,12 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
                                      (row_bytes % 16 == 0));
     const int ctas = cluster_ctas_for(c.N, sizeof(T), static_cast<size_t>(di->max_smem_optin));
     double zl = 0, zh = 0;
-    void (*ck)(const KernelArgs) = sizeof(T) == 4 ? (gen_mode ? cluster_kernel_f32<true> : (tail ? cluster_kernel_f32<false, true> : cluster_kernel_f32<false>))
+    // stored fp32 samples, no tail indices: raw-coordinate sweep B unless the caller's frame is far from the origin
+    static const bool env_large_cl = getenv("DRCVAR_LARGE_COORDS") != nullptr;
+    const bool raw_b = !(c.flags & DRCVAR_FLAG_LARGE_COORDS) && !env_large_cl;
+    void (*ck)(const KernelArgs) = sizeof(T) == 4 ? (gen_mode ? cluster_kernel_f32<true>
+                                                              : (tail ? cluster_kernel_f32<false, true>
+                                                                      : (raw_b ? cluster_kernel_f32<false, false, true> : cluster_kernel_f32<false>)))
                                                   : cluster_kernel_f64;
     const long long cl_n_sigma = sizeof(T) == 4 ? c.N : std::max<long long>(1, c.N / 4);   // fp64: moments on every 4th row
     if (bulk_ok && ctas && plan_window(c.N, kc, cl_n_sigma, 0.7 * kClPool, &zl, &zh)) {
