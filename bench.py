@@ -35,8 +35,6 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--settle-s", type=float, default=1.0, dest="settle_s",
-                    help="idle seconds between generating the synthetic batch and the warm-up (the RNG fill leaves the board power-capped)")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--scenarios", type=int, default=4096)
     ap.add_argument("--obstacles", type=int, default=8)
@@ -480,11 +478,6 @@ def run_ours(a):
         nonlocal out
         out = pkg.compute_halfspaces(samples, ego, stream=stream, out=out, **RISK)
 
-    # generating the synthetic batch (tens of GB of RNG kernels) leaves the board at its power cap; the workload itself starts
-    # from an idle board, so let it settle before the warm-up (stated in config.settle_s; clocks / reasons are still sampled)
-    torch.cuda.synchronize()
-    if a.settle_s > 0:
-        time.sleep(a.settle_s)
     warm = max(a.warmup, 3)
     for _ in range(warm):
         step()
@@ -701,7 +694,6 @@ def run_ours(a):
             "config": {"workload": workload_name(a), "halfspaces_per_gpu": B, "samples_per_halfspace": N,
                        "input_dtype": a.dtype, "parallelism": f"scenario-shard x{world} (no collective on the hot path)",
                        "l2": f"inputs ({need / 1e9:.1f} GB per GPU) are larger than L2; no flush needed",
-                       "settle_s": a.settle_s,
                        "precision": "fp32 samples: fp32 screening with rigorous bounds, exact fp64 threshold / window losses, fp32 "
                                     "partial sums of the surely-above set (1e-5 m north-star bar); fp64 samples: see f64_inputs"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
