@@ -301,6 +301,20 @@ __device__ __forceinline__ void classify_f32(float p, float thr_above, float thr
 
 // exact classification of one fp64 loss, branch-free (the if / else-if form spent 14 % of the fp64 kernel's warp samples
 // resolving divergent branches):  up = L > t_hi: sum and count;  keep = !up && L >= t_lo: `bit` into the mask
+// The same on the canonical PROJECTION p (L = 0 - p, a negation: exact): up = p < -t_hi, keep = !up && p <= -t_lo, and the sum
+// of the projections of the "up" set, whose negative is the sum of their losses bit for bit (round-to-nearest is symmetric).
+// One DADD less per sample than forming L first.
+__device__ __forceinline__ void classify_f64_proj(double p, double nt_hi, double nt_lo, double& sp_gt, int& c_gt, unsigned& mask,
+                                                  unsigned bit) {
+  asm("{\n\t.reg .pred u, k;\n\t"
+      "setp.lt.f64 u, %3, %4;\n\t"
+      "setp.le.and.f64 k, %3, %5, !u;\n\t"
+      "@u add.rn.f64 %0, %0, %3;\n\t"
+      "@u add.s32 %1, %1, 1;\n\t"
+      "@k add.u32 %2, %2, %6;\n\t}"
+      : "+d"(sp_gt), "+r"(c_gt), "+r"(mask)
+      : "d"(p), "d"(nt_hi), "d"(nt_lo), "r"(bit));
+}
 __device__ __forceinline__ void classify_f64(double L, double t_hi, double t_lo, double& s_gt, int& c_gt, unsigned& mask,
                                              unsigned bit) {
   asm("{\n\t.reg .pred u, k;\n\t"
@@ -1313,14 +1327,16 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
           for (int w2 = 0; w2 < kMaskWords; ++w2) mask[w2] |= (w2 == wg) ? mk : 0u;   // selects keep mask[] in registers
         }
       } else {
+        const double nt_hi = -t_hi, nt_lo = -t_lo;   // window edges for the projection p = -L
+        double sp_gt = 0.0;                          // sum of the projections of the losses above the window
 #pragma unroll
         for (int wd = 0; wd < kMaskWords; ++wd) {
           const int r_lo = wd * kRowsPerWord;
           const int r_hi = rows_all < r_lo + kRowsPerWord ? rows_all : r_lo + kRowsPerWord;
           unsigned bit = 1u;
-          auto one = [&](const V2 v, unsigned bt) {   // exact canonical loss of one sample (rows in increasing order: s_gt is deterministic)
-            const double L = loss_of(h0, h1, v.x, v.y);
-            classify_f64(L, t_hi, t_lo, s_gt, c_gt, mask[wd], bt);
+          auto one = [&](const V2 v, unsigned bt) {   // exact canonical projection of one sample (rows in increasing order: the sum is deterministic)
+            const double p = __dadd_rn(__dmul_rn(h0, v.x), __dmul_rn(h1, v.y));
+            classify_f64_proj(p, nt_hi, nt_lo, sp_gt, c_gt, mask[wd], bt);
           };
           int r = r_lo;
           const int g_hi = r_lo + (((r_hi < full_rows ? r_hi : full_rows) - r_lo) & ~3);
@@ -1337,6 +1353,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
             if (i < N) one(sm[i], bit);
           }
         }
+        s_gt = __dsub_rn(0.0, sp_gt);   // sum of the losses, same bits as adding L = 0 - p in the same order (and never -0)
       }
       PH_MARK(4)
 
