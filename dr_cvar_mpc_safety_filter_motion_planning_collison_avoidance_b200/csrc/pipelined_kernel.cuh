@@ -50,6 +50,11 @@ struct PBars {
 constexpr int kPBarCount = kSweepThreads + 32;   // every named barrier: the 8 sweep warps arrive, one helper warp waits
 constexpr int kPOverflowBit = 1 << 30;
 
+// explicit shared-space 8-byte copy for the compaction loop of phase 2a (no generic -> shared conversion, no pointer pairs)
+__device__ __forceinline__ void smem_copy8(uint32_t dst, uint32_t src) {
+  asm volatile("{\n\t.reg .b64 t;\n\tld.shared.b64 t, [%1];\n\tst.shared.b64 [%0], t;\n\t}" ::"r"(dst), "r"(src) : "memory");
+}
+
 template <int W> struct PCaps {
   static constexpr int kWarpCand = W == 8 ? drcvar::kWarpCand : 80;   // doubles per sweep warp in the candidate buffer ...
   static constexpr int kCandCap = W == 8 ? drcvar::kCandCap : 48;     // ... of which candidate losses (the rest: per-lane sums)
@@ -541,6 +546,7 @@ __global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipeli
   uint32_t phase = 0;
   const long long n_it = (a.B - static_cast<long long>(blockIdx.x) + gridDim.x - 1) / gridDim.x;
   V2* wlist = list_base + warp * kWarpList;
+  const uint32_t wlist_s = smem_u32(wlist), tslot_s = smem_u32(smem_raw) + 16u * static_cast<uint32_t>(tid);   // shared-space addresses (phase 2a)
   // state of the previous halfspace carried into its deferred exact phase
   int n_list_prev = -1;                         // -1: nothing usable (window not placed / list overflow)
   float ax_prev = 0.f, ay_prev = 0.f, cf_prev = 0.f;
@@ -832,14 +838,13 @@ __global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipeli
         if constexpr (kF32) {
           const float4* sm4 = reinterpret_cast<const float4*>(smem_raw);
           const float h0f = win->h0f, h1f = win->h1f, thr_keep = win->thr_keep, thr_above = win->thr_above;
-          const int full4 = full_rows & ~3;
           // kRawB: coordinates as they are (thresholds are in that space); otherwise relative to the first sample
           const float2 nf = make_float2(-first.x, -first.y);
           auto shifted = [&](float x, float y) { return kRawB ? make_float2(x, y) : __fadd2_rn(make_float2(x, y), nf); };
 #pragma unroll
-          for (int wd = 0; wd < kMaskWords; ++wd) {
+          for (int wd = 0; wd < kMaskWords; ++wd) {   // all complete rows (groups of four, then the one to three left over)
             const int r_lo = wd * kRowsPerWord;
-            const int r_hi = full4 < r_lo + kRowsPerWord ? full4 : r_lo + kRowsPerWord;
+            const int r_hi = full_rows < r_lo + kRowsPerWord ? full_rows : r_lo + kRowsPerWord;
             unsigned bit = 1u;
 #pragma unroll 4
             for (int r = r_lo; r < r_hi; ++r) {
@@ -851,24 +856,18 @@ __global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipeli
               bit <<= 2;
             }
           }
-          if (full4 < rows_all) {
+          if (full_rows < rows_all) {   // the ragged last row: samples beyond N are neither above nor kept
+            const float4 v = sm4[full_rows * kSweepThreads + tid];
+            const int i0 = full_rows * kRowSamples + 2 * tid;
+            const float2 d0 = shifted(v.x, v.y), d1 = shifted(v.z, v.w);
+            float p0 = fmaf(h1f, d0.y, h0f * d0.x), p1 = fmaf(h1f, d1.y, h0f * d1.x);
+            if (i0 >= N) p0 = __int_as_float(0x7f800000);
+            if (i0 + 1 >= N) p1 = __int_as_float(0x7f800000);
             unsigned mk = 0;
-            unsigned bit = 1u << ((2 * full4) & 31);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int row = full4 + k;
-              const int rr = row < rows_all ? row : rows_all - 1;
-              const float4 v = sm4[rr * kSweepThreads + tid];
-              const int i0 = row * kRowSamples + 2 * tid;
-              const float2 d0 = shifted(v.x, v.y), d1 = shifted(v.z, v.w);
-              float p0 = fmaf(h1f, d0.y, h0f * d0.x), p1 = fmaf(h1f, d1.y, h0f * d1.x);
-              if (i0 >= N) p0 = __int_as_float(0x7f800000);
-              if (i0 + 1 >= N) p1 = __int_as_float(0x7f800000);
-              classify_f32(p0, thr_above, thr_keep, d0.x, d0.y, ax, ay, cf, mk, bit);
-              classify_f32(p1, thr_above, thr_keep, d1.x, d1.y, ax, ay, cf, mk, bit + bit);
-              bit <<= 2;
-            }
-            const int wg = (2 * full4) >> 5;
+            const unsigned bit = 1u << ((2 * full_rows) & 31);
+            classify_f32(p0, thr_above, thr_keep, d0.x, d0.y, ax, ay, cf, mk, bit);
+            classify_f32(p1, thr_above, thr_keep, d1.x, d1.y, ax, ay, cf, mk, bit + bit);
+            const int wg = (2 * full_rows) >> 5;
 #pragma unroll
             for (int w2 = 0; w2 < kMaskWords; ++w2) mask[w2] |= (w2 == wg) ? mk : 0u;
           }
@@ -922,7 +921,27 @@ __global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipeli
           n_list = __shfl_sync(kFull, incl, 31);
           excl = incl - mine_n;
         }
-        if (n_list <= kWarpList) {
+        if (kF32 && n_list <= kWarpList) {
+          // fp32 samples: 32-bit shared-space addresses; bit P = 2 r + e of a word <-> byte (P >> 1) * kRowBytes + (P & 1) * 8
+          static_assert(!kF32 || kRowBytes == 4096u, "offset arithmetic of the fp32 compaction loop");
+          uint32_t dst_s = wlist_s + 8u * static_cast<uint32_t>(excl);
+#pragma unroll
+          for (int wd = 0; wd < kMaskWords; ++wd) {
+            if (wd * 32 < rows_all * kPerLoad) {
+              unsigned mm = mask[wd];
+              const uint32_t wb = tslot_s + 16u * kRowBytes * wd;
+              while (mm) {
+                const unsigned bp = 31u - static_cast<unsigned>(__clz(static_cast<int>(mm)));
+                mm ^= 1u << bp;
+                const uint32_t off = ((bp << 11) & 0xF000u) | ((bp << 3) & 8u);
+                DRCVAR_ASSERT(dst_s + 8u <= wlist_s + 8u * kWarpList && (wb - tslot_s + 16u * tid + off) + 8u <= slot_bytes);
+                smem_copy8(dst_s, wb + off);
+                dst_s += 8u;
+              }
+            }
+          }
+          n_list_prev = n_list;
+        } else if (n_list <= kWarpList) {
           V2* dst = wlist + excl;
           const unsigned char* tbase = smem_raw + 16u * tid;
 #pragma unroll
