@@ -13,6 +13,9 @@
 //     flag set (`redo_list[b] = 1`) and the follow-up launch of the streaming kernel computes it (the mechanism of the
 //     cluster kernel).  Launches that disable the window, want tail indices, generate samples or use strided views stay
 //     on halfspace_kernel.
+// fp32 samples, default instantiation <float, 8, true>: sweep B projects and sums the RAW coordinates (thresholds moved into that
+// space with a rigorous rounding bound; coordinates too large for raw fp32 sums -> redo pass); <float, 8, false> keeps the
+// coordinates relative to the first sample (DRCVAR_FLAG_LARGE_COORDS).  Same h, T and tail set either way.
 // Learned window (non-Gaussian samples): the finisher keeps ONE chain of states per CTA, state(i) after its i-th
 // halfspace, in a ring of four; the director places window(i) with state(i-3) after waiting for finisher(i-3): a fixed
 // lag, hence deterministic.  A miss moves the centre two half-widths towards the side the threshold is on (known from the
@@ -55,6 +58,8 @@ __device__ __forceinline__ void smem_copy8(uint32_t dst, uint32_t src) {
   asm volatile("{\n\t.reg .b64 t;\n\tld.shared.b64 t, [%1];\n\tst.shared.b64 [%0], t;\n\t}" ::"r"(dst), "r"(src) : "memory");
 }
 
+// Sweep warps per CTA: 8 (two CTAs per SM: fp32 samples) or 16 (fp64 samples: the 160 KB slot allows ONE CTA per SM, so the
+// CTA itself brings the warps that hide the sweeps' latency; per-warp list capacities halve with the per-warp share).
 template <int W> struct PCaps {
   static constexpr int kWarpCand = W == 8 ? drcvar::kWarpCand : 80;   // doubles per sweep warp in the candidate buffer ...
   static constexpr int kCandCap = W == 8 ? drcvar::kCandCap : 48;     // ... of which candidate losses (the rest: per-lane sums)
