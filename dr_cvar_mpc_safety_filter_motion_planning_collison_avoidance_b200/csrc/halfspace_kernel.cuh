@@ -336,6 +336,13 @@ __device__ __forceinline__ double value_of(unsigned long long k) {
   unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
   return __longlong_as_double(static_cast<long long>(u));
 }
+// explicit shared-space copies for the compaction loop of phase 2a (no generic -> shared conversion, no pointer pairs)
+__device__ __forceinline__ void smem_copy8(uint32_t dst, uint32_t src) {
+  asm volatile("{\n\t.reg .b64 t;\n\tld.shared.b64 t, [%1];\n\tst.shared.b64 [%0], t;\n\t}" ::"r"(dst), "r"(src) : "memory");
+}
+__device__ __forceinline__ void smem_copy16(uint32_t dst, uint32_t src) {
+  asm volatile("{\n\t.reg .b64 t, u;\n\tld.shared.v2.b64 {t, u}, [%1];\n\tst.shared.v2.b64 [%0], {t, u};\n\t}" ::"r"(dst), "r"(src) : "memory");
+}
 // canonical loss  L = 0 - (rn(h0*x) + rn(h1*y))   (never fused)
 __device__ __forceinline__ double loss_of(double h0, double h1, double x, double y) {
   return __dsub_rn(0.0, __dadd_rn(__dmul_rn(h0, x), __dmul_rn(h1, y)));
@@ -874,6 +881,7 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
   const int full_rows = N / kRowSamples;                 // rows of 16-byte loads fully inside the data
   const int rows_all = (N + kRowSamples - 1) / kRowSamples;
   V2* wlist = list_base + warp * kWarpList;
+  const uint32_t wlist_s = smem_u32(wlist), tslot_s = smem_u32(smem_raw) + 16u * static_cast<uint32_t>(tid);   // shared-space addresses (phase 2a)
   const double inv_n = 1.0 / static_cast<double>(N);
   double inv_sub = inv_n;   // 1 / (#samples in the second moments): all samples (fp32) / every 4th row (fp64)
   if (!kF32) {
@@ -1287,11 +1295,10 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
         const float4* sm4 = reinterpret_cast<const float4*>(smem_raw);
         const float h0f = ctl->h0f, h1f = ctl->h1f, thr_keep = ctl->thr_keep, thr_above = ctl->thr_above;
         const float2 nf = make_float2(-first.x, -first.y);
-        const int full4 = full_rows & ~3;   // rows in complete groups of 4 that need no masking
 #pragma unroll
-        for (int wd = 0; wd < kMaskWords; ++wd) {
+        for (int wd = 0; wd < kMaskWords; ++wd) {   // all complete rows (groups of four, then the one to three left over)
           const int r_lo = wd * kRowsPerWord;
-          const int r_hi = full4 < r_lo + kRowsPerWord ? full4 : r_lo + kRowsPerWord;
+          const int r_hi = full_rows < r_lo + kRowsPerWord ? full_rows : r_lo + kRowsPerWord;
           unsigned bit = 1u;
 #pragma unroll 4   // (8 rows per iteration issue no better and cost 1.3 KB of instruction-cache footprint)
           for (int r = r_lo; r < r_hi; ++r) {
@@ -1303,26 +1310,20 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
             bit <<= 2;
           }
         }
-        if (full4 < rows_all) {
-          // last group (1-4 rows, the last one possibly ragged): four loads in flight like every other group; samples
-          // beyond N get p = +inf (neither "above" nor kept); rows beyond the data re-read the last row (masked anyway)
+        if (full_rows < rows_all) {
+          // the ragged last row: samples beyond N get p = +inf (neither "above" nor kept).  (Pushing every row after the last
+          // complete group of four through this masked code cost the pipelined kernel 2.7 %.)
+          const float4 v = sm4[full_rows * kSweepThreads + tid];
+          const int i0 = full_rows * kRowSamples + 2 * tid;
+          const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nf), d1 = __fadd2_rn(make_float2(v.z, v.w), nf);
+          float p0 = fmaf(h1f, d0.y, h0f * d0.x), p1 = fmaf(h1f, d1.y, h0f * d1.x);
+          if (i0 >= N) p0 = __int_as_float(0x7f800000);
+          if (i0 + 1 >= N) p1 = __int_as_float(0x7f800000);
           unsigned mk = 0;
-          unsigned bit = 1u << ((2 * full4) & 31);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int row = full4 + k;
-            const int rr = row < rows_all ? row : rows_all - 1;
-            const float4 v = sm4[rr * kSweepThreads + tid];
-            const int i0 = row * kRowSamples + 2 * tid;
-            const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nf), d1 = __fadd2_rn(make_float2(v.z, v.w), nf);
-            float p0 = fmaf(h1f, d0.y, h0f * d0.x), p1 = fmaf(h1f, d1.y, h0f * d1.x);
-            if (i0 >= N) p0 = __int_as_float(0x7f800000);
-            if (i0 + 1 >= N) p1 = __int_as_float(0x7f800000);
-            classify_f32(p0, thr_above, thr_keep, d0.x, d0.y, ax, ay, cf, mk, bit);
-            classify_f32(p1, thr_above, thr_keep, d1.x, d1.y, ax, ay, cf, mk, bit + bit);
-            bit <<= 2;
-          }
-          const int wg = (2 * full4) >> 5;   // a group of 4 rows never straddles a mask word
+          const unsigned bit = 1u << ((2 * full_rows) & 31);
+          classify_f32(p0, thr_above, thr_keep, d0.x, d0.y, ax, ay, cf, mk, bit);
+          classify_f32(p1, thr_above, thr_keep, d1.x, d1.y, ax, ay, cf, mk, bit + bit);
+          const int wg = (2 * full_rows) >> 5;
 #pragma unroll
           for (int w2 = 0; w2 < kMaskWords; ++w2) mask[w2] |= (w2 == wg) ? mk : 0u;   // selects keep mask[] in registers
         }
@@ -1383,20 +1384,23 @@ __global__ void __launch_bounds__(kThreads, 2) halfspace_kernel(const KernelArgs
       }
       bool overflow = n_list > kWarpList;
       if (!overflow) {
-        V2* dst = wlist + excl;
-        // byte address of mask bit P = 32 wd + bp:  fp32: (P>>1) rows of 4 KB + 16 tid + 8 (P&1);  fp64: P rows + 16 tid
-        const unsigned char* tbase = smem_raw + 16u * tid;
+        // 32-bit shared-space addresses; byte address of mask bit P = 32 wd + bp:  fp32: (P>>1) rows of 4 KB + 16 tid + 8 (P&1);
+        // fp64: P rows + 16 tid
+        uint32_t dst_s = wlist_s + static_cast<uint32_t>(sizeof(V2)) * static_cast<uint32_t>(excl);
 #pragma unroll
         for (int wd = 0; wd < kMaskWords; ++wd) {
           if (wd * 32 < rows_all * kPerLoad) {
             unsigned mm = mask[wd];
-            const unsigned char* wbase = tbase + (kF32 ? 16u : 32u) * 4096u * wd;
+            const uint32_t wb = tslot_s + (kF32 ? 16u : 32u) * 4096u * wd;
             while (mm) {
               const unsigned bp = 31u - static_cast<unsigned>(__clz(static_cast<int>(mm)));   // highest set bit (one FLO)
               mm ^= 1u << bp;
-              const unsigned off = kF32 ? (((bp & 30u) << 11) | ((bp & 1u) << 3)) : (bp << 12);
-              DRCVAR_ASSERT(dst < wlist + kWarpList && (wbase + off) + sizeof(V2) <= smem_raw + slot_bytes);
-              *dst++ = *reinterpret_cast<const V2*>(wbase + off);
+              const uint32_t off = kF32 ? (((bp << 11) & 0xF000u) | ((bp << 3) & 8u)) : (bp << 12);
+              DRCVAR_ASSERT(dst_s + sizeof(V2) <= wlist_s + sizeof(V2) * kWarpList &&
+                            (wb - tslot_s + 16u * tid + off) + sizeof(V2) <= slot_bytes);
+              if constexpr (kF32) smem_copy8(dst_s, wb + off);
+              else smem_copy16(dst_s, wb + off);
+              dst_s += static_cast<uint32_t>(sizeof(V2));
             }
           }
         }

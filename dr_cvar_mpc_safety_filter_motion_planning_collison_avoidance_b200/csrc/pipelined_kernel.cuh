@@ -53,11 +53,6 @@ struct PBars {
 constexpr int kPBarCount = kSweepThreads + 32;   // every named barrier: the 8 sweep warps arrive, one helper warp waits
 constexpr int kPOverflowBit = 1 << 30;
 
-// explicit shared-space 8-byte copy for the compaction loop of phase 2a (no generic -> shared conversion, no pointer pairs)
-__device__ __forceinline__ void smem_copy8(uint32_t dst, uint32_t src) {
-  asm volatile("{\n\t.reg .b64 t;\n\tld.shared.b64 t, [%1];\n\tst.shared.b64 [%0], t;\n\t}" ::"r"(dst), "r"(src) : "memory");
-}
-
 // Sweep warps per CTA: 8 (two CTAs per SM: fp32 samples) or 16 (fp64 samples: the 160 KB slot allows ONE CTA per SM, so the
 // CTA itself brings the warps that hide the sweeps' latency; per-warp list capacities halve with the per-warp share).
 template <int W> struct PCaps {
