@@ -11,15 +11,31 @@ the samples are drawn from (nominal trajectory, covariance, a 64-bit Philox key 
 else that treats the object as an array (`np.asarray`, indexing, the reference's visualisation code) materialises it
 ONCE through the same kernel's sample dump — the values are the ones the fused path classifies, bit for bit (fp32).
 
-Parity with the reference's random STREAM is unpinned by construction (numpy's legacy MT19937 polar method consumes a
-data-dependent number of uniforms per normal): the distribution is the reference's, the
-stream is the one `oracle/sample_gen.py` specifies.  The nominal trajectory and the Laplace realization follow the
+Parity with the reference's random STREAM cannot be had from a counter-based generator (numpy's legacy MT19937 polar method
+consumes a data-dependent number of uniforms per normal): in the default (lazy) mode the
+distribution is the reference's and the stream is the one `oracle/sample_gen.py` specifies.  The SEEDED REFERENCE-STREAM
+mode (`DRCVAR_REFERENCE_STREAM=1` in the environment, or `obstacles.REFERENCE_STREAM = True`) is the parity mode: the sample
+trajectories are drawn on the host with the reference's numpy calls in the reference's order and returned as the dense
+float64 array the reference returns — bit-identical to `/root/reference/simulation/obstacles.py` under the same
+`np.random.seed` (tests/test_dropin_api.py checks the seed-42 `head_on` / `multi_obstacle` arrays of the golden files) —
+and take the stored-sample path through the kernel like any other numpy array.  The nominal trajectory and the Laplace realization follow the
 reference's arithmetic exactly (same recurrence / same numpy calls in the same order); the realization still differs
 from a reference run with the same seed because the sample generation no longer advances numpy's generator.
 """
+import os
+
 import numpy as np
 
 from dr_cvar_mpc_safety_filter_motion_planning_collison_avoidance_b200 import engine as _engine
+
+# seeded reference-stream mode (module docstring): None = follow the DRCVAR_REFERENCE_STREAM environment variable
+REFERENCE_STREAM = None
+
+
+def _reference_stream():
+    if REFERENCE_STREAM is not None:
+        return bool(REFERENCE_STREAM)
+    return os.environ.get("DRCVAR_REFERENCE_STREAM", "0") not in ("", "0")
 
 
 class GeneratedSampleTrajectories:
@@ -97,7 +113,18 @@ def generate_nominal_trajectory(start_pos, direction, speed, n_steps, dt):
 
 
 def generate_obstacle_sample_trajectories(nominal_trajectory, n_samples, noise_cov, dt):
-    """Sample trajectories [n_samples, n_steps+1, dim] around the nominal one (reference :43-77), as a lazy array."""
+    """Sample trajectories [n_samples, n_steps+1, dim] around the nominal one (reference :43-77), as a lazy array — or, in
+    the seeded reference-stream mode, as the dense array of the reference's own draws."""
+    if _reference_stream():
+        # one multivariate_normal call per time step t >= 1, n_samples rows each, zero mean: the reference's consumption of
+        # numpy's global generator (reference :65-75); step 0 is the nominal start for every sample
+        steps, dim = nominal_trajectory.shape
+        dense = np.empty((n_samples, steps, dim))
+        dense[:, 0, :] = nominal_trajectory[0, :]
+        zero = np.zeros(dim)
+        for t in range(1, steps):
+            dense[:, t, :] = nominal_trajectory[t, :] + np.random.multivariate_normal(mean=zero, cov=noise_cov, size=n_samples)
+        return dense
     key = int(np.random.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(np.random.randint(0, 2 ** 31 - 1))
     return GeneratedSampleTrajectories(nominal_trajectory, n_samples, noise_cov, key)
 

@@ -310,3 +310,33 @@ def test_obstacle_dropin_feeds_the_generate_mode(dropin):
         for i in range(2):
             assert abs(again["dr_cvar"][t][i].g_tilde - hs["dr_cvar"][t][i].g_tilde) <= 1e-6
             assert np.abs(again["dr_cvar"][t][i].h - hs["dr_cvar"][t][i].h).max() <= 1e-9   # fp64 mean vs shifted fp32 lane sums
+
+
+@pytest.mark.parametrize("name, cfg", [
+    ("head_on_seed42.npz", {"obstacle_start": np.array([4.0, 0.0]), "obstacle_direction": np.array([-1.0, 0.0])}),
+    ("multi_obstacle_seed42.npz", {"obstacles": [
+        {"start": np.array([0.0, 2.0]), "direction": np.array([0.0, -0.5]), "speed": 0.8},
+        {"start": np.array([-3.0, 0.5]), "direction": np.array([0.7, 0.0]), "speed": 0.6},
+        {"start": np.array([1.5, -2.0]), "direction": np.array([-0.2, 0.5]), "speed": 0.7}]}),
+])
+def test_reference_stream_mode_reproduces_the_reference_arrays(dropin, golden_dir, name, cfg):
+    """SURVEY §8-f2 'a seeded mode that reproduces host arrays for parity': with the reference-stream mode on, np.random.seed(42)
+    (main.py:191) + generate_obstacle_scenarios give the SAME float64 sample trajectories the reference's own
+    simulation/obstacles.py produced (tests/golden/make_golden.py stored their first HORIZON+1 steps), bit for bit; scenario
+    parameters: config/scenarios.py:21-28,50-65, config/parameters.py:17,25,26 (SIM_TIME 30 s, DT 0.2 s, 20 samples)."""
+    ob = dropin["simulation.obstacles"]
+    want = np.load(os.path.join(golden_dir, name))["sample_trajectories"]          # [n_obs, N, H+1, 2]
+    ob.REFERENCE_STREAM = True
+    try:
+        np.random.seed(42)
+        data = ob.generate_obstacle_scenarios(cfg, 30.0, 0.2, 20)
+    finally:
+        ob.REFERENCE_STREAM = None
+    got = data["sample_trajectories"]
+    assert len(got) == want.shape[0]
+    for k, tr in enumerate(got):
+        assert isinstance(tr, np.ndarray) and tr.dtype == np.float64 and tr.shape == (20, 151, 2)
+        assert np.array_equal(tr[:, : want.shape[2], :], want[k]), (name, k)
+    # and the default mode stays lazy
+    np.random.seed(42)
+    assert not isinstance(ob.generate_obstacle_scenarios(cfg, 30.0, 0.2, 20)["sample_trajectories"][0], np.ndarray)
