@@ -340,3 +340,30 @@ def test_reference_stream_mode_reproduces_the_reference_arrays(dropin, golden_di
     # and the default mode stays lazy
     np.random.seed(42)
     assert not isinstance(ob.generate_obstacle_scenarios(cfg, 30.0, 0.2, 20)["sample_trajectories"][0], np.ndarray)
+
+
+@pytest.mark.gpu
+def test_reference_stream_mode_end_to_end(dropin, golden_dir):
+    """main.py's flow with the seeded reference-stream mode: np.random.seed(42) -> generate_obstacle_scenarios ->
+    compute_safe_halfspaces_for_trajectory (main.py:61,95) gives the halfspaces the unmodified reference produced from ITS
+    draws of the same seed (tests/golden/multi_obstacle_seed42.npz)."""
+    z = np.load(os.path.join(golden_dir, "multi_obstacle_seed42.npz"))
+    alpha, delta, eps, rr, ro, horizon = (float(v) for v in z["params"])
+    ob, env_mod = dropin["simulation.obstacles"], dropin["simulation.environment"]
+    cfg = {"obstacles": [{"start": np.array([0.0, 2.0]), "direction": np.array([0.0, -0.5]), "speed": 0.8},
+                         {"start": np.array([-3.0, 0.5]), "direction": np.array([0.7, 0.0]), "speed": 0.6},
+                         {"start": np.array([1.5, -2.0]), "direction": np.array([-0.2, 0.5]), "speed": 0.7}]}
+    ob.REFERENCE_STREAM = True
+    try:
+        np.random.seed(42)
+        data = ob.generate_obstacle_scenarios(cfg, 30.0, 0.2, 20)
+    finally:
+        ob.REFERENCE_STREAM = None
+    env = env_mod.SafetyFilteringEnvironment(rr, ro, int(horizon), 0.2, alpha, delta, eps)
+    hs = env.compute_safe_halfspaces_for_trajectory(data["sample_trajectories"], z["x_ref"])
+    n_steps, n_obs = z["g_mean"].shape
+    for metric in ("mean", "cvar", "dr_cvar"):
+        for t in range(n_steps):
+            for i in range(n_obs):
+                h, g = hs[metric][t][i].get_constraint_params()
+                assert np.abs(h - z[f"h_{metric}"][t, i]).max() < 1e-12 and abs(g - z[f"g_{metric}"][t, i]) < 1e-9
