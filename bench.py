@@ -265,7 +265,7 @@ def kernel_source_hash():
 def measured_traffic(n, dtype, halfspaces):
     """DRAM bytes per launch from the committed ncu capture of THIS kernel build (profiles/traffic*.json), else None."""
     stamp = kernel_source_hash()
-    for tname in ("traffic.json", "traffic_n100k.json"):
+    for tname in ("traffic.json", "traffic_f64.json", "traffic_n100k.json"):
         tpath = os.path.join(ROOT, "profiles", tname)
         if not os.path.exists(tpath):
             continue
@@ -677,7 +677,8 @@ def run_ours(a):
                           "dtype": "f64-in/f64-acc",
                           "roofline": {"bound": "hbm", "achieved": gbs64, "peak": peak, "unit": "GB/s", "frac": gbs64 / peak,
                                        "kernel": "halfspace_kernel<double>", "algorithmic_bytes_per_launch": bytes64,
-                                       "traffic": None},
+                                       "traffic": measured_traffic(N, "f64", B64)[0],
+                                       "traffic_source": measured_traffic(N, "f64", B64)[1]},
                           "e2e": e2e64, "parity_spot_check": par64,
                           "note": ("the full config-4 batch in fp64" if scn64 == a.scenarios else
                                    f"largest resident fp64 batch ({scn64} of {a.scenarios} scenarios)") +
