@@ -112,3 +112,13 @@ def test_no_cpu_fallback_without_a_gpu():
     for path in glob.glob(os.path.join(pkg_dir, "**", "*.py"), recursive=True):
         src = open(path).read()
         assert "import oracle" not in src and "from oracle" not in src, path
+
+
+def test_flag_and_status_constants_match_the_header(lib):
+    """_lib.py mirrors the DRCVAR_FLAG_* / status bits of include/drcvar.h by value (the ctypes stub of INTEGRATION.md)."""
+    src = open(os.path.join(ROOT, "include", "drcvar.h")).read()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+DRCVAR_FLAG_([A-Z_]+)\s+(\d+)u", src)}
+    assert len(flags) >= 8 and "LARGE_COORDS" in flags
+    for name, value in flags.items():
+        assert getattr(lib, "FLAG_" + name) == value, name
+    assert len(set(flags.values())) == len(flags) and all(v & (v - 1) == 0 for v in flags.values())   # distinct single bits
