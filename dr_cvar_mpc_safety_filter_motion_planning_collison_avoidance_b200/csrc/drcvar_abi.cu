@@ -377,6 +377,18 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
         KernelArgs ra = a;   // the streaming kernel places its own windows (and learns them after two misses in a row)
         ra.redo_list = redo;
         ra.bulk = 1;
+        {
+          // most hand-backs are statistical misses of the planned window: the second attempt takes twice the width, so that it
+          // finds the threshold among its candidates instead of falling through to the multi-pass general select
+          // (config 4: 55 -> 31 us per redo pass; speed only, the threshold is exact either way)
+          const double mid = 0.5 * (ra.z_lo + ra.z_hi), half = ra.z_hi - ra.z_lo;
+          ra.z_lo = mid - half;
+          ra.z_hi = mid + half;
+          ra.z_mid_f = static_cast<float>(mid);
+          ra.z_half_f = static_cast<float>(half);
+          ra.z_lo_f = ra.z_mid_f - ra.z_half_f;
+          ra.z_hi_f = ra.z_mid_f + ra.z_half_f;
+        }
         const long long rgrid = std::min<long long>(c.B, di->sms);
         streaming_kernel<T, false><<<static_cast<unsigned>(rgrid), kStreamThreads, 0, stream>>>(ra);
         e = cudaGetLastError();
