@@ -355,9 +355,9 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
     static const int env_f64 = getenv("DRCVAR_PIPELINE_F64") ? atoi(getenv("DRCVAR_PIPELINE_F64")) : DRCVAR_PIPELINE_F64_DEFAULT;
     const long long per_load = 16 / (2 * sizeof(T));
     // returns DRCVAR_OK after launching, a negative error, or 1 when the path does not apply (fall through)
-    auto run_pipelined = [&](auto pk, int threads, size_t psmem, long long row_samples, const KernelArgs& base) -> int {
+    auto run_pipelined = [&](auto pk, int threads, size_t psmem, long long row_samples, const KernelArgs& base, int words = kMaskWords) -> int {
       const long long rows_all = (c.N + row_samples - 1) / row_samples;
-      if (rows_all * per_load > 32 * kMaskWords || psmem > static_cast<size_t>(di->max_smem_optin)) return 1;
+      if (rows_all * per_load > 32 * words || psmem > static_cast<size_t>(di->max_smem_optin)) return 1;
       CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem)));
       int p_per_sm = 0;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p_per_sm, pk, threads, psmem));
@@ -409,10 +409,14 @@ int launch_on_device(const Call& c, int device, cudaStream_t stream) {
         // halfspaces too large for raw fp32 sums are handed to the redo pass, so the flag only ever changes the speed
         static const bool env_large = getenv("DRCVAR_LARGE_COORDS") != nullptr;
         const bool large = (c.flags & DRCVAR_FLAG_LARGE_COORDS) || env_large;
+        // N <= 16 384 (64 samples per thread): the raw instantiation with two mask words per thread (less code between the hot loops)
+        const bool two_words = !large && ((c.N + 511) / 512) * 2 <= 64;
         const int r = large ? run_pipelined(pipelined_kernel<float, 8, false>, pipelined_threads<8>(),
                                             slot_bytes_for(c.N, 4) + pipelined_fixed_smem_bytes<8>(4), 512, a)
-                            : run_pipelined(pipelined_kernel<float, 8, true>, pipelined_threads<8>(),
-                                            slot_bytes_for(c.N, 4) + pipelined_fixed_smem_bytes<8>(4), 512, a);
+                      : two_words ? run_pipelined(pipelined_kernel<float, 8, true, 2>, pipelined_threads<8>(),
+                                                  slot_bytes_for(c.N, 4) + pipelined_fixed_smem_bytes<8>(4), 512, a, 2)
+                                  : run_pipelined(pipelined_kernel<float, 8, true>, pipelined_threads<8>(),
+                                                  slot_bytes_for(c.N, 4) + pipelined_fixed_smem_bytes<8>(4), 512, a);
         if (r <= 0) return r;
       }
     } else {

@@ -78,10 +78,14 @@ template <int W> __host__ __device__ constexpr int pipelined_threads() { return 
 // (one FADD2 less per sample).  Raw fp32 partial sums are only as good as the coordinates are small, so a halfspace whose
 // coordinates are too large for them (see `raw_ok` in the window placement) is handed to the redo pass; callers whose frames
 // are far from the origin select the shifted instantiation (DRCVAR_FLAG_LARGE_COORDS), which has no such limit.
-template <typename T, int W = 8, bool kRawB = false>
+// kWords: mask words per thread the instantiation carries (drcvar::kMaskWords = 4 covers every size; 2 covers 64 samples per thread,
+// i.e. N <= 16 384 fp32 samples, and leaves the unrolled sweep-B / phase-2a copies of words 2 and 3 out of the instruction stream).
+template <typename T, int W = 8, bool kRawB = false, int kWords = drcvar::kMaskWords>
 __global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipelined_kernel(const KernelArgs a) {
   using V2 = typename Vec2<T>::type;
   constexpr bool kF32 = sizeof(T) == 4;
+  constexpr int kMaskWords = kWords;   // (shadows the namespace-level constant)
+  static_assert(kWords >= 1 && kWords <= drcvar::kMaskWords, "mask words per thread");
   static_assert(!kRawB || kF32, "raw-coordinate sweep B: fp32 samples");
   static_assert(W == 8 || (W == 16 && !kF32), "16 sweep warps: fp64 samples (one thread per slot of the 512-wide canonical tree)");
   // the names of halfspace_kernel.cuh, for THIS instantiation's team size (they shadow the namespace-level constants)
@@ -830,7 +834,9 @@ __global__ void __launch_bounds__(pipelined_threads<W>(), W == 8 ? 2 : 1) pipeli
       c_gt_prev = 0;
       s_gt_prev = 0.0;
       if (win->hand.window_ok) {
-        unsigned mask[kMaskWords] = {0u, 0u, 0u, 0u};
+        unsigned mask[kMaskWords];
+#pragma unroll
+        for (int w2 = 0; w2 < kMaskWords; ++w2) mask[w2] = 0u;
         float ax = 0.f, ay = 0.f, cf = 0.f;
         int c_gt = 0;
         double s_gt = 0.0;
